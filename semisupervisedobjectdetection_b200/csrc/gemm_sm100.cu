@@ -1,0 +1,396 @@
+// tcgen05 / TMA / TMEM GEMM for sm_100a:   D[M,N] = alpha * (A · B^T) (+ bias) (* row_scale) (+ residual)
+//
+// One persistent CTA per SM, 6 warps:
+//   warp 0      : TMA producer   (cp.async.bulk.tensor -> 128B-swizzled smem ring, mbarrier complete_tx)
+//   warp 1      : MMA issuer     (one elected lane issues tcgen05.mma, accumulators in TMEM, double buffered)
+//   warps 2..5  : epilogue       (tcgen05.ld -> registers -> bias / drop-path scale / residual -> global)
+//
+// Operand layouts ("major-ness") are runtime options so that the same kernel serves
+//   forward  Linear      : A = X  [M,K] K-major,           B = W  [N,K] K-major
+//   dgrad                : A = dY [M,N'] K-major,          B = W  [N',K'] used as [K'(n), N'(k)]  MN-major
+//   wgrad (split-K)      : A = dY^T (stored [tokens,N'])   MN-major, B = X^T (stored [tokens,K']) MN-major
+// which removes every explicit transpose from the backward pass.
+//
+// Reference semantics served by this kernel: nn.Linear / 1x1 Conv2d / k==stride Conv2d call sites in
+// segformer_source/models/segformer/modeling_segformer.py:163-165,171-173,236,301,307,713,738 (forward) and their
+// autograd-derived gradients.
+#include "common.cuh"
+#include "sfk_internal.h"
+
+namespace sfk {
+
+static constexpr int BLOCK_M = 128;
+static constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
+static constexpr int UMMA_K = 16;
+static constexpr int MAX_BLOCK_N = 256;
+static constexpr int TMEM_COLS = 512;  // 2 accumulator buffers x 256 fp32 columns
+static constexpr int GEMM_THREADS = 192;
+static constexpr int MAX_STAGES = 8;
+
+struct GemmKernelParams {
+  int M, N, K;
+  int block_n;
+  int a_mn, b_mn;
+  int splits;
+  int k_blocks;  // ceil(K / BLOCK_K)
+  int m_tiles, n_tiles;
+  int stages;
+  uint32_t stage_bytes;  // A + B bytes per stage
+  // epilogue
+  float alpha;
+  const float* bias;
+  const float* residual;
+  long long ldr;
+  const float* row_scale;
+  int rows_per_scale;
+  void* out;
+  long long ldo;
+  int out_bf16;
+  int atomic_add;
+  int relu;
+};
+
+__device__ __forceinline__ void red_add_f32(float* addr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmKernelParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-B alignment is required by SWIZZLE_128B atoms; dynamic smem base is only 16-B aligned by contract.
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const uint32_t a_bytes = BLOCK_M * BLOCK_K * 2;
+  const uint32_t bars_off = p.stages * p.stage_bytes;
+  // barrier block: full[S], empty[S], tmem_full[2], tmem_empty[2], tmem_ptr
+  const uint32_t bar_full = smem_base + bars_off;
+  const uint32_t bar_empty = bar_full + 8 * MAX_STAGES;
+  const uint32_t bar_tfull = bar_empty + 8 * MAX_STAGES;
+  const uint32_t bar_tempty = bar_tfull + 16;
+  const uint32_t tmem_slot = bar_tempty + 16;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + bars_off + 16 * MAX_STAGES + 32);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  const int tiles_mn = p.m_tiles * p.n_tiles;
+  const int total_units = tiles_mn * p.splits;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const int split = unit % p.splits;
+        const int tile = unit / p.splits;
+        const int n_blk = tile % p.n_tiles;
+        const int m_blk = tile / p.n_tiles;
+        const int kb0 = (int)(((long long)split * p.k_blocks) / p.splits);
+        const int kb1 = (int)(((long long)(split + 1) * p.k_blocks) / p.splits);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t sa = smem_base + stage * p.stage_bytes;
+          const uint32_t sb = sa + a_bytes;
+          const uint32_t full = bar_full + 8 * stage;
+          mbar_arrive_expect_tx(full, p.stage_bytes);
+          if (!p.a_mn) {
+            tma_load_2d(sa, &tmap_a, full, kb * BLOCK_K, m_blk * BLOCK_M);
+          } else {
+            // stored [K, M] (M contiguous): 2 boxes of [64 m, 64 k]
+            tma_load_2d(sa, &tmap_a, full, m_blk * BLOCK_M, kb * BLOCK_K);
+            tma_load_2d(sa + 8192, &tmap_a, full, m_blk * BLOCK_M + 64, kb * BLOCK_K);
+          }
+          if (!p.b_mn) {
+            tma_load_2d(sb, &tmap_b, full, kb * BLOCK_K, n_blk * p.block_n);
+          } else {
+            for (int j = 0; j < p.block_n / 64; ++j)
+              tma_load_2d(sb + j * 8192, &tmap_b, full, n_blk * p.block_n + j * 64, kb * BLOCK_K);
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = umma_idesc_bf16(BLOCK_M, p.block_n, p.a_mn, p.b_mn);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase[2] = {0, 0};
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      const int split = unit % p.splits;
+      const int kb0 = (int)(((long long)split * p.k_blocks) / p.splits);
+      const int kb1 = (int)(((long long)(split + 1) * p.k_blocks) / p.splits);
+      // wait for the epilogue to have drained this accumulator buffer
+      mbar_wait(bar_tempty + 8 * acc, acc_phase[acc] ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * MAX_BLOCK_N;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(bar_full + 8 * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_base + stage * p.stage_bytes;
+          const uint32_t sb = sa + a_bytes;
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            const uint64_t adesc = p.a_mn ? umma_smem_desc(sa + kk * 2048, 8192, 1024)
+                                          : umma_smem_desc(sa + kk * 32, 16, 1024);
+            const uint64_t bdesc = p.b_mn ? umma_smem_desc(sb + kk * 2048, 8192, 1024)
+                                          : umma_smem_desc(sb + kk * 32, 16, 1024);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * stage);                  // smem slot reusable once these MMAs retire
+          if (kb == kb1 - 1) umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      acc_phase[acc] ^= 1;
+      acc ^= 1;
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase[2] = {0, 0};
+    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      const int tile = unit / p.splits;
+      const int n_blk = tile % p.n_tiles;
+      const int m_blk = tile / p.n_tiles;
+      mbar_wait(bar_tfull + 8 * acc, acc_phase[acc]);
+      tc_fence_after();
+      const long long row = (long long)m_blk * BLOCK_M + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      float rscale = p.alpha;
+      if (p.row_scale != nullptr && row_ok) rscale *= p.row_scale[row / p.rows_per_scale];
+      const int n0 = n_blk * p.block_n;
+      for (int c = 0; c < p.block_n; c += 32) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * MAX_BLOCK_N + c, r);
+        tmem_ld_wait();
+        const int col0 = n0 + c;
+        if (!row_ok || col0 >= p.N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const bool full_chunk = (col0 + 32 <= p.N);
+        if (p.bias != nullptr) {
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= rscale;
+        if (p.residual != nullptr) {
+          const float* rp = p.residual + row * p.ldr + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+              v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += rp[j];
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.atomic_add) {
+          float* op = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) red_add_v4_f32(op + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) red_add_f32(op + j, v[j]);
+          }
+        } else if (p.out_bf16) {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 o;
+              o.x = pack_bf16x2(v[j], v[j + 1]);
+              o.y = pack_bf16x2(v[j + 2], v[j + 3]);
+              o.z = pack_bf16x2(v[j + 4], v[j + 5]);
+              o.w = pack_bf16x2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(op + j) = o;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) op[j] = __float2bfloat16(v[j]);
+          }
+        } else {
+          float* op = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
+          if (full_chunk) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) op[j] = v[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      acc_phase[acc] ^= 1;
+      acc ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+static int pick_block_n(int N, int b_mn, int M) {
+  // candidates must be multiples of 32 (epilogue chunk) and of 64 when B is MN-major (64-wide TMA boxes)
+  const int cands_k[] = {256, 224, 192, 160, 128, 96, 64, 32};
+  const int cands_mn[] = {256, 192, 128, 64};
+  const int* cands = b_mn ? cands_mn : cands_k;
+  const int nc = b_mn ? 4 : 8;
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const int sms = num_sms();
+  int best = cands[nc - 1];
+  double best_cost = 1e30;
+  for (int i = 0; i < nc; ++i) {
+    const int bn = cands[i];
+    const int n_tiles = (N + bn - 1) / bn;
+    const long long tiles = (long long)m_tiles * n_tiles;
+    const long long waves = (tiles + sms - 1) / sms;
+    // cost ~ waves * (MMA time of a tile ~ bn) with a fixed per-tile overhead (~48 columns worth)
+    const double cost = (double)waves * (bn + 48);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
+  SFK_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  SFK_REQUIRE(g.a != nullptr && g.b != nullptr && g.out != nullptr, "gemm: null pointer");
+  SFK_REQUIRE((reinterpret_cast<uintptr_t>(g.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.b) & 15) == 0,
+              "gemm: operands must be 16-byte aligned");
+  SFK_REQUIRE((g.lda % 8) == 0 && (g.ldb % 8) == 0, "gemm: lda/ldb must be multiples of 8 elements (lda=%lld ldb=%lld)",
+              g.lda, g.ldb);
+  const int esz = g.out_bf16 ? 2 : 4;
+  SFK_REQUIRE((reinterpret_cast<uintptr_t>(g.out) & 15) == 0 && ((g.ldo * esz) % 16) == 0,
+              "gemm: output must be 16-byte aligned with a 16-byte multiple row pitch");
+  SFK_REQUIRE(!(g.atomic_add && g.out_bf16), "gemm: atomic accumulation needs an fp32 output");
+  if (g.residual) SFK_REQUIRE((reinterpret_cast<uintptr_t>(g.residual) & 15) == 0 && (g.ldr % 4) == 0,
+                              "gemm: residual must be 16-byte aligned");
+  if (g.bias) SFK_REQUIRE((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
+
+  GemmKernelParams p;
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.a_mn = g.a_mn ? 1 : 0;
+  p.b_mn = g.b_mn ? 1 : 0;
+  p.block_n = g.block_n > 0 ? g.block_n : pick_block_n(g.N, p.b_mn, g.M);
+  SFK_REQUIRE(p.block_n % 32 == 0 && p.block_n >= 32 && p.block_n <= MAX_BLOCK_N, "gemm: bad block_n %d", p.block_n);
+  SFK_REQUIRE(!p.b_mn || p.block_n % 64 == 0, "gemm: MN-major B needs block_n %% 64 == 0");
+  p.k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
+  p.m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
+  p.n_tiles = (g.N + p.block_n - 1) / p.block_n;
+  int splits = g.splits;
+  if (splits <= 0) {
+    splits = 1;
+    if (g.atomic_add) {
+      const long long tiles = (long long)p.m_tiles * p.n_tiles;
+      const int sms = num_sms();
+      if (tiles < sms) splits = (int)((2LL * sms + tiles - 1) / tiles);
+      // keep at least 4 k-blocks per split so the pipeline has something to overlap
+      const int max_splits = p.k_blocks >= 4 ? p.k_blocks / 4 : 1;
+      if (splits > max_splits) splits = max_splits;
+    }
+  }
+  if (splits > p.k_blocks) splits = p.k_blocks;
+  if (splits < 1) splits = 1;
+  SFK_REQUIRE(splits == 1 || g.atomic_add, "gemm: split-K requires atomic accumulation");
+  p.splits = splits;
+  p.stage_bytes = BLOCK_M * BLOCK_K * 2 + p.block_n * BLOCK_K * 2;
+  const int smem_budget = 227 * 1024 - 2048;
+  int stages = smem_budget / (int)p.stage_bytes;
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  SFK_REQUIRE(stages >= 2, "gemm: not enough shared memory for 2 stages");
+  p.stages = stages;
+  p.alpha = g.alpha;
+  p.bias = g.bias;
+  p.residual = g.residual;
+  p.ldr = g.ldr;
+  p.row_scale = g.row_scale;
+  p.rows_per_scale = g.rows_per_scale > 0 ? g.rows_per_scale : 1;
+  p.out = g.out;
+  p.ldo = g.ldo;
+  p.out_bf16 = g.out_bf16;
+  p.atomic_add = g.atomic_add;
+  p.relu = g.relu;
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!p.a_mn) rc = make_tmap_2d_bf16(&ta, g.a, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda * 2, BLOCK_K, BLOCK_M);
+  else         rc = make_tmap_2d_bf16(&ta, g.a, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda * 2, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!p.b_mn) rc = make_tmap_2d_bf16(&tb, g.b, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb * 2, BLOCK_K, p.block_n);
+  else         rc = make_tmap_2d_bf16(&tb, g.b, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb * 2, 64, BLOCK_K);
+  if (rc) return rc;
+
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 16 * MAX_STAGES + 64 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    SFK_REQUIRE(e == cudaSuccess, "gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const long long units = (long long)p.m_tiles * p.n_tiles * p.splits;
+  int grid = (int)(units < num_sms() ? units : num_sms());
+  gemm_bf16_tcgen05_kernel<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);
+  return check_launch("gemm_bf16_tcgen05_kernel");
+}
+
+}  // namespace sfk
