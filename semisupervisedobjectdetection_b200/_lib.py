@@ -33,18 +33,53 @@ def load() -> ctypes.CDLL:
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
                 "There is no CPU / PyTorch fallback for this package."
             )
-        _lib = ctypes.CDLL(LIB_PATH)
-        _lib.sfk_last_error.restype = ctypes.c_char_p
-        _lib.sfk_version.restype = ctypes.c_int
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in header_prototypes().items():
+            fn = getattr(lib, name)  # AttributeError here == header/library mismatch: fail loudly
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
     return _lib
+
+
+_CTYPE = {
+    "int": ctypes.c_int,
+    "long long": ctypes.c_longlong,
+    "float": ctypes.c_float,
+    "double": ctypes.c_double,
+    "size_t": ctypes.c_size_t,
+    "sfk_stream_t": ctypes.c_void_p,
+}
+
+
+def _ctype_of(decl: str):
+    decl = decl.strip()
+    if "*" in decl:
+        return ctypes.c_void_p
+    base = re.sub(r"\b(const|unsigned)\b", "", decl)
+    base = re.sub(r"\b[a-zA-Z_][a-zA-Z0-9_]*$", "", base.strip()).strip() or decl  # drop the parameter name
+    if base not in _CTYPE:
+        raise SfkError(f"sfk.h: cannot map C type {decl!r}")
+    return _CTYPE[base]
+
+
+def header_prototypes() -> dict:
+    """Parse include/sfk.h into {name: (restype, [argtypes])} so that ctypes marshals 64-bit and float args exactly."""
+    with open(HEADER_PATH) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"(const char\*|int|size_t)\s+(sfk_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        restype = ctypes.c_char_p if "char" in ret else (ctypes.c_size_t if ret == "size_t" else ctypes.c_int)
+        argtypes = [] if args in ("", "void") else [_ctype_of(a) for a in args.split(",")]
+        protos[name] = (restype, argtypes)
+    return protos
 
 
 def declared_symbols() -> list[str]:
     """Every function name declared in include/sfk.h (used by the CPU-side ABI test)."""
-    with open(HEADER_PATH) as f:
-        text = f.read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(sfk_[a-z0-9_]+)\s*\(", text)))
+    return sorted(header_prototypes())
 
 
 def last_error() -> str:
@@ -65,14 +100,15 @@ def ensure_device() -> None:
         _device_checked = True
 
 
-def stream_ptr() -> ctypes.c_void_p:
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
 
 
-def ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device address of a tensor (None -> NULL)."""
     if t is None:
-        return ctypes.c_void_p(0)
-    return ctypes.c_void_p(t.data_ptr())
+        return None
+    return t.data_ptr()
 
 
 c_int = ctypes.c_int

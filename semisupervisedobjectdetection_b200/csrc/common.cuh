@@ -175,6 +175,16 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
 }
+// same with an explicit layout type (2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B)
+__device__ __forceinline__ uint64_t umma_smem_desc_lt(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(layout_type & 7u) << 61;
+  return d;
+}
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32
 __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t m, uint32_t n, uint32_t a_mn_major,
                                                              uint32_t b_mn_major) {
@@ -195,5 +205,9 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t m, uint32_
 // 2-D bf16 tensor, inner dimension contiguous. box_inner must be 64 (128 B) for SWIZZLE_128B.
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                       uint32_t box_inner, uint32_t box_outer);
+
+// 3-D bf16 tensor (d0 contiguous). box0 * 2 bytes must equal swizzle_bytes (64 or 128).
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                      uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2, int swizzle_bytes);
 
 }  // namespace sfk

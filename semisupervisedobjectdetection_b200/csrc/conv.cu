@@ -1,0 +1,451 @@
+// Channels-last (token-major) convolution helpers of the SegFormer path:
+//   * depthwise 3x3 (+bias) (+exact-erf GELU)                      MS:283-294, MS:310-313
+//   * its backward (recompute pre-activation, dpre, dW, db, dgrad)
+//   * patch gather ("im2col") for the overlapping patch-embed conv MS:123-131 and for the k==stride SR conv MS:171-173,
+//     and the matching scatter/gather for their input gradients.
+// All kernels move 64/128-bit vectors with the channel dimension innermost (fully coalesced).
+#include "common.cuh"
+#include "sfk_internal.h"
+
+namespace sfk {
+
+// ------------------------------------------------------------------------------------------------
+// depthwise 3x3, stride 1, pad 1.  x: bf16 [B,H,W,C].  wt: fp32 [9][C] (tap-major copy of weight[C,1,3,3]).
+// Each thread produces SEG consecutive outputs along W for VEC channels, loading a 3 x (SEG+2) window once.
+// ------------------------------------------------------------------------------------------------
+static constexpr int DW_SEG = 4;
+
+template <int VEC> struct VecIO;
+template <> struct VecIO<8> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* f) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* f) {
+    uint4 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+};
+template <> struct VecIO<4> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* f) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* f) {
+    uint2 u;
+    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+// mode 0: y = gelu(conv(x) + bias)     mode 1: y = conv_flipped(x)  (input gradient of the conv)
+template <int MODE>
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
+                                                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B,
+                                                        int H, int W, int C) {
+  constexpr int VEC = 8;
+  const int CG = C / VEC;
+  const int nseg = (W + DW_SEG - 1) / DW_SEG;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)B * H * nseg * CG;
+  if (idx >= total) return;
+  const int cg = (int)(idx % CG);
+  long long t = idx / CG;
+  const int seg = (int)(t % nseg);
+  t /= nseg;
+  const int yy = (int)(t % H);
+  const int b = (int)(t / H);
+  const int c0 = cg * VEC;
+  const int x0 = seg * DW_SEG;
+
+  float w[9][VEC];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const int kk = MODE == 1 ? 8 - k : k;
+    const float4 a = __ldg(reinterpret_cast<const float4*>(wt + (long long)kk * C + c0));
+    const float4 bq = __ldg(reinterpret_cast<const float4*>(wt + (long long)kk * C + c0 + 4));
+    w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
+    w[k][4] = bq.x; w[k][5] = bq.y; w[k][6] = bq.z; w[k][7] = bq.w;
+  }
+  float acc[DW_SEG][VEC];
+#pragma unroll
+  for (int o = 0; o < DW_SEG; ++o)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[o][v] = 0.f;
+  if (MODE == 0) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c0));
+    const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+#pragma unroll
+    for (int o = 0; o < DW_SEG; ++o) {
+      acc[o][0] = a.x; acc[o][1] = a.y; acc[o][2] = a.z; acc[o][3] = a.w;
+      acc[o][4] = bq.x; acc[o][5] = bq.y; acc[o][6] = bq.z; acc[o][7] = bq.w;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int sy = yy + r - 1;
+    if (sy < 0 || sy >= H) continue;
+    const __nv_bfloat16* rowp = x + ((long long)(b * H + sy) * W) * C + c0;
+#pragma unroll
+    for (int j = 0; j < DW_SEG + 2; ++j) {
+      const int sx = x0 + j - 1;
+      if (sx < 0 || sx >= W) continue;
+      float f[VEC];
+      VecIO<VEC>::ld(rowp + (long long)sx * C, f);
+#pragma unroll
+      for (int tt = 0; tt < 3; ++tt) {
+        const int o = j - tt;  // output position that sees column j through tap tt
+        if (o >= 0 && o < DW_SEG) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[o][v] = fmaf(w[r * 3 + tt][v], f[v], acc[o][v]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < DW_SEG; ++o) {
+    if (x0 + o >= W) break;
+    if (MODE == 0) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) acc[o][v] = gelu_erf(acc[o][v]);
+    }
+    VecIO<VEC>::st(y + ((long long)(b * H + yy) * W + x0 + o) * C + c0, acc[o]);
+  }
+}
+
+int dwconv3x3(const void* x, const float* wt, const float* bias, void* y, int B, int H, int W, int C, int mode,
+              cudaStream_t stream) {
+  SFK_REQUIRE(C % 8 == 0, "dwconv3x3: C=%d must be a multiple of 8", C);
+  const long long total = (long long)B * H * ((W + DW_SEG - 1) / DW_SEG) * (C / 8);
+  if (total == 0) return 0;
+  const unsigned grid = (unsigned)((total + 255) / 256);
+  if (mode == 0)
+    dwconv3x3_kernel<0><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, wt, bias, (__nv_bfloat16*)y, B, H, W, C);
+  else
+    dwconv3x3_kernel<1><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, wt, nullptr, (__nv_bfloat16*)y, B, H, W, C);
+  return check_launch("dwconv3x3_kernel");
+}
+
+// Backward stage 1: recompute pre = conv(x)+bias, dpre = dg * gelu'(pre); accumulate dW[9][C] and db[C].
+// Each thread walks POS consecutive (b, y, seg) positions for VEC=4 channels and issues its atomics once.
+template <int DUMMY>
+__global__ void __launch_bounds__(256) dwconv3x3_gelu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
+                                                                 const float* __restrict__ bias,
+                                                                 const __nv_bfloat16* __restrict__ dg,
+                                                                 __nv_bfloat16* __restrict__ dpre, float* __restrict__ dwt,
+                                                                 float* __restrict__ dbias, int B, int H, int W, int C,
+                                                                 int pos_per_thread) {
+  constexpr int VEC = 4;
+  const int CG = C / VEC;
+  const int nseg = (W + DW_SEG - 1) / DW_SEG;
+  const long long npos = (long long)B * H * nseg;
+  const long long nchunks = (npos + pos_per_thread - 1) / pos_per_thread;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= nchunks * CG) return;
+  const int cg = (int)(idx % CG);
+  const long long chunk = idx / CG;
+  const int c0 = cg * VEC;
+  float w[9][VEC], dw[9][VEC], db[VEC], bs[VEC];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(wt + (long long)k * C + c0));
+    w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) dw[k][v] = 0.f;
+  }
+  {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c0));
+    bs[0] = a.x; bs[1] = a.y; bs[2] = a.z; bs[3] = a.w;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) db[v] = 0.f;
+  }
+  long long p1 = (chunk + 1) * pos_per_thread;
+  if (p1 > npos) p1 = npos;
+  for (long long pos = chunk * pos_per_thread; pos < p1; ++pos) {
+    const int seg = (int)(pos % nseg);
+    const long long t = pos / nseg;
+    const int yy = (int)(t % H);
+    const int b = (int)(t / H);
+    const int x0 = seg * DW_SEG;
+    float win[3][DW_SEG + 2][VEC];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int sy = yy + r - 1;
+      const bool vy = sy >= 0 && sy < H;
+#pragma unroll
+      for (int j = 0; j < DW_SEG + 2; ++j) {
+        const int sx = x0 + j - 1;
+        if (vy && sx >= 0 && sx < W) {
+          VecIO<VEC>::ld(x + ((long long)(b * H + sy) * W + sx) * C + c0, win[r][j]);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) win[r][j][v] = 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < DW_SEG; ++o) {
+      if (x0 + o >= W) break;
+      float pre[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) pre[v] = bs[v];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int tt = 0; tt < 3; ++tt)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) pre[v] = fmaf(w[r * 3 + tt][v], win[r][o + tt][v], pre[v]);
+      const long long off = ((long long)(b * H + yy) * W + x0 + o) * C + c0;
+      float g[VEC], d[VEC];
+      VecIO<VEC>::ld(dg + off, g);
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) {
+        d[v] = g[v] * gelu_erf_grad(pre[v]);
+        db[v] += d[v];
+      }
+      VecIO<VEC>::st(dpre + off, d);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int tt = 0; tt < 3; ++tt)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) dw[r * 3 + tt][v] = fmaf(d[v], win[r][o + tt][v], dw[r * 3 + tt][v]);
+    }
+  }
+  if (dwt != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) atomicAdd(dwt + (long long)k * C + c0 + v, dw[k][v]);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) atomicAdd(dbias + c0 + v, db[v]);
+  }
+}
+
+int dwconv3x3_gelu_bwd(const void* x, const float* wt, const float* bias, const void* dg, void* dpre, float* dwt,
+                       float* dbias, int B, int H, int W, int C, cudaStream_t stream) {
+  SFK_REQUIRE(C % 8 == 0, "dwconv3x3_gelu_bwd: C=%d must be a multiple of 8", C);
+  const int CG = C / 4;
+  const long long npos = (long long)B * H * ((W + DW_SEG - 1) / DW_SEG);
+  if (npos == 0) return 0;
+  // enough threads to fill the machine (~16 warps/SM), as few atomics as possible
+  long long want_threads = (long long)num_sms() * 2048;
+  long long chunks = want_threads / CG;
+  if (chunks < 1) chunks = 1;
+  int ppt = (int)((npos + chunks - 1) / chunks);
+  if (ppt < 1) ppt = 1;
+  chunks = (npos + ppt - 1) / ppt;
+  const long long total = chunks * CG;
+  dwconv3x3_gelu_bwd_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
+      (const __nv_bfloat16*)x, wt, bias, (const __nv_bfloat16*)dg, (__nv_bfloat16*)dpre, dwt, dbias, B, H, W, C, ppt);
+  return check_launch("dwconv3x3_gelu_bwd_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Patch gather for a KxK / stride S / pad P conv on a channels-last bf16 map:
+//   A[m, (ky*K+kx)*C + c] = x[b, oy*S+ky-P, ox*S+kx-P, c]  (0 outside), m = (b*Ho+oy)*Wo+ox
+// x rows may live inside a longer token sequence: token t of sample b is at row b*tok_stride + tok_offset + t.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) im2col_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ A,
+                                                          int B, int H, int W, int C, int K, int S, int P, int Ho, int Wo,
+                                                          long long tok_stride, long long tok_offset) {
+  const int C8 = C >> 3;
+  const long long total = (long long)B * Ho * Wo * K * K * C8;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % C8);
+  long long t = idx / C8;
+  const int tap = (int)(t % (K * K));
+  const long long m = t / (K * K);
+  const int ox = (int)(m % Wo);
+  const int oy = (int)((m / Wo) % Ho);
+  const long long b = m / ((long long)Wo * Ho);
+  const int ky = tap / K, kx = tap % K;
+  const int sy = oy * S + ky - P, sx = ox * S + kx - P;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (sy >= 0 && sy < H && sx >= 0 && sx < W)
+    v = *reinterpret_cast<const uint4*>(x + (b * tok_stride + tok_offset + (long long)sy * W + sx) * C + c8 * 8);
+  *reinterpret_cast<uint4*>(A + idx * 8) = v;
+}
+
+int im2col_nhwc(const void* x, void* A, int B, int H, int W, int C, int K, int S, int P, long long tok_stride,
+                long long tok_offset, cudaStream_t stream) {
+  SFK_REQUIRE(C % 8 == 0, "im2col_nhwc: C=%d must be a multiple of 8", C);
+  const int Ho = (H + 2 * P - K) / S + 1, Wo = (W + 2 * P - K) / S + 1;
+  const long long total = (long long)B * Ho * Wo * K * K * (C / 8);
+  if (total == 0) return 0;
+  im2col_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)A, B, H, W,
+                                                                          C, K, S, P, Ho, Wo, tok_stride, tok_offset);
+  return check_launch("im2col_nhwc_kernel");
+}
+
+// Stage-1 gather from the fp32 NCHW image: A[m, c*K*K + ky*K + kx] (OIHW-flatten order), K padded to Kp with zeros.
+__global__ void __launch_bounds__(256) im2col_nchw_f32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ A, int B,
+                                                              int Cin, int H, int W, int K, int S, int P, int Ho, int Wo,
+                                                              int Kp) {
+  const long long total = (long long)B * Ho * Wo * Kp;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int k = (int)(idx % Kp);
+  const long long m = idx / Kp;
+  float v = 0.f;
+  if (k < Cin * K * K) {
+    const int c = k / (K * K), r = k % (K * K);
+    const int ky = r / K, kx = r % K;
+    const int ox = (int)(m % Wo);
+    const int oy = (int)((m / Wo) % Ho);
+    const long long b = m / ((long long)Wo * Ho);
+    const int sy = oy * S + ky - P, sx = ox * S + kx - P;
+    if (sy >= 0 && sy < H && sx >= 0 && sx < W) v = x[((b * Cin + c) * H + sy) * W + sx];
+  }
+  A[idx] = __float2bfloat16(v);
+}
+
+int im2col_nchw_f32(const float* x, void* A, int B, int Cin, int H, int W, int K, int S, int P, int Kp,
+                    cudaStream_t stream) {
+  const int Ho = (H + 2 * P - K) / S + 1, Wo = (W + 2 * P - K) / S + 1;
+  const long long total = (long long)B * Ho * Wo * Kp;
+  if (total == 0) return 0;
+  im2col_nchw_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, (__nv_bfloat16*)A, B, Cin, H, W, K, S, P, Ho,
+                                                                              Wo, Kp);
+  return check_launch("im2col_nchw_f32_kernel");
+}
+
+// Input gradient of the patch conv: dx[b, y, x, c] (+)= sum over taps of dA[m(b,oy,ox), tap*C + c].
+// Gather formulation (no atomics): every input pixel visits the <= ceil(K/S)^2 patches that contain it.
+__global__ void __launch_bounds__(256) col2im_nhwc_kernel(const __nv_bfloat16* __restrict__ dA, float* __restrict__ dx, int B,
+                                                          int H, int W, int C, int K, int S, int P, int Ho, int Wo,
+                                                          long long tok_stride, long long tok_offset, int accumulate) {
+  const int C4 = C >> 2;
+  const long long total = (long long)B * H * W * C4;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int c4 = (int)(idx % C4);
+  long long t = idx / C4;
+  const int sx = (int)(t % W);
+  const int sy = (int)((t / W) % H);
+  const long long b = t / ((long long)W * H);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int ky = (sy + P) % S; ky < K; ky += S) {
+    const int oy = (sy + P - ky) / S;
+    if (sy + P - ky < 0 || oy >= Ho) continue;
+    for (int kx = (sx + P) % S; kx < K; kx += S) {
+      const int ox = (sx + P - kx) / S;
+      if (sx + P - kx < 0 || ox >= Wo) continue;
+      const long long m = (b * Ho + oy) * Wo + ox;
+      const uint2 u = *reinterpret_cast<const uint2*>(dA + (m * K * K + ky * K + kx) * C + c4 * 4);
+      const float2 a = unpack_bf16x2(u.x), bq = unpack_bf16x2(u.y);
+      acc.x += a.x; acc.y += a.y; acc.z += bq.x; acc.w += bq.y;
+    }
+  }
+  float* dst = dx + (b * tok_stride + tok_offset + (long long)sy * W + sx) * C + c4 * 4;
+  if (accumulate) {
+    const float4 o = *reinterpret_cast<const float4*>(dst);
+    acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+  }
+  *reinterpret_cast<float4*>(dst) = acc;
+}
+
+int col2im_nhwc(const void* dA, float* dx, int B, int H, int W, int C, int K, int S, int P, long long tok_stride,
+                long long tok_offset, int accumulate, cudaStream_t stream) {
+  SFK_REQUIRE(C % 4 == 0, "col2im_nhwc: C=%d must be a multiple of 4", C);
+  const int Ho = (H + 2 * P - K) / S + 1, Wo = (W + 2 * P - K) / S + 1;
+  const long long total = (long long)B * H * W * (C / 4);
+  if (total == 0) return 0;
+  col2im_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)dA, dx, B, H, W, C, K, S, P, Ho,
+                                                                          Wo, tok_stride, tok_offset, accumulate);
+  return check_launch("col2im_nhwc_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight re-layouts for the bf16 shadow copies (run once per optimiser step)
+// ------------------------------------------------------------------------------------------------
+// OIHW fp32 -> [O, (ky,kx,c)] bf16 (channels-last patch order), row pitch ldo
+__global__ void conv_weight_ohwi_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int O, int I, int KH,
+                                        int KW, long long ldo) {
+  const long long total = (long long)O * I * KH * KW;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % I);
+  long long t = idx / I;
+  const int kx = (int)(t % KW);
+  t /= KW;
+  const int ky = (int)(t % KH);
+  const long long o = t / KH;
+  out[o * ldo + ((long long)ky * KW + kx) * I + c] = __float2bfloat16(w[((o * I + c) * KH + ky) * KW + kx]);
+}
+
+int conv_weight_ohwi(const float* w, void* out, int O, int I, int KH, int KW, long long ldo, cudaStream_t stream) {
+  const long long total = (long long)O * I * KH * KW;
+  if (total == 0) return 0;
+  conv_weight_ohwi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(w, (__nv_bfloat16*)out, O, I, KH, KW, ldo);
+  return check_launch("conv_weight_ohwi_kernel");
+}
+
+// inverse for gradients: dW_oihw[o,c,ky,kx] += g[o, (ky,kx,c)] (fp32 -> fp32)
+__global__ void conv_wgrad_ohwi_to_oihw_kernel(const float* __restrict__ g, float* __restrict__ dw, int O, int I, int KH, int KW,
+                                               long long ldg) {
+  const long long total = (long long)O * I * KH * KW;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int kx = (int)(idx % KW);
+  long long t = idx / KW;
+  const int ky = (int)(t % KH);
+  t /= KH;
+  const int c = (int)(t % I);
+  const long long o = t / I;
+  dw[idx] += g[o * ldg + ((long long)ky * KW + kx) * I + c];
+}
+
+int conv_wgrad_ohwi_to_oihw(const float* g, float* dw, int O, int I, int KH, int KW, long long ldg, cudaStream_t stream) {
+  const long long total = (long long)O * I * KH * KW;
+  if (total == 0) return 0;
+  conv_wgrad_ohwi_to_oihw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(g, dw, O, I, KH, KW, ldg);
+  return check_launch("conv_wgrad_ohwi_to_oihw_kernel");
+}
+
+// generic 2-D strided transpose-free copy fp32 -> bf16 with row pitches (for weight shadows incl. K padding)
+__global__ void cast_2d_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst, long long ldd,
+                               long long rows, int cols, int cols_padded) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= rows * cols_padded) return;
+  const int c = (int)(idx % cols_padded);
+  const long long r = idx / cols_padded;
+  dst[r * ldd + c] = __float2bfloat16(c < cols ? src[r * lds + c] : 0.f);
+}
+
+int cast_2d(const float* src, long long lds, void* dst, long long ldd, long long rows, int cols, int cols_padded,
+            cudaStream_t stream) {
+  if (rows * cols_padded == 0) return 0;
+  cast_2d_kernel<<<(unsigned)((rows * cols_padded + 255) / 256), 256, 0, stream>>>(src, lds, (__nv_bfloat16*)dst, ldd, rows, cols,
+                                                                                  cols_padded);
+  return check_launch("cast_2d_kernel");
+}
+
+// [C,1,3,3] fp32 -> tap-major [9][C] fp32 and back (gradient accumulate)
+__global__ void dw_weight_to_tap_kernel(const float* __restrict__ w, float* __restrict__ wt, int C) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= 9 * C) return;
+  const int k = idx / C, c = idx % C;
+  wt[idx] = w[c * 9 + k];
+}
+__global__ void dw_wgrad_from_tap_kernel(const float* __restrict__ dwt, float* __restrict__ dw, int C) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= 9 * C) return;
+  const int c = idx / 9, k = idx % 9;
+  dw[idx] += dwt[k * C + c];
+}
+int dw_weight_to_tap(const float* w, float* wt, int C, cudaStream_t stream) {
+  dw_weight_to_tap_kernel<<<(9 * C + 255) / 256, 256, 0, stream>>>(w, wt, C);
+  return check_launch("dw_weight_to_tap_kernel");
+}
+int dw_wgrad_from_tap(const float* dwt, float* dw, int C, cudaStream_t stream) {
+  dw_wgrad_from_tap_kernel<<<(9 * C + 255) / 256, 256, 0, stream>>>(dwt, dw, C);
+  return check_launch("dw_wgrad_from_tap_kernel");
+}
+
+}  // namespace sfk

@@ -1,0 +1,419 @@
+// All-MLP decode head kernels (MS:752-782), channels-last:
+//   * bilinear upsample (align_corners=False) of a per-stage projection into its channel slice of the concat buffer
+//     (MS:769-774, concat order c4,c3,c2,c1) and the transposed gather for its gradient
+//   * BatchNorm2d batch statistics / running-stat update (MS:744,775; eps 1e-5, momentum 0.1)
+//   * BN apply + ReLU + Dropout + 1x1 classifier fused into one pass over the fuse-conv output (MS:775-780),
+//     and the two-pass backward (per-channel reductions, then dx).
+#include "common.cuh"
+#include "sfk_internal.h"
+
+namespace sfk {
+
+// PyTorch area_pixel_compute_source_index(align_corners=False): src = scale*(dst+0.5)-0.5, clamped at 0
+__device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int& i0, int& i1, float& l1) {
+  float src = scale * (dst + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  l1 = src - i0;
+}
+
+// out[b, y, x, ch_off + c] = bilinear(in[b, :, :, c]);  in: bf16 [B,h,w,C], out: bf16 [B,H,W,ld_out]
+__global__ void __launch_bounds__(256) upsample_concat_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                              int B, int h, int w, int C, int H, int W, long long ld_out,
+                                                              int ch_off) {
+  const int C8 = C >> 3;
+  const long long total = (long long)B * H * W * C8;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % C8);
+  long long t = idx / C8;
+  const int x = (int)(t % W);
+  t /= W;
+  const int y = (int)(t % H);
+  const long long b = t / H;
+  __nv_bfloat16* op = out + ((b * H + y) * W + x) * ld_out + ch_off + c8 * 8;
+  if (h == H && w == W) {
+    *reinterpret_cast<uint4*>(op) = *reinterpret_cast<const uint4*>(in + ((b * h + y) * w + x) * C + c8 * 8);
+    return;
+  }
+  int y0, y1, x0, x1;
+  float ly, lx;
+  bilinear_src(y, (float)h / (float)H, h, y0, y1, ly);
+  bilinear_src(x, (float)w / (float)W, w, x0, x1, lx);
+  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+  const __nv_bfloat16* base = in + b * h * w * C + c8 * 8;
+  const uint4 a = *reinterpret_cast<const uint4*>(base + ((long long)y0 * w + x0) * C);
+  const uint4 bq = *reinterpret_cast<const uint4*>(base + ((long long)y0 * w + x1) * C);
+  const uint4 c = *reinterpret_cast<const uint4*>(base + ((long long)y1 * w + x0) * C);
+  const uint4 d = *reinterpret_cast<const uint4*>(base + ((long long)y1 * w + x1) * C);
+  const uint32_t* ap = reinterpret_cast<const uint32_t*>(&a);
+  const uint32_t* bp = reinterpret_cast<const uint32_t*>(&bq);
+  const uint32_t* cp = reinterpret_cast<const uint32_t*>(&c);
+  const uint32_t* dp = reinterpret_cast<const uint32_t*>(&d);
+  uint4 o;
+  uint32_t* o32 = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 fa = unpack_bf16x2(ap[i]), fb = unpack_bf16x2(bp[i]), fc = unpack_bf16x2(cp[i]), fd = unpack_bf16x2(dp[i]);
+    o32[i] = pack_bf16x2(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x, w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
+  }
+  *reinterpret_cast<uint4*>(op) = o;
+}
+
+int upsample_concat(const void* in, void* out, int B, int h, int w, int C, int H, int W, long long ld_out, int ch_off,
+                    cudaStream_t stream) {
+  SFK_REQUIRE(C % 8 == 0 && ld_out % 8 == 0 && ch_off % 8 == 0, "upsample_concat: channel counts must be multiples of 8");
+  const long long total = (long long)B * H * W * (C / 8);
+  if (total == 0) return 0;
+  upsample_concat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, h, w,
+                                                                              C, H, W, ld_out, ch_off);
+  return check_launch("upsample_concat_kernel");
+}
+
+// Transposed bilinear: din[b, yi, xi, c] = sum over hi-res (y, x) of weight(y,x -> yi,xi) * dout[b, y, x, ch_off + c].
+// Gather formulation: every low-res pixel scans the hi-res window that can reference it (no atomics, deterministic).
+__global__ void __launch_bounds__(256) upsample_concat_bwd_kernel(const __nv_bfloat16* __restrict__ dout,
+                                                                  __nv_bfloat16* __restrict__ din, int B, int h, int w, int C,
+                                                                  int H, int W, long long ld_out, int ch_off) {
+  const int C8 = C >> 3;
+  const long long total = (long long)B * h * w * C8;
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % C8);
+  long long t = idx / C8;
+  const int xi = (int)(t % w);
+  t /= w;
+  const int yi = (int)(t % h);
+  const long long b = t / h;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (h == H && w == W) {
+    *reinterpret_cast<uint4*>(din + idx * 8) =
+        *reinterpret_cast<const uint4*>(dout + ((b * H + yi) * W + xi) * ld_out + ch_off + c8 * 8);
+    return;
+  }
+  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
+  // hi-res rows whose source rows {y0, y1} can include yi: src in (yi-1, yi+1)
+  const float fy = (float)H / (float)h, fx = (float)W / (float)w;
+  int ylo = (int)floorf((yi - 1 + 0.5f) * fy - 0.5f) - 1, yhi = (int)ceilf((yi + 1 + 0.5f) * fy - 0.5f) + 1;
+  int xlo = (int)floorf((xi - 1 + 0.5f) * fx - 0.5f) - 1, xhi = (int)ceilf((xi + 1 + 0.5f) * fx - 0.5f) + 1;
+  if (ylo < 0) ylo = 0;
+  if (xlo < 0) xlo = 0;
+  if (yhi > H - 1) yhi = H - 1;
+  if (xhi > W - 1) xhi = W - 1;
+  for (int y = ylo; y <= yhi; ++y) {
+    int y0, y1;
+    float ly;
+    bilinear_src(y, sy, h, y0, y1, ly);
+    float wy = 0.f;
+    if (y0 == yi) wy += 1.f - ly;
+    if (y1 == yi) wy += ly;
+    if (wy == 0.f) continue;
+    for (int x = xlo; x <= xhi; ++x) {
+      int x0, x1;
+      float lx;
+      bilinear_src(x, sx, w, x0, x1, lx);
+      float wx = 0.f;
+      if (x0 == xi) wx += 1.f - lx;
+      if (x1 == xi) wx += lx;
+      if (wx == 0.f) continue;
+      const float wt = wy * wx;
+      const uint4 v = *reinterpret_cast<const uint4*>(dout + ((b * H + y) * W + x) * ld_out + ch_off + c8 * 8);
+      const uint32_t* vp = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = unpack_bf16x2(vp[i]);
+        acc[2 * i] = fmaf(wt, f.x, acc[2 * i]);
+        acc[2 * i + 1] = fmaf(wt, f.y, acc[2 * i + 1]);
+      }
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+  o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+  *reinterpret_cast<uint4*>(din + idx * 8) = o;
+}
+
+int upsample_concat_bwd(const void* dout, void* din, int B, int h, int w, int C, int H, int W, long long ld_out, int ch_off,
+                        cudaStream_t stream) {
+  SFK_REQUIRE(C % 8 == 0 && ld_out % 8 == 0 && ch_off % 8 == 0, "upsample_concat_bwd: channel counts must be multiples of 8");
+  const long long total = (long long)B * h * w * (C / 8);
+  if (total == 0) return 0;
+  upsample_concat_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)din,
+                                                                                  B, h, w, C, H, W, ld_out, ch_off);
+  return check_launch("upsample_concat_bwd_kernel");
+}
+
+// out[b*N + t, :] (bf16) += vec[b, :] (f32)     — cls_proj broadcast add (MS:720-723)
+__global__ void __launch_bounds__(256) add_sample_bias_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ vec,
+                                                              long long rows, int rows_per_sample, int C) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int C2 = C >> 1;
+  if (idx >= rows * C2) return;
+  const int c2 = (int)(idx % C2);
+  const long long row = idx / C2;
+  const float2 v = *reinterpret_cast<const float2*>(vec + (row / rows_per_sample) * C + c2 * 2);
+  uint32_t* p = reinterpret_cast<uint32_t*>(out + row * C + c2 * 2);
+  const float2 o = unpack_bf16x2(*p);
+  *p = pack_bf16x2(o.x + v.x, o.y + v.y);
+}
+int add_sample_bias(void* out, const float* vec, long long rows, int rows_per_sample, int C, cudaStream_t stream) {
+  SFK_REQUIRE(C % 2 == 0, "add_sample_bias: C must be even");
+  if (rows == 0) return 0;
+  add_sample_bias_kernel<<<(unsigned)((rows * (C / 2) + 255) / 256), 256, 0, stream>>>((__nv_bfloat16*)out, vec, rows,
+                                                                                       rows_per_sample, C);
+  return check_launch("add_sample_bias_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm batch statistics over rows of x [M, C] (bf16): partial[blk][0][c] = sum, partial[blk][1][c] = sum of squares
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) bn_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial,
+                                                         long long M, int C, int rows_per_block) {
+  const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
+  if (c >= C) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > M) r1 = M;
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * C + c));
+    s0 += v.x; s1 += v.y;
+    q0 = fmaf(v.x, v.x, q0); q1 = fmaf(v.y, v.y, q1);
+  }
+  float* p = partial + (long long)blockIdx.y * 2 * C;
+  p[c] = s0; p[c + 1] = s1;
+  p[C + c] = q0; p[C + c + 1] = q1;
+}
+
+// mean / rstd (biased variance) + running-stat update with the unbiased variance (nn.BatchNorm2d train mode)
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblocks, long long M, int C, float eps, float momentum,
+                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    s += (double)partial[(long long)b * 2 * C + c];
+    q += (double)partial[(long long)b * 2 * C + C + c];
+  }
+  const double mu = s / (double)M;
+  double var = q / (double)M - mu * mu;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)mu;
+  rstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean != nullptr) {
+    const double unbiased = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+size_t bn_stats_workspace_bytes(long long M, int C) {
+  long long gy = (long long)num_sms() * 8 / ((C / 2 + 127) / 128);
+  if (gy < 1) gy = 1;
+  if (gy > M) gy = M > 0 ? M : 1;
+  return (size_t)gy * 2 * C * sizeof(float);
+}
+
+int bn_batch_stats(const void* x, long long M, int C, float eps, float momentum, float* mean, float* rstd, float* running_mean,
+                   float* running_var, float* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  SFK_REQUIRE(C % 2 == 0, "bn_batch_stats: C must be even");
+  SFK_REQUIRE(M > 0, "bn_batch_stats: empty batch");
+  const int gx = (C / 2 + 127) / 128;
+  long long gy = (long long)num_sms() * 8 / gx;
+  if (gy < 1) gy = 1;
+  if (gy > M) gy = M;
+  SFK_REQUIRE(workspace_bytes >= (size_t)gy * 2 * C * sizeof(float), "bn_batch_stats: workspace too small");
+  const int rpb = (int)((M + gy - 1) / gy);
+  gy = (M + rpb - 1) / rpb;
+  bn_partial_kernel<<<dim3(gx, (unsigned)gy), 128, 0, stream>>>((const __nv_bfloat16*)x, workspace, M, C, rpb);
+  int rc = check_launch("bn_partial_kernel");
+  if (rc) return rc;
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(workspace, (int)gy, M, C, eps, momentum, mean, rstd, running_mean,
+                                                          running_var);
+  return check_launch("bn_finalize_kernel");
+}
+
+// eval mode: mean = running_mean, rstd = 1/sqrt(running_var + eps)
+__global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, float eps, float* __restrict__ mean,
+                                     float* __restrict__ rstd, int C) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= C) return;
+  mean[c] = rm[c];
+  rstd[c] = 1.f / sqrtf(rv[c] + eps);
+}
+int bn_eval_stats(const float* rm, const float* rv, float eps, float* mean, float* rstd, int C, cudaStream_t stream) {
+  bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, stream>>>(rm, rv, eps, mean, rstd, C);
+  return check_launch("bn_eval_stats_kernel");
+}
+
+// counter-based dropout mask: keep iff hash(seed, element) >= p  (regenerated identically in backward)
+__device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned long long idx) {
+  unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+static constexpr int CLS_MAX_LABELS = 8;
+
+// One warp per row of x [M, C]: y = relu(bn(x)) * dropmask ; logits[b, l, pix] = sum_c y[c] * Wc[l, c] + bc[l]
+template <int DUMMY>
+__global__ void __launch_bounds__(256) bn_relu_cls_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
+                                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, const float* __restrict__ wc,
+                                                              const float* __restrict__ bc, float* __restrict__ logits,
+                                                              long long M, int C, int NL, int pix_per_sample, float drop_p,
+                                                              unsigned long long seed) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= M) return;
+  float acc[CLS_MAX_LABELS];
+#pragma unroll
+  for (int l = 0; l < CLS_MAX_LABELS; ++l) acc[l] = 0.f;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (int c = lane * 2; c < C; c += 64) {
+    const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + row * C + c));
+    float y0 = fmaxf((v.x - mean[c]) * rstd[c] * gamma[c] + beta[c], 0.f);
+    float y1 = fmaxf((v.y - mean[c + 1]) * rstd[c + 1] * gamma[c + 1] + beta[c + 1], 0.f);
+    if (drop_p > 0.f) {
+      y0 = hash_uniform(seed, (unsigned long long)row * C + c) >= drop_p ? y0 * keep_scale : 0.f;
+      y1 = hash_uniform(seed, (unsigned long long)row * C + c + 1) >= drop_p ? y1 * keep_scale : 0.f;
+    }
+#pragma unroll
+    for (int l = 0; l < CLS_MAX_LABELS; ++l)
+      if (l < NL) acc[l] = fmaf(y0, wc[l * C + c], fmaf(y1, wc[l * C + c + 1], acc[l]));
+  }
+  const long long b = row / pix_per_sample, pix = row % pix_per_sample;
+#pragma unroll
+  for (int l = 0; l < CLS_MAX_LABELS; ++l) {
+    if (l < NL) {
+      const float s = warp_sum(acc[l]);
+      if (lane == 0) logits[(b * NL + l) * pix_per_sample + pix] = s + bc[l];
+    }
+  }
+}
+
+int bn_relu_cls_fwd(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta, const float* wc,
+                    const float* bc, float* logits, long long M, int C, int NL, int pix_per_sample, float drop_p,
+                    unsigned long long seed, cudaStream_t stream) {
+  SFK_REQUIRE(NL >= 1 && NL <= CLS_MAX_LABELS, "bn_relu_cls: num_labels=%d unsupported (1..%d)", NL, CLS_MAX_LABELS);
+  SFK_REQUIRE(C % 2 == 0, "bn_relu_cls: C must be even");
+  if (M == 0) return 0;
+  bn_relu_cls_fwd_kernel<0><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>((const __nv_bfloat16*)x, mean, rstd, gamma, beta, wc, bc,
+                                                                         logits, M, C, NL, pix_per_sample, drop_p, seed);
+  return check_launch("bn_relu_cls_fwd_kernel");
+}
+
+// Backward pass A (one warp per row, block-level column reduction):
+//   dyb[c] = (sum_l dlogit[l] * Wc[l,c]) * dropmask * [bn(x) > 0]      (gradient at the BN output)
+//   sums[0][c] += dyb[c] ; sums[1][c] += dyb[c] * xhat[c]               (-> dbeta, dgamma, BN dx terms)
+//   dwc[l][c] += dlogit[l] * y[c] ; dbc[l] += dlogit[l]
+// Backward pass B recomputes dyb and writes dx = gamma*rstd*(dyb - sums0/M - xhat*sums1/M)  (train) or gamma*rstd*dyb (eval)
+template <int PASS>
+__global__ void __launch_bounds__(256) bn_relu_cls_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
+                                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, const float* __restrict__ wc,
+                                                              const float* __restrict__ dlogits, float* __restrict__ sums,
+                                                              float* __restrict__ dwc, float* __restrict__ dbc,
+                                                              __nv_bfloat16* __restrict__ dx, long long M, int C, int NL,
+                                                              int pix_per_sample, float drop_p, unsigned long long seed,
+                                                              int train_stats, int rows_per_block) {
+  extern __shared__ float sh[];  // PASS 0: [2 + NL][C] block accumulators
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  if (PASS == 0) {
+    for (int i = threadIdx.x; i < (2 + NL) * C; i += 256) sh[i] = 0.f;
+    __syncthreads();
+  }
+  const float invM = 1.f / (float)M;
+  const long long row0 = (long long)blockIdx.x * rows_per_block;
+  float dbc_acc[CLS_MAX_LABELS];
+#pragma unroll
+  for (int l = 0; l < CLS_MAX_LABELS; ++l) dbc_acc[l] = 0.f;
+  for (int i = warp; i < rows_per_block; i += 8) {
+    const long long row = row0 + i;
+    if (row >= M) break;
+    const long long b = row / pix_per_sample, pix = row % pix_per_sample;
+    float dl[CLS_MAX_LABELS];
+#pragma unroll
+    for (int l = 0; l < CLS_MAX_LABELS; ++l) {
+      dl[l] = l < NL ? dlogits[(b * NL + l) * pix_per_sample + pix] : 0.f;
+      dbc_acc[l] += dl[l];
+    }
+    for (int c = lane * 2; c < C; c += 64) {
+      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + row * C + c));
+      float xh[2] = {(v.x - mean[c]) * rstd[c], (v.y - mean[c + 1]) * rstd[c + 1]};
+      float o[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float bn = xh[k] * gamma[c + k] + beta[c + k];
+        float m = bn > 0.f ? 1.f : 0.f;
+        if (drop_p > 0.f) m *= hash_uniform(seed, (unsigned long long)row * C + c + k) >= drop_p ? keep_scale : 0.f;
+        float dy = 0.f;
+#pragma unroll
+        for (int l = 0; l < CLS_MAX_LABELS; ++l)
+          if (l < NL) dy = fmaf(dl[l], wc[l * C + c + k], dy);
+        const float dyb = dy * m;
+        if (PASS == 0) {
+          atomicAdd(&sh[c + k], dyb);
+          atomicAdd(&sh[C + c + k], dyb * xh[k]);
+          const float yv = fmaxf(bn, 0.f) * (drop_p > 0.f ? (m > 0.f ? keep_scale : 0.f) : 1.f);
+#pragma unroll
+          for (int l = 0; l < CLS_MAX_LABELS; ++l)
+            if (l < NL) atomicAdd(&sh[(2 + l) * C + c + k], dl[l] * yv);
+        } else {
+          float g = gamma[c + k] * rstd[c + k];
+          o[k] = train_stats ? g * (dyb - sums[c + k] * invM - xh[k] * sums[C + c + k] * invM) : g * dyb;
+        }
+      }
+      if (PASS == 1) *reinterpret_cast<uint32_t*>(dx + row * C + c) = pack_bf16x2(o[0], o[1]);
+    }
+  }
+  if (PASS == 0) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(sums + i, sh[i]);
+    for (int i = threadIdx.x; i < NL * C; i += 256) atomicAdd(dwc + i, sh[2 * C + i]);
+    if (lane == 0) {
+#pragma unroll
+      for (int l = 0; l < CLS_MAX_LABELS; ++l)
+        if (l < NL) atomicAdd(dbc + l, dbc_acc[l]);
+    }
+  }
+}
+
+// sums: f32 [2][C] workspace (zero-filled here). After the call sums[0] = dbeta, sums[1] = dgamma contributions.
+int bn_relu_cls_bwd(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta, const float* wc,
+                    const float* dlogits, float* sums, float* dwc, float* dbc, void* dx, long long M, int C, int NL,
+                    int pix_per_sample, float drop_p, unsigned long long seed, int train_stats, cudaStream_t stream) {
+  SFK_REQUIRE(NL >= 1 && NL <= CLS_MAX_LABELS, "bn_relu_cls_bwd: num_labels=%d unsupported", NL);
+  if (M == 0) return 0;
+  cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)2 * C * sizeof(float), stream);
+  SFK_REQUIRE(e == cudaSuccess, "bn_relu_cls_bwd: memset failed: %s", cudaGetErrorString(e));
+  int rpb = 64;
+  long long grid = (M + rpb - 1) / rpb;
+  const long long max_grid = (long long)num_sms() * 4;
+  if (grid > max_grid) {
+    rpb = (int)((M + max_grid - 1) / max_grid);
+    rpb = (rpb + 7) / 8 * 8;
+    grid = (M + rpb - 1) / rpb;
+  }
+  const size_t smem = (size_t)(2 + NL) * C * sizeof(float);
+  SFK_REQUIRE(smem <= 48 * 1024, "bn_relu_cls_bwd: C*(2+NL) too large for shared memory");
+  bn_relu_cls_bwd_kernel<0><<<(unsigned)grid, 256, smem, stream>>>((const __nv_bfloat16*)x, mean, rstd, gamma, beta, wc, dlogits,
+                                                                   sums, dwc, dbc, nullptr, M, C, NL, pix_per_sample, drop_p,
+                                                                   seed, train_stats, rpb);
+  int rc = check_launch("bn_relu_cls_bwd_kernel<0>");
+  if (rc) return rc;
+  bn_relu_cls_bwd_kernel<1><<<(unsigned)grid, 256, 0, stream>>>((const __nv_bfloat16*)x, mean, rstd, gamma, beta, wc, dlogits, sums,
+                                                                nullptr, nullptr, (__nv_bfloat16*)dx, M, C, NL, pix_per_sample,
+                                                                drop_p, seed, train_stats, rpb);
+  return check_launch("bn_relu_cls_bwd_kernel<1>");
+}
+
+}  // namespace sfk

@@ -41,6 +41,8 @@ struct GemmKernelParams {
   const float* bias;
   const float* residual;
   long long ldr;
+  RowMap res_map;
+  RowMap out_map;
   const float* row_scale;
   int rows_per_scale;
   void* out;
@@ -50,6 +52,10 @@ struct GemmKernelParams {
   int relu;
 };
 
+__device__ __forceinline__ long long gemm_map_row(long long row, const RowMap& m) {
+  if (m.period > 0) row += (row / m.period) * m.extra;
+  return row + m.offset;
+}
 __device__ __forceinline__ void red_add_f32(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
@@ -192,6 +198,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       float rscale = p.alpha;
       if (p.row_scale != nullptr && row_ok) rscale *= p.row_scale[row / p.rows_per_scale];
       const int n0 = n_blk * p.block_n;
+      const long long orow = gemm_map_row(row, p.out_map);
       for (int c = 0; c < p.block_n; c += 32) {
         uint32_t r[32];
         __syncwarp();
@@ -218,7 +225,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= rscale;
         if (p.residual != nullptr) {
-          const float* rp = p.residual + row * p.ldr + col0;
+          const float* rp = p.residual + gemm_map_row(row, p.res_map) * p.ldr + col0;
           if (full_chunk) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -235,7 +242,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
         }
         if (p.atomic_add) {
-          float* op = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
+          float* op = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0;
           if (full_chunk) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) red_add_v4_f32(op + j, v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -244,7 +251,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               if (col0 + j < p.N) red_add_f32(op + j, v[j]);
           }
         } else if (p.out_bf16) {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col0;
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + col0;
           if (full_chunk) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
@@ -260,7 +267,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               if (col0 + j < p.N) op[j] = __float2bfloat16(v[j]);
           }
         } else {
-          float* op = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
+          float* op = reinterpret_cast<float*>(p.out) + orow * p.ldo + col0;
           if (full_chunk) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
@@ -363,6 +370,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.bias = g.bias;
   p.residual = g.residual;
   p.ldr = g.ldr;
+  p.res_map = g.res_map;
+  p.out_map = g.out_map;
   p.row_scale = g.row_scale;
   p.rows_per_scale = g.rows_per_scale > 0 ? g.rows_per_scale : 1;
   p.out = g.out;

@@ -77,6 +77,30 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return 0;
 }
 
+int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                      uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2, int swizzle_bytes) {
+  PFN_encodeTiled enc = get_encode();
+  SFK_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  SFK_REQUIRE((int)box0 * 2 == swizzle_bytes, "tensor map: inner box (%u elems) must equal the swizzle span (%d B)", box0,
+              swizzle_bytes);
+  SFK_REQUIRE(box1 >= 1 && box1 <= 256 && box2 >= 1 && box2 <= 256, "tensor map: box out of range");
+  SFK_REQUIRE(stride1_bytes % 16 == 0 && stride2_bytes % 16 == 0, "tensor map: strides must be multiples of 16 bytes");
+  SFK_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: base must be 16-byte aligned");
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                        : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                                               : CU_TENSOR_MAP_SWIZZLE_32B;
+  cuuint64_t gdim[3] = {d0, d1, d2};
+  cuuint64_t gstride[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {box0, box1, box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SFK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(3d) failed with CUresult %d (dims %llu,%llu,%llu strides %llu,%llu)",
+              (int)r, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+              (unsigned long long)stride1_bytes, (unsigned long long)stride2_bytes);
+  return 0;
+}
+
 }  // namespace sfk
 
 extern "C" {

@@ -1,0 +1,364 @@
+// Bandwidth-bound row-wise kernels: LayerNorm fwd/bwd, scaled casts, column sums, token concat/split.
+// One warp per row, 128-bit loads, warp-shuffle reductions (no shared memory needed for C <= 1024).
+//
+// Reference call sites: nn.LayerNorm at MS:133,174,325,333,418 (eps = 1e-5, biased variance, affine) and the
+// autograd gradients of those; bias gradients of every nn.Linear/Conv2d on the path.
+#include "common.cuh"
+#include "sfk_internal.h"
+
+namespace sfk {
+
+static constexpr int LN_CHUNK_LIMIT = 8;  // float4 chunks per lane -> C <= 1024
+
+__device__ __forceinline__ long long map_row(long long row, const RowMap& m) {
+  if (m.period > 0) row += (row / m.period) * m.extra;
+  return row + m.offset;
+}
+
+template <typename T> struct Ld4;
+template <> struct Ld4<float> {
+  static __device__ __forceinline__ float4 ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void st(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Ld4<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 ld(const __nv_bfloat16* p) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float4 v) {
+    uint2 u;
+    u.x = pack_bf16x2(v.x, v.y);
+    u.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm forward
+// ------------------------------------------------------------------------------------------------
+template <typename TIn, typename TOut, int LN_MAX_CHUNKS>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const TIn* __restrict__ x, RowMap in_map, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, TOut* __restrict__ y,
+                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                     long long rows, int C, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const TIn* xr = x + map_row(row, in_map) * C;
+  const int nchunk = C >> 2;
+  float4 v[LN_MAX_CHUNKS];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
+    const int ci = lane + 32 * k;
+    if (ci < nchunk) {
+      v[k] = Ld4<TIn>::ld(xr + ci * 4);
+      s += v[k].x + v[k].y + v[k].z + v[k].w;
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
+    const int ci = lane + 32 * k;
+    if (ci < nchunk) {
+      const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  TOut* yr = y + row * C;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
+    const int ci = lane + 32 * k;
+    if (ci < nchunk) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + ci);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + ci);
+      float4 o;
+      o.x = (v[k].x - mean) * rstd * g.x + b.x;
+      o.y = (v[k].y - mean) * rstd * g.y + b.y;
+      o.z = (v[k].z - mean) * rstd * g.z + b.z;
+      o.w = (v[k].w - mean) * rstd * g.w + b.w;
+      Ld4<TOut>::st(yr + ci * 4, o);
+    }
+  }
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+int layernorm_fwd(const void* x, int x_bf16, RowMap in_map, const float* gamma, const float* beta, void* y, int y_bf16,
+                  float* mean, float* rstd, long long rows, int C, float eps, cudaStream_t stream) {
+  SFK_REQUIRE(C % 4 == 0 && C <= 4 * 32 * LN_CHUNK_LIMIT, "layernorm: C=%d unsupported (need C %% 4 == 0, C <= 1024)", C);
+  if (rows == 0) return 0;
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+#define LAUNCH_N(TI, TO, NCH) ln_fwd_kernel<TI, TO, NCH><<<grid, 256, 0, stream>>>((const TI*)x, in_map, gamma, beta, (TO*)y, mean, rstd, rows, C, eps)
+#define LAUNCH(TI, TO)                                   \
+  do {                                                   \
+    if (C <= 128) LAUNCH_N(TI, TO, 1);                   \
+    else if (C <= 256) LAUNCH_N(TI, TO, 2);              \
+    else if (C <= 512) LAUNCH_N(TI, TO, 4);              \
+    else LAUNCH_N(TI, TO, 8);                            \
+  } while (0)
+  if (x_bf16 && y_bf16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
+  else if (x_bf16) LAUNCH(__nv_bfloat16, float);
+  else if (y_bf16) LAUNCH(float, __nv_bfloat16);
+  else LAUNCH(float, float);
+#undef LAUNCH
+#undef LAUNCH_N
+  return check_launch("ln_fwd_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward:  dx = rstd * (dy*g - mean_c(dy*g) - xhat * mean_c(dy*g*xhat))  (+ dres)
+//                      dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy
+// ------------------------------------------------------------------------------------------------
+template <typename TDy, typename TX, typename TDx, int LN_MAX_CHUNKS>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const TDy* __restrict__ dy, const TX* __restrict__ x, RowMap x_map,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                     const float* __restrict__ gamma, const float* __restrict__ dres,
+                                                     RowMap dres_map, TDx* __restrict__ dx, RowMap dx_map,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows,
+                                                     int C, int rows_per_block) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunk = C >> 2;
+  float4 gacc[LN_MAX_CHUNKS], bacc[LN_MAX_CHUNKS], g[LN_MAX_CHUNKS];
+#pragma unroll
+  for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
+    gacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int ci = lane + 32 * k;
+    g[k] = ci < nchunk ? __ldg(reinterpret_cast<const float4*>(gamma) + ci) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const long long row0 = (long long)blockIdx.x * rows_per_block;
+  for (int i = warp; i < rows_per_block; i += 8) {
+    const long long row = row0 + i;
+    if (row >= rows) break;
+    const TDy* dyr = dy + row * C;
+    const TX* xr = x + map_row(row, x_map) * C;
+    const float mu = mean[row], rs = rstd[row];
+    float4 dyv[LN_MAX_CHUNKS], xh[LN_MAX_CHUNKS];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
+      const int ci = lane + 32 * k;
+      if (ci < nchunk) {
+        dyv[k] = Ld4<TDy>::ld(dyr + ci * 4);
+        const float4 xv = Ld4<TX>::ld(xr + ci * 4);
+        xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        const float a = dyv[k].x * g[k].x, b = dyv[k].y * g[k].y, c = dyv[k].z * g[k].z, d = dyv[k].w * g[k].w;
+        s1 += a + b + c + d;
+        s2 += a * xh[k].x + b * xh[k].y + c * xh[k].z + d * xh[k].w;
+        gacc[k].x += dyv[k].x * xh[k].x; gacc[k].y += dyv[k].y * xh[k].y;
+        gacc[k].z += dyv[k].z * xh[k].z; gacc[k].w += dyv[k].w * xh[k].w;
+        bacc[k].x += dyv[k].x; bacc[k].y += dyv[k].y; bacc[k].z += dyv[k].z; bacc[k].w += dyv[k].w;
+      }
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+    TDx* dxr = dx + map_row(row, dx_map) * C;
+    const float* rr = dres ? dres + map_row(row, dres_map) * C : nullptr;
+#pragma unroll
+    for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
+      const int ci = lane + 32 * k;
+      if (ci < nchunk) {
+        float4 o;
+        o.x = rs * (dyv[k].x * g[k].x - s1 - xh[k].x * s2);
+        o.y = rs * (dyv[k].y * g[k].y - s1 - xh[k].y * s2);
+        o.z = rs * (dyv[k].z * g[k].z - s1 - xh[k].z * s2);
+        o.w = rs * (dyv[k].w * g[k].w - s1 - xh[k].w * s2);
+        if (rr) {
+          const float4 r4 = *reinterpret_cast<const float4*>(rr + ci * 4);
+          o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+        }
+        Ld4<TDx>::st(dxr + ci * 4, o);
+      }
+    }
+  }
+  if (dgamma == nullptr) return;
+  // cross-warp reduction of the per-column partials, then one atomic per column per block
+  extern __shared__ float red[];  // [8][2*C]
+  float* my = red + warp * 2 * C;
+#pragma unroll
+  for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
+    const int ci = lane + 32 * k;
+    if (ci < nchunk) {
+      *reinterpret_cast<float4*>(my + ci * 4) = gacc[k];
+      *reinterpret_cast<float4*>(my + C + ci * 4) = bacc[k];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += red[w * 2 * C + c];
+    if (c < C) atomicAdd(dgamma + c, t);
+    else atomicAdd(dbeta + (c - C), t);
+  }
+}
+
+int layernorm_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, RowMap x_map, const float* mean,
+                  const float* rstd, const float* gamma, const float* dres, RowMap dres_map, void* dx, int dx_bf16,
+                  RowMap dx_map, float* dgamma, float* dbeta, long long rows, int C, cudaStream_t stream) {
+  SFK_REQUIRE(C % 4 == 0 && C <= 4 * 32 * LN_CHUNK_LIMIT, "layernorm_bwd: C=%d unsupported", C);
+  if (rows == 0) return 0;
+  int rows_per_block = 64;
+  long long grid = (rows + rows_per_block - 1) / rows_per_block;
+  const long long max_grid = (long long)num_sms() * 8;
+  if (grid > max_grid) {
+    rows_per_block = (int)((rows + max_grid - 1) / max_grid);
+    rows_per_block = (rows_per_block + 7) / 8 * 8;
+    grid = (rows + rows_per_block - 1) / rows_per_block;
+  }
+  const size_t smem = (size_t)8 * 2 * C * sizeof(float);
+#define LAUNCH_N(TD, TX, TO, NCH)                                                                                       \
+  if (smem > 48 * 1024) cudaFuncSetAttribute(ln_bwd_kernel<TD, TX, TO, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  ln_bwd_kernel<TD, TX, TO, NCH><<<(unsigned)grid, 256, smem, stream>>>((const TD*)dy, (const TX*)x, x_map, mean, rstd, gamma, \
+                                                                        dres, dres_map, (TO*)dx, dx_map, dgamma, dbeta, rows, \
+                                                                        C, rows_per_block)
+#define LAUNCH(TD, TX, TO)                               \
+  do {                                                   \
+    if (C <= 128) { LAUNCH_N(TD, TX, TO, 1); }           \
+    else if (C <= 256) { LAUNCH_N(TD, TX, TO, 2); }      \
+    else if (C <= 512) { LAUNCH_N(TD, TX, TO, 4); }      \
+    else { LAUNCH_N(TD, TX, TO, 8); }                    \
+  } while (0)
+  const int key = (dy_bf16 ? 4 : 0) | (x_bf16 ? 2 : 0) | (dx_bf16 ? 1 : 0);
+  switch (key) {
+    case 0: LAUNCH(float, float, float); break;
+    case 1: LAUNCH(float, float, __nv_bfloat16); break;
+    case 2: LAUNCH(float, __nv_bfloat16, float); break;
+    case 3: LAUNCH(float, __nv_bfloat16, __nv_bfloat16); break;
+    case 4: LAUNCH(__nv_bfloat16, float, float); break;
+    case 5: LAUNCH(__nv_bfloat16, float, __nv_bfloat16); break;
+    case 6: LAUNCH(__nv_bfloat16, __nv_bfloat16, float); break;
+    default: LAUNCH(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16); break;
+  }
+#undef LAUNCH
+#undef LAUNCH_N
+  return check_launch("ln_bwd_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// y_bf16[row, :] = x_f32[map(row), :] * scale[row / rows_per_scale]   (drop-path backward / plain cast)
+// ------------------------------------------------------------------------------------------------
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) scale_cast_kernel(const TIn* __restrict__ x, RowMap in_map, TOut* __restrict__ y,
+                                                         RowMap out_map, const float* __restrict__ scale, int rows_per_scale,
+                                                         long long rows, int C4) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= rows * C4) return;
+  const long long row = idx / C4;
+  const int c = (int)(idx - row * C4) * 4;
+  float4 v = Ld4<TIn>::ld(x + map_row(row, in_map) * (C4 * 4LL) + c);
+  if (scale) {
+    const float s = scale[row / rows_per_scale];
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+  }
+  Ld4<TOut>::st(y + map_row(row, out_map) * (C4 * 4LL) + c, v);
+}
+
+int scale_cast(const void* x, int x_bf16, RowMap in_map, void* y, int y_bf16, RowMap out_map, const float* scale,
+               int rows_per_scale, long long rows, int C, cudaStream_t stream) {
+  SFK_REQUIRE(C % 4 == 0, "scale_cast: C=%d must be a multiple of 4", C);
+  if (rows == 0) return 0;
+  const long long n = rows * (C / 4);
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (rows_per_scale <= 0) rows_per_scale = 1;
+#define LAUNCH(TI, TO) scale_cast_kernel<TI, TO><<<grid, 256, 0, stream>>>((const TI*)x, in_map, (TO*)y, out_map, scale, rows_per_scale, rows, C / 4)
+  if (x_bf16 && y_bf16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
+  else if (x_bf16) LAUNCH(__nv_bfloat16, float);
+  else if (y_bf16) LAUNCH(float, __nv_bfloat16);
+  else LAUNCH(float, float);
+#undef LAUNCH
+  return check_launch("scale_cast_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[c] += sum_rows x[row, c]   (bias gradients).  Block = 256 columns x ROWS rows, one atomic per column.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out,
+                                                     long long rows, int C, int rows_per_block) {
+  const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
+  if (c >= C) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  long long r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float a0 = 0.f, a1 = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    if constexpr (sizeof(T) == 2) {
+      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + r * ld + c));
+      a0 += v.x; a1 += v.y;
+    } else {
+      const float2 v = *reinterpret_cast<const float2*>(x + r * ld + c);
+      a0 += v.x; a1 += v.y;
+    }
+  }
+  atomicAdd(out + c, a0);
+  atomicAdd(out + c + 1, a1);
+}
+
+int colsum(const void* x, int x_bf16, long long ld, float* out, long long rows, int C, cudaStream_t stream) {
+  SFK_REQUIRE(C % 2 == 0 && ld % 2 == 0, "colsum: C and ld must be even");
+  if (rows == 0) return 0;
+  const int gx = (C / 2 + 127) / 128;
+  long long gy = (long long)num_sms() * 4 / gx;
+  if (gy < 1) gy = 1;
+  int rpb = (int)((rows + gy - 1) / gy);
+  if (rpb < 32) rpb = 32;
+  gy = (rows + rpb - 1) / rpb;
+  dim3 grid(gx, (unsigned)gy);
+  if (x_bf16) colsum_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)x, ld, out, rows, C, rpb);
+  else colsum_kernel<float><<<grid, 128, 0, stream>>>((const float*)x, ld, out, rows, C, rpb);
+  return check_launch("colsum_kernel");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Token concat: out[b, 0:P, :] = front (shared [P,C] when front_batch_stride == 0, else per-sample),
+//               out[b, P:P+N, :] = x[b, :, :]                      (MS:446-460)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) concat_front_kernel(const float* __restrict__ front, long long front_batch_stride,
+                                                           const float* __restrict__ x, float* __restrict__ out, int B, int P,
+                                                           int N, int C4) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)B * (P + N) * C4;
+  if (idx >= total) return;
+  const int c = (int)(idx % C4);
+  const long long rowg = idx / C4;
+  const int t = (int)(rowg % (P + N));
+  const long long b = rowg / (P + N);
+  float4 v;
+  if (t < P) v = *reinterpret_cast<const float4*>(front + b * front_batch_stride + ((long long)t * C4 + c) * 4);
+  else v = *reinterpret_cast<const float4*>(x + ((b * N + (t - P)) * C4 + c) * 4);
+  *reinterpret_cast<float4*>(out + idx * 4) = v;
+}
+
+int concat_front(const float* front, long long front_batch_stride, const float* x, float* out, int B, int P, int N, int C,
+                 cudaStream_t stream) {
+  SFK_REQUIRE(C % 4 == 0, "concat_front: C must be a multiple of 4");
+  const long long total = (long long)B * (P + N) * (C / 4);
+  if (total == 0) return 0;
+  concat_front_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(front, front_batch_stride, x, out, B, P, N, C / 4);
+  return check_launch("concat_front_kernel");
+}
+
+// dfront[P,C] (+)= sum_b g[b, 0:P, :] (shared prompt rows: MS:451 repeat -> sum over batch)
+__global__ void front_grad_sum_kernel(const float* __restrict__ g, float* __restrict__ dfront, int B, int P, int T, int C) {
+  const int idx = blockIdx.x * 256 + threadIdx.x;
+  if (idx >= P * C) return;
+  const int t = idx / C, c = idx % C;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += g[((long long)b * T + t) * C + c];
+  dfront[idx] += s;
+}
+
+int front_grad_sum(const float* g, float* dfront, int B, int P, int T, int C, cudaStream_t stream) {
+  if (P * C == 0) return 0;
+  front_grad_sum_kernel<<<(P * C + 255) / 256, 256, 0, stream>>>(g, dfront, B, P, T, C);
+  return check_launch("front_grad_sum_kernel");
+}
+
+}  // namespace sfk

@@ -5,6 +5,14 @@
 
 namespace sfk {
 
+// Row remap used where a [B, N, C] tensor lives inside a [B, P+N, C] one (prompt / cls rows in front):
+//   mapped = row + (period > 0 ? (row / period) * extra : 0) + offset
+struct RowMap {
+  long long period = 0;
+  long long extra = 0;
+  long long offset = 0;
+};
+
 struct GemmDesc {
   // D[M,N] = alpha * A·B^T (+bias[N]) (*row_scale[row / rows_per_scale]) (+residual fp32) -> out (fp32 | bf16 | fp32 +=)
   int M = 0, N = 0, K = 0;
@@ -18,6 +26,8 @@ struct GemmDesc {
   const float* bias = nullptr;
   const float* residual = nullptr;
   long long ldr = 0;
+  RowMap res_map;            // residual row = map(row)
+  RowMap out_map;            // output row = map(row)
   const float* row_scale = nullptr;
   int rows_per_scale = 1;
   void* out = nullptr;
@@ -30,5 +40,60 @@ struct GemmDesc {
 };
 
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream);
+
+// ---- attention.cu ----
+struct AttentionDesc {
+  int B = 0, heads = 0, T = 0, Tk = 0, D = 0;
+  float scale = 1.f;
+  const void* q = nullptr;       // bf16, token t of sample b at q + b*q_batch_stride + t*ldq (+ head*D)
+  long long ldq = 0, q_batch_stride = 0;
+  const void* k = nullptr;       // bf16, same addressing with ldkv / kv_batch_stride
+  const void* v = nullptr;
+  long long ldkv = 0, kv_batch_stride = 0;
+  void* o = nullptr;             // bf16 out
+  long long ldo = 0, o_batch_stride = 0;
+  float* lse = nullptr;          // [B, heads, T], log2 domain
+};
+struct AttentionBwdDesc : AttentionDesc {
+  const void* dO = nullptr;      // bf16, addressed like o
+  float* delta = nullptr;        // workspace [B, heads, T]
+  float* dq = nullptr;           // fp32, += (caller zero-fills)
+  long long ld_dq = 0, dq_batch_stride = 0;
+  float* dk = nullptr;           // fp32, += (caller zero-fills)
+  float* dv = nullptr;
+  long long ld_dkv = 0, dkv_batch_stride = 0;
+};
+int attention_fwd(const AttentionDesc& a, cudaStream_t stream);
+int attention_bwd(const AttentionBwdDesc& a, cudaStream_t stream);
+
+// ---- rowwise.cu ----
+int layernorm_fwd(const void* x, int x_bf16, RowMap in_map, const float* gamma, const float* beta, void* y, int y_bf16,
+                  float* mean, float* rstd, long long rows, int C, float eps, cudaStream_t stream);
+int layernorm_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, RowMap x_map, const float* mean,
+                  const float* rstd, const float* gamma, const float* dres, RowMap dres_map, void* dx, int dx_bf16,
+                  RowMap dx_map, float* dgamma, float* dbeta, long long rows, int C, cudaStream_t stream);
+int scale_cast(const void* x, int x_bf16, RowMap in_map, void* y, int y_bf16, RowMap out_map, const float* scale,
+               int rows_per_scale, long long rows, int C, cudaStream_t stream);
+int colsum(const void* x, int x_bf16, long long ld, float* out, long long rows, int C, cudaStream_t stream);
+int concat_front(const float* front, long long front_batch_stride, const float* x, float* out, int B, int P, int N, int C,
+                 cudaStream_t stream);
+int front_grad_sum(const float* g, float* dfront, int B, int P, int T, int C, cudaStream_t stream);
+
+// ---- conv.cu ----
+int dwconv3x3(const void* x, const float* wt, const float* bias, void* y, int B, int H, int W, int C, int mode,
+              cudaStream_t stream);
+int dwconv3x3_gelu_bwd(const void* x, const float* wt, const float* bias, const void* dg, void* dpre, float* dwt,
+                       float* dbias, int B, int H, int W, int C, cudaStream_t stream);
+int im2col_nhwc(const void* x, void* A, int B, int H, int W, int C, int K, int S, int P, long long tok_stride,
+                long long tok_offset, cudaStream_t stream);
+int im2col_nchw_f32(const float* x, void* A, int B, int Cin, int H, int W, int K, int S, int P, int Kp, cudaStream_t stream);
+int col2im_nhwc(const void* dA, float* dx, int B, int H, int W, int C, int K, int S, int P, long long tok_stride,
+                long long tok_offset, int accumulate, cudaStream_t stream);
+int conv_weight_ohwi(const float* w, void* out, int O, int I, int KH, int KW, long long ldo, cudaStream_t stream);
+int conv_wgrad_ohwi_to_oihw(const float* g, float* dw, int O, int I, int KH, int KW, long long ldg, cudaStream_t stream);
+int cast_2d(const float* src, long long lds, void* dst, long long ldd, long long rows, int cols, int cols_padded,
+            cudaStream_t stream);
+int dw_weight_to_tap(const float* w, float* wt, int C, cudaStream_t stream);
+int dw_wgrad_from_tap(const float* dwt, float* dw, int C, cudaStream_t stream);
 
 }  // namespace sfk
