@@ -37,6 +37,12 @@ int sfk_version(void);
 /* 0 iff the current CUDA device is compute capability 10.x (sm_100). */
 int sfk_device_check(void);
 
+/* Number of kernels libsfk has launched in this process (bench.py's gpu_launches). */
+long long sfk_launch_count(void);
+/* Live timing of the dominant kernel: CUDA events around every GEMM launch between begin and end (end synchronises). */
+int sfk_profile_gemm_begin(void);
+int sfk_profile_gemm_end(double* total_ms, double* total_flops, long long* launches);
+
 /* ---- dense contractions (tcgen05 + TMA + TMEM) ------------------------------------------------------------
  * D[M,N] = alpha * (A · B^T) (+ bias[N]) (* row_scale[row / rows_per_scale]) (+ residual[M,N] f32) (relu)
  *   a: bf16.  a_mn == 0: stored [M, lda], K contiguous.   a_mn == 1: stored [K, lda], M contiguous.
@@ -107,6 +113,102 @@ int sfk_scale_cast(const void* x, int x_bf16, void* y, int y_bf16, const float* 
                    long long rows, int C, sfk_stream_t stream);
 /* out[c] += sum_rows x[row, c] (bias gradients) */
 int sfk_colsum(const void* x, int x_bf16, long long ld, float* out, long long rows, int C, sfk_stream_t stream);
+
+/* ---- one SegformerLayer (MS:320-363) per call ------------------------------------------------------------------
+ * x: f32 [B, N, C] spatial tokens; front: f32 [B, ptl, C] prompt / cls rows placed in front (MS:446-460) or NULL.
+ * out: f32 [B, N, C]; front_out: f32 [B, ptl, C] (the `cls_token` slice returned by MS:352,363).
+ * Parameter gradients are accumulated (+=) directly into the f32 buffers of sfk_layer_grads (NULL = frozen, MS a14). */
+typedef struct { int B, H, W, C, heads, sr, hidden, ptl; } sfk_layer_dims;
+typedef struct {
+  const void *wq, *wkv, *wo, *wsr, *w1, *w2;   /* bf16 shadows: [C,C], [2C,C] (key rows, value rows), [C,C], [C,(ky,kx,c)], [4C,C], [C,4C] */
+  const float *bq, *bkv, *bo, *bsr, *b1, *b2;
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *lnsr_g, *lnsr_b;
+  const float *dw_wt, *dw_b;                   /* depthwise weight tap-major [9][4C], bias [4C] */
+  const float *drop_scale_attn, *drop_scale_mlp; /* per-sample drop-path multipliers mask/keep (MS:95-102) or NULL */
+} sfk_layer_params;
+typedef struct {
+  float *dwq, *dwk, *dwv, *dwo, *dwsr, *dw1, *dw2;   /* same shapes as the nn.Parameters (sr: OIHW) */
+  float *dbq, *dbk, *dbv, *dbo, *dbsr, *db1, *db2;
+  float *dln1_g, *dln1_b, *dln2_g, *dln2_b, *dlnsr_g, *dlnsr_b;
+  float *ddw, *ddb;                                  /* depthwise [4C,1,3,3], [4C] */
+} sfk_layer_grads;
+size_t sfk_layer_saved_bytes(const sfk_layer_dims* dims);
+size_t sfk_layer_scratch_bytes(const sfk_layer_dims* dims);
+int sfk_layer_fwd(const sfk_layer_dims* dims, const sfk_layer_params* params, const float* x, const float* front, float* out,
+                  float* front_out, void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes, sfk_stream_t stream);
+int sfk_layer_bwd(const sfk_layer_dims* dims, const sfk_layer_params* params, const sfk_layer_grads* grads, const float* x,
+                  const float* dout, const float* dfront_out, float* dx, float* dfront, void* saved, size_t saved_bytes,
+                  void* scratch, size_t scratch_bytes, sfk_stream_t stream);
+
+/* ---- decode head (MS:752-782) ------------------------------------------------------------------------------ */
+/* out[b,y,x,ch_off:ch_off+C] = bilinear(in[b,:,:,0:C]) (align_corners=False), bf16 channels-last; and its transpose */
+int sfk_upsample_concat(const void* in, void* out, int B, int h, int w, int C, int H, int W, long long ld_out, int ch_off,
+                        sfk_stream_t stream);
+int sfk_upsample_concat_bwd(const void* dout, void* din, int B, int h, int w, int C, int H, int W, long long ld_out,
+                            int ch_off, sfk_stream_t stream);
+/* out[row,:] (bf16) += vec[row / rows_per_sample, :] (f32): cls_proj broadcast add (MS:720-723) */
+int sfk_add_sample_bias(void* out, const float* vec, long long rows, int rows_per_sample, int C, sfk_stream_t stream);
+/* BatchNorm2d statistics over x bf16 [M, C]: batch mean / rstd (+ running-stat update) or eval-mode stats */
+size_t sfk_bn_stats_workspace_bytes(long long M, int C);
+int sfk_bn_batch_stats(const void* x, long long M, int C, float eps, float momentum, float* mean, float* rstd,
+                       float* running_mean, float* running_var, float* workspace, size_t workspace_bytes,
+                       sfk_stream_t stream);
+int sfk_bn_eval_stats(const float* running_mean, const float* running_var, float eps, float* mean, float* rstd, int C,
+                      sfk_stream_t stream);
+/* logits[b,l,pix] = classifier(dropout(relu(bn(x)))) fused (MS:775-780); x bf16 [B*pix, C]; NL <= 8 */
+int sfk_bn_relu_cls_fwd(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                        const float* wc, const float* bc, float* logits, long long M, int C, int NL, int pix_per_sample,
+                        float drop_p, long long seed, sfk_stream_t stream);
+/* sums: f32 [2][C] (out: dbeta, dgamma); dwc [NL,C] += ; dbc [NL] += ; dx bf16 [M, C] */
+int sfk_bn_relu_cls_bwd(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                        const float* wc, const float* dlogits, float* sums, float* dwc, float* dbc, void* dx, long long M,
+                        int C, int NL, int pix_per_sample, float drop_p, long long seed, int train_stats,
+                        sfk_stream_t stream);
+
+/* ---- wrapper tail + losses (SFM:117-125, LOSS:16-95, MS:853-868) ---------------------------------------------- */
+/* y[p,:,:] = act(bilinear(x[p,:,:])) over `planes` f32 planes; act: 0 none, 1 sigmoid */
+int sfk_upsample_nchw_fwd(const float* x, float* y, long long planes, int h, int w, int H, int W, int act,
+                          sfk_stream_t stream);
+/* dx = bilinear^T(dy * (yact ? yact*(1-yact) : 1)) */
+int sfk_upsample_nchw_bwd(const float* dy, const float* yact, float* dx, long long planes, int h, int w, int H, int W,
+                          int accumulate, sfk_stream_t stream);
+size_t sfk_dice_workspace_bytes(int N);
+/* sums f32 [N,3] = {tp, fp, fn}; loss[0] = 1 - mean_n (2|tp|+s)/(fp+fn+s); target g is i64 or f32 */
+int sfk_dice_fwd(const float* p, long long p_stride, const void* g, int g_is_i64, long long g_stride, int N, long long P,
+                 int hard_threshold, float smooth, float* workspace, float* sums, float* loss, sfk_stream_t stream);
+int sfk_dice_bwd(const float* p, long long p_stride, const void* g, int g_is_i64, long long g_stride, const float* sums,
+                 const float* dloss, float smooth, float* dp, long long dp_stride, int N, long long P, int accumulate,
+                 sfk_stream_t stream);
+size_t sfk_loss_workspace_bytes(void);
+/* out[0] = mean over ALL pixels of BCEWithLogits(z, y) * [y >= 0 && y != ignore] (MS:863-866); out[1] = #valid */
+int sfk_bce_valid_fwd(const float* z, const void* labels_i64, long long ignore_index, long long n, float* workspace,
+                      float* out, sfk_stream_t stream);
+int sfk_bce_valid_bwd(const float* z, const void* labels_i64, long long ignore_index, const float* dloss, float* dz,
+                      long long n, sfk_stream_t stream);
+/* CrossEntropyLoss(ignore_index) over z f32 [N,L,P], labels i64 [N,P]; out[0] = loss, out[1] = #non-ignored */
+int sfk_ce_ignore_fwd(const float* z, const void* labels_i64, long long ignore_index, int N, int L, long long P,
+                      float* workspace, float* out, sfk_stream_t stream);
+int sfk_ce_ignore_bwd(const float* z, const void* labels_i64, long long ignore_index, const float* out, const float* dloss,
+                      float* dz, int N, int L, long long P, sfk_stream_t stream);
+/* out[0] = sum((a-b)^2) / denom  (LOSS:44-54 with denom = N*C*N) */
+int sfk_mse_fwd(const float* a, const float* b, long long n, float denom, float* workspace, float* out, sfk_stream_t stream);
+int sfk_mse_bwd(const float* a, const float* b, const float* dloss, float denom, float* da, float* db, long long n,
+                sfk_stream_t stream);
+
+/* ---- teacher-student glue (TS:24-56, TS:111-114, TS:202-204) ------------------------------------------------- */
+size_t sfk_pseudo_workspace_bytes(int N);
+/* pseudo i64 [N,P] = p >= thr_hi; stats f32 [N,5] = {sum|p|, confidence, #positive, dice_loss_n, keep} */
+int sfk_pseudo_label_threshold(const float* p, void* pseudo_i64, float* stats, int N, long long P, float thr_hi,
+                               float thr_lo, float conf_thr, float min_pixels, int allow_throw, float* workspace,
+                               sfk_stream_t stream);
+int sfk_denoise_labels(const float* t0, const float* gt, float* out, long long n, sfk_stream_t stream);
+
+/* ---- optimiser (SFM:32-37,158-162) and teacher refresh --------------------------------------------------------- */
+/* clip_grad_value_(clip) then Adam with L2 weight decay over flat f32 buffers; step is 1-based */
+int sfk_clip_adam_l2(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, float clip, int step, sfk_stream_t stream);
+/* t = decay*t + (1-decay)*s */
+int sfk_ema_lerp(float* t, const float* s, long long n, float decay, sfk_stream_t stream);
 
 #ifdef __cplusplus
 }

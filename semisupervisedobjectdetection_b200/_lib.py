@@ -69,9 +69,10 @@ def header_prototypes() -> dict:
         text = f.read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     protos = {}
-    for m in re.finditer(r"(const char\*|int|size_t)\s+(sfk_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+    for m in re.finditer(r"(const char\*|int|size_t|long long)\s+(sfk_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
         ret, name, args = m.group(1), m.group(2), m.group(3).strip()
-        restype = ctypes.c_char_p if "char" in ret else (ctypes.c_size_t if ret == "size_t" else ctypes.c_int)
+        restype = (ctypes.c_char_p if "char" in ret else ctypes.c_size_t if ret == "size_t"
+                   else ctypes.c_longlong if ret == "long long" else ctypes.c_int)
         argtypes = [] if args in ("", "void") else [_ctype_of(a) for a in args.split(",")]
         protos[name] = (restype, argtypes)
     return protos

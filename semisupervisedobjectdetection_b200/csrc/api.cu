@@ -111,4 +111,93 @@ int sfk_colsum(const void* x, int x_bf16, long long ld, float* out, long long ro
   return colsum(x, x_bf16, ld, out, rows, C, static_cast<cudaStream_t>(stream));
 }
 
+
+#define ST static_cast<cudaStream_t>(stream)
+int sfk_upsample_concat(const void* in, void* out, int B, int h, int w, int C, int H, int W, long long ld_out, int ch_off,
+                        sfk_stream_t stream) { return upsample_concat(in, out, B, h, w, C, H, W, ld_out, ch_off, ST); }
+int sfk_upsample_concat_bwd(const void* dout, void* din, int B, int h, int w, int C, int H, int W, long long ld_out,
+                            int ch_off, sfk_stream_t stream) {
+  return upsample_concat_bwd(dout, din, B, h, w, C, H, W, ld_out, ch_off, ST);
+}
+int sfk_add_sample_bias(void* out, const float* vec, long long rows, int rows_per_sample, int C, sfk_stream_t stream) {
+  return add_sample_bias(out, vec, rows, rows_per_sample, C, ST);
+}
+size_t sfk_bn_stats_workspace_bytes(long long M, int C) { return bn_stats_workspace_bytes(M, C); }
+int sfk_bn_batch_stats(const void* x, long long M, int C, float eps, float momentum, float* mean, float* rstd,
+                       float* running_mean, float* running_var, float* workspace, size_t workspace_bytes,
+                       sfk_stream_t stream) {
+  return bn_batch_stats(x, M, C, eps, momentum, mean, rstd, running_mean, running_var, workspace, workspace_bytes, ST);
+}
+int sfk_bn_eval_stats(const float* running_mean, const float* running_var, float eps, float* mean, float* rstd, int C,
+                      sfk_stream_t stream) { return bn_eval_stats(running_mean, running_var, eps, mean, rstd, C, ST); }
+int sfk_bn_relu_cls_fwd(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                        const float* wc, const float* bc, float* logits, long long M, int C, int NL, int pix_per_sample,
+                        float drop_p, long long seed, sfk_stream_t stream) {
+  return bn_relu_cls_fwd(x, mean, rstd, gamma, beta, wc, bc, logits, M, C, NL, pix_per_sample, drop_p,
+                         (unsigned long long)seed, ST);
+}
+int sfk_bn_relu_cls_bwd(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta,
+                        const float* wc, const float* dlogits, float* sums, float* dwc, float* dbc, void* dx, long long M,
+                        int C, int NL, int pix_per_sample, float drop_p, long long seed, int train_stats,
+                        sfk_stream_t stream) {
+  return bn_relu_cls_bwd(x, mean, rstd, gamma, beta, wc, dlogits, sums, dwc, dbc, dx, M, C, NL, pix_per_sample, drop_p,
+                         (unsigned long long)seed, train_stats, ST);
+}
+int sfk_upsample_nchw_fwd(const float* x, float* y, long long planes, int h, int w, int H, int W, int act,
+                          sfk_stream_t stream) { return upsample_nchw_fwd(x, y, planes, h, w, H, W, act, ST); }
+int sfk_upsample_nchw_bwd(const float* dy, const float* yact, float* dx, long long planes, int h, int w, int H, int W,
+                          int accumulate, sfk_stream_t stream) {
+  return upsample_nchw_bwd(dy, yact, dx, planes, h, w, H, W, accumulate, ST);
+}
+size_t sfk_dice_workspace_bytes(int N) { return dice_workspace_bytes(N); }
+int sfk_dice_fwd(const float* p, long long p_stride, const void* g, int g_is_i64, long long g_stride, int N, long long P,
+                 int hard_threshold, float smooth, float* workspace, float* sums, float* loss, sfk_stream_t stream) {
+  return dice_fwd(p, p_stride, g, g_is_i64, g_stride, N, P, hard_threshold, smooth, workspace, sums, loss, ST);
+}
+int sfk_dice_bwd(const float* p, long long p_stride, const void* g, int g_is_i64, long long g_stride, const float* sums,
+                 const float* dloss, float smooth, float* dp, long long dp_stride, int N, long long P, int accumulate,
+                 sfk_stream_t stream) {
+  return dice_bwd(p, p_stride, g, g_is_i64, g_stride, sums, dloss, smooth, dp, dp_stride, N, P, accumulate, ST);
+}
+size_t sfk_loss_workspace_bytes(void) { return loss_workspace_bytes(); }
+int sfk_bce_valid_fwd(const float* z, const void* labels_i64, long long ignore_index, long long n, float* workspace,
+                      float* out, sfk_stream_t stream) {
+  return bce_valid_fwd(z, (const long long*)labels_i64, ignore_index, n, workspace, out, ST);
+}
+int sfk_bce_valid_bwd(const float* z, const void* labels_i64, long long ignore_index, const float* dloss, float* dz,
+                      long long n, sfk_stream_t stream) {
+  return bce_valid_bwd(z, (const long long*)labels_i64, ignore_index, dloss, dz, n, ST);
+}
+int sfk_ce_ignore_fwd(const float* z, const void* labels_i64, long long ignore_index, int N, int L, long long P,
+                      float* workspace, float* out, sfk_stream_t stream) {
+  return ce_ignore_fwd(z, (const long long*)labels_i64, ignore_index, N, L, P, workspace, out, ST);
+}
+int sfk_ce_ignore_bwd(const float* z, const void* labels_i64, long long ignore_index, const float* out, const float* dloss,
+                      float* dz, int N, int L, long long P, sfk_stream_t stream) {
+  return ce_ignore_bwd(z, (const long long*)labels_i64, ignore_index, out, dloss, dz, N, L, P, ST);
+}
+int sfk_mse_fwd(const float* a, const float* b, long long n, float denom, float* workspace, float* out, sfk_stream_t stream) {
+  return mse_fwd(a, b, n, denom, workspace, out, ST);
+}
+int sfk_mse_bwd(const float* a, const float* b, const float* dloss, float denom, float* da, float* db, long long n,
+                sfk_stream_t stream) { return mse_bwd(a, b, dloss, denom, da, db, n, ST); }
+size_t sfk_pseudo_workspace_bytes(int N) { return pseudo_workspace_bytes(N); }
+int sfk_pseudo_label_threshold(const float* p, void* pseudo_i64, float* stats, int N, long long P, float thr_hi,
+                               float thr_lo, float conf_thr, float min_pixels, int allow_throw, float* workspace,
+                               sfk_stream_t stream) {
+  return pseudo_label_threshold(p, (long long*)pseudo_i64, stats, N, P, thr_hi, thr_lo, conf_thr, min_pixels, allow_throw,
+                                workspace, ST);
+}
+int sfk_denoise_labels(const float* t0, const float* gt, float* out, long long n, sfk_stream_t stream) {
+  return denoise_labels(t0, gt, out, n, ST);
+}
+int sfk_clip_adam_l2(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                     float eps, float weight_decay, float clip, int step, sfk_stream_t stream) {
+  return clip_adam_l2(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, clip, step, ST);
+}
+int sfk_ema_lerp(float* t, const float* s, long long n, float decay, sfk_stream_t stream) {
+  return ema_lerp(t, s, n, decay, ST);
+}
+#undef ST
+
 }  // extern "C"

@@ -23,6 +23,8 @@ int  check_launch(const char* what);  // returns 0 or negative error, records me
   } while (0)
 
 int num_sms();
+void prof_gemm_begin(double flops, cudaStream_t st);
+void prof_gemm_end(cudaStream_t st);
 
 // ----------------------------------------------------------------------------------------------
 // small device utilities

@@ -398,7 +398,9 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   }
   const long long units = (long long)p.m_tiles * p.n_tiles * p.splits;
   int grid = (int)(units < num_sms() ? units : num_sms());
+  prof_gemm_begin(2.0 * (double)g.M * (double)g.N * (double)g.K, stream);
   gemm_bf16_tcgen05_kernel<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);
+  prof_gemm_end(stream);
   return check_launch("gemm_bf16_tcgen05_kernel");
 }
 

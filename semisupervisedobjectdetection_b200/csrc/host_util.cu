@@ -3,7 +3,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "sfk_internal.h"
@@ -20,7 +22,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static std::atomic<long long> g_launches{0};
+
 int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -101,9 +106,65 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t 
   return 0;
 }
 
+// ---- live per-launch timing of the dominant kernel (bench.py roofline): CUDA events around every GEMM launch ----
+struct ProfState {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // pairs
+  size_t used = 0;
+  double flops = 0.0;
+  long long launches = 0;
+};
+static ProfState g_prof;
+
+void prof_gemm_begin(double flops, cudaStream_t st) {
+  if (!g_prof.on) return;
+  if (g_prof.used + 2 > g_prof.ev.size()) {
+    for (int i = 0; i < 2; ++i) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) { g_prof.on = false; return; }
+      g_prof.ev.push_back(e);
+    }
+  }
+  cudaEventRecord(g_prof.ev[g_prof.used], st);
+  g_prof.flops += flops;
+  g_prof.launches += 1;
+}
+void prof_gemm_end(cudaStream_t st) {
+  if (!g_prof.on) return;
+  cudaEventRecord(g_prof.ev[g_prof.used + 1], st);
+  g_prof.used += 2;
+}
+
 }  // namespace sfk
 
 extern "C" {
+
+long long sfk_launch_count(void) { return sfk::g_launches.load(); }
+
+int sfk_profile_gemm_begin(void) {
+  sfk::g_prof.on = true;
+  sfk::g_prof.used = 0;
+  sfk::g_prof.flops = 0.0;
+  sfk::g_prof.launches = 0;
+  return 0;
+}
+
+/* Synchronises the device, sums the per-launch GEMM durations recorded since sfk_profile_gemm_begin. */
+int sfk_profile_gemm_end(double* total_ms, double* total_flops, long long* launches) {
+  sfk::g_prof.on = false;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { sfk::set_error("profile: sync failed: %s", cudaGetErrorString(e)); return -1; }
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < sfk::g_prof.used; i += 2) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, sfk::g_prof.ev[i], sfk::g_prof.ev[i + 1]) == cudaSuccess) ms += t;
+  }
+  *total_ms = ms;
+  *total_flops = sfk::g_prof.flops;
+  *launches = sfk::g_prof.launches;
+  return 0;
+}
+
 
 const char* sfk_last_error(void) { return sfk::g_err; }
 

@@ -1,0 +1,414 @@
+// One SegformerLayer (MS:320-363) forward / backward as a single host call that enqueues the whole kernel
+// sequence on the caller's stream:
+//   LN1 -> Q | (SR conv -> LN) -> KV -> fused attention -> O-proj (+drop-path, +residual) -> split prompt rows ->
+//   LN2 -> dense1 -> depthwise3x3+GELU -> dense2 (+drop-path, +residual)
+// Prompt / cls rows ("front" rows, MS:446-465) are carried in front of the spatial tokens: T = P + N.
+// The residual stream is fp32, GEMM operands bf16, accumulation fp32.  Activations needed by backward live in a
+// caller-provided `saved` arena; everything else in a reusable `scratch` arena.  Parameter gradients are accumulated
+// straight into the caller's fp32 gradient buffers (split-K red.global.add), there is no separate "+=" pass.
+#include "common.cuh"
+#include "sfk_internal.h"
+#include "../../include/sfk.h"
+
+namespace sfk {
+
+namespace {
+
+struct Arena {
+  uint8_t* base;
+  size_t off = 0, cap;
+  Arena(void* b, size_t c) : base(static_cast<uint8_t*>(b)), cap(c) {}
+  template <typename T> T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+  bool ok() const { return base == nullptr || off <= cap; }
+};
+
+struct Dims {
+  long long B, H, W, C, heads, sr, hidden, P;
+  long long N, T, Nkv, Tk, D;
+};
+
+Dims make_dims(const sfk_layer_dims& d) {
+  Dims x;
+  x.B = d.B; x.H = d.H; x.W = d.W; x.C = d.C; x.heads = d.heads; x.sr = d.sr; x.hidden = d.hidden; x.P = d.ptl;
+  x.N = x.H * x.W;
+  x.T = x.P + x.N;
+  x.Nkv = x.sr > 1 ? (x.H / x.sr) * (x.W / x.sr) : x.N;
+  x.Tk = x.P + x.Nkv;
+  x.D = x.C / x.heads;
+  return x;
+}
+
+struct Saved {
+  float* xcat;      // [B,T,C] fp32 (only when P > 0; otherwise the caller's x is used)
+  float *mean1, *rstd1, *mean2, *rstd2, *mean_sr, *rstd_sr;
+  __nv_bfloat16* xn1;   // [B*T, C]
+  __nv_bfloat16* q;     // [B*T, C]
+  float* sr_out;        // [B*Tk, C] fp32 (sr > 1)
+  __nv_bfloat16* kvn;   // [B*Tk, C] (sr > 1; else aliases xn1)
+  __nv_bfloat16* kv;    // [B*Tk, 2C]
+  __nv_bfloat16* ctx;   // [B*T, C]
+  float* lse;           // [B*heads*T]
+  float* x1;            // [B,T,C] fp32
+  __nv_bfloat16* xn2;   // [B*N, C]
+  __nv_bfloat16* h1;    // [B*N, hidden]
+  __nv_bfloat16* g;     // [B*N, hidden]
+};
+
+Saved carve_saved(Arena& a, const Dims& d) {
+  Saved s;
+  s.xcat = d.P > 0 ? a.take<float>(d.B * d.T * d.C) : nullptr;
+  s.mean1 = a.take<float>(d.B * d.T);
+  s.rstd1 = a.take<float>(d.B * d.T);
+  s.mean2 = a.take<float>(d.B * d.N);
+  s.rstd2 = a.take<float>(d.B * d.N);
+  s.xn1 = a.take<__nv_bfloat16>(d.B * d.T * d.C);
+  s.q = a.take<__nv_bfloat16>(d.B * d.T * d.C);
+  if (d.sr > 1) {
+    s.mean_sr = a.take<float>(d.B * d.Tk);
+    s.rstd_sr = a.take<float>(d.B * d.Tk);
+    s.sr_out = a.take<float>(d.B * d.Tk * d.C);
+    s.kvn = a.take<__nv_bfloat16>(d.B * d.Tk * d.C);
+  } else {
+    s.mean_sr = s.rstd_sr = nullptr;
+    s.sr_out = nullptr;
+    s.kvn = s.xn1;
+  }
+  s.kv = a.take<__nv_bfloat16>(d.B * d.Tk * 2 * d.C);
+  s.ctx = a.take<__nv_bfloat16>(d.B * d.T * d.C);
+  s.lse = a.take<float>(d.B * d.heads * d.T);
+  s.x1 = a.take<float>(d.B * d.T * d.C);
+  s.xn2 = a.take<__nv_bfloat16>(d.B * d.N * d.C);
+  s.h1 = a.take<__nv_bfloat16>(d.B * d.N * d.hidden);
+  s.g = a.take<__nv_bfloat16>(d.B * d.N * d.hidden);
+  return s;
+}
+
+int check_dims(const Dims& d) {
+  SFK_REQUIRE(d.B > 0 && d.H > 0 && d.W > 0 && d.C > 0 && d.heads > 0 && d.hidden > 0 && d.sr >= 1 && d.P >= 0,
+              "layer: bad dims");
+  SFK_REQUIRE(d.C % d.heads == 0 && (d.D == 32 || d.D == 64), "layer: head dim %lld unsupported (32 or 64)", d.D);
+  SFK_REQUIRE(d.C % 8 == 0 && d.hidden % 8 == 0, "layer: C and hidden must be multiples of 8");
+  SFK_REQUIRE(d.sr == 1 || (d.H % d.sr == 0 && d.W % d.sr == 0), "layer: H,W must be divisible by the reduction ratio");
+  return 0;
+}
+
+RowMap spatial_map(const Dims& d) {  // compact spatial row (b*N + t) -> row in a [B, P+N] sequence
+  RowMap m;
+  if (d.P > 0) { m.period = d.N; m.extra = d.P; m.offset = d.P; }
+  return m;
+}
+RowMap front_map(long long P, long long rest) {  // compact front row (b*P + t) -> row in a [B, P+rest] sequence
+  RowMap m;
+  m.period = P; m.extra = rest; m.offset = 0;
+  return m;
+}
+RowMap kv_spatial_map(const Dims& d) {  // compact reduced row (b*Nkv + t) -> row in [B, P+Nkv]
+  RowMap m;
+  if (d.P > 0) { m.period = d.Nkv; m.extra = d.P; m.offset = d.P; }
+  return m;
+}
+
+#define TRY(expr)            \
+  do {                       \
+    int _rc = (expr);        \
+    if (_rc != 0) return _rc; \
+  } while (0)
+
+GemmDesc linear_fwd(const void* a, long long lda, const void* w, long long ldw, long long M, long long N, long long K,
+                    const float* bias, void* out, long long ldo, int out_bf16) {
+  GemmDesc g;
+  g.M = (int)M; g.N = (int)N; g.K = (int)K;
+  g.a = a; g.lda = lda; g.b = w; g.ldb = ldw;
+  g.bias = bias; g.out = out; g.ldo = ldo; g.out_bf16 = out_bf16;
+  return g;
+}
+// dX[M, K_in] = dY[M, N_out] · W[N_out, K_in]
+GemmDesc linear_dgrad(const void* dy, long long lddy, const void* w, long long ldw, long long M, long long n_out, long long k_in,
+                      void* out, long long ldo, int out_bf16) {
+  GemmDesc g;
+  g.M = (int)M; g.N = (int)k_in; g.K = (int)n_out;
+  g.a = dy; g.lda = lddy; g.b = w; g.ldb = ldw; g.b_mn = 1;
+  g.out = out; g.ldo = ldo; g.out_bf16 = out_bf16;
+  return g;
+}
+// dW[N_out, K_in] += dY[tokens, N_out]^T · X[tokens, K_in]
+GemmDesc linear_wgrad(const void* dy, long long lddy, const void* x, long long ldx, long long tokens, long long n_out,
+                      long long k_in, float* dw, long long lddw) {
+  GemmDesc g;
+  g.M = (int)n_out; g.N = (int)k_in; g.K = (int)tokens;
+  g.a = dy; g.lda = lddy; g.a_mn = 1; g.b = x; g.ldb = ldx; g.b_mn = 1;
+  g.out = dw; g.ldo = lddw; g.atomic_add = 1;
+  return g;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+size_t layer_saved_bytes(const sfk_layer_dims& dd) {
+  Dims d = make_dims(dd);
+  Arena a(nullptr, 0);
+  carve_saved(a, d);
+  return a.off + 256;
+}
+
+size_t layer_scratch_bytes(const sfk_layer_dims& dd) {
+  Dims d = make_dims(dd);
+  // generous upper bound covering forward (im2col) and backward temporaries
+  size_t tok = (size_t)d.B * d.T, sp = (size_t)d.B * d.N, kv = (size_t)d.B * d.Tk;
+  size_t b = 0;
+  b += sp * d.hidden * 2 * 3;                 // dg, dpre, dh1
+  b += sp * d.C * 2 * 2;                      // dmlp, dxn2
+  b += tok * d.C * (4 + 2 + 2 + 4 + 2 + 4 + 2 + 4);  // dx1, da, dctx, dq(f32), dq(bf16), dxn1(f32), dxn1 total(bf16), dxcat
+  b += kv * 2 * d.C * (4 + 2);                // dkv f32 + bf16
+  b += kv * d.C * (4 + 2 + 2 + 2);            // dkvn, dsr, dsr compact
+  b += (size_t)d.B * d.heads * d.T * 4;       // delta
+  if (d.sr > 1) b += (size_t)d.B * d.Nkv * d.sr * d.sr * d.C * 2 * 2 + (size_t)d.C * d.sr * d.sr * d.C * 4;  // A_sr, dA_sr, dWsr
+  b += (size_t)10 * d.hidden * 4;             // depthwise weight-grad staging
+  return b + 64 * 256;
+}
+
+// ------------------------------------------------------------------------------------------------
+int layer_forward(const sfk_layer_dims& dd, const sfk_layer_params& p, const float* x, const float* front, float* out,
+                  float* front_out, void* saved_buf, size_t saved_bytes, void* scratch_buf, size_t scratch_bytes,
+                  cudaStream_t st) {
+  const Dims d = make_dims(dd);
+  TRY(check_dims(d));
+  SFK_REQUIRE((d.P > 0) == (front != nullptr), "layer_forward: front rows must be given iff ptl > 0");
+  Arena sa(saved_buf, saved_bytes);
+  Saved s = carve_saved(sa, d);
+  SFK_REQUIRE(sa.off <= saved_bytes, "layer_forward: saved arena too small (%zu < %zu)", saved_bytes, sa.off);
+  Arena sc(scratch_buf, scratch_bytes);
+  const long long C = d.C, rows_all = d.B * d.T, rows_sp = d.B * d.N, rows_kv = d.B * d.Tk;
+  const RowMap id;
+
+  const float* xcat = x;
+  if (d.P > 0) {
+    TRY(concat_front(front, d.P * C, x, s.xcat, (int)d.B, (int)d.P, (int)d.N, (int)C, st));
+    xcat = s.xcat;
+  }
+  // LN1 over all rows
+  TRY(layernorm_fwd(xcat, 0, id, p.ln1_g, p.ln1_b, s.xn1, 1, s.mean1, s.rstd1, rows_all, (int)C, 1e-5f, st));
+  // Q
+  TRY(gemm_bf16(linear_fwd(s.xn1, C, p.wq, C, rows_all, C, C, p.bq, s.q, C, 1), st));
+  // spatial reduction
+  if (d.sr > 1) {
+    const long long Ksr = d.sr * d.sr * C;
+    __nv_bfloat16* A = sc.take<__nv_bfloat16>(d.B * d.Nkv * Ksr);
+    SFK_REQUIRE(sc.off <= scratch_bytes, "layer_forward: scratch arena too small");
+    TRY(im2col_nhwc(s.xn1, A, (int)d.B, (int)d.H, (int)d.W, (int)C, (int)d.sr, (int)d.sr, 0, d.T, d.P, st));
+    GemmDesc g = linear_fwd(A, Ksr, p.wsr, Ksr, d.B * d.Nkv, C, Ksr, p.bsr, s.sr_out, C, 0);
+    g.out_map = kv_spatial_map(d);
+    TRY(gemm_bf16(g, st));
+    if (d.P > 0)  // prompt rows bypass the conv but do go through the SR LayerNorm (MS:194-205)
+      TRY(scale_cast(s.xn1, 1, front_map(d.P, d.N), s.sr_out, 0, front_map(d.P, d.Nkv), nullptr, 1, d.B * d.P, (int)C, st));
+    TRY(layernorm_fwd(s.sr_out, 0, id, p.lnsr_g, p.lnsr_b, s.kvn, 1, s.mean_sr, s.rstd_sr, rows_kv, (int)C, 1e-5f, st));
+  }
+  // K | V in one GEMM
+  TRY(gemm_bf16(linear_fwd(s.kvn, C, p.wkv, C, rows_kv, 2 * C, C, p.bkv, s.kv, 2 * C, 1), st));
+  // fused attention
+  {
+    AttentionDesc a;
+    a.B = (int)d.B; a.heads = (int)d.heads; a.T = (int)d.T; a.Tk = (int)d.Tk; a.D = (int)d.D;
+    a.scale = 1.0f / sqrtf((float)d.D);
+    a.q = s.q; a.ldq = C; a.q_batch_stride = d.T * C;
+    a.k = s.kv; a.v = s.kv + C; a.ldkv = 2 * C; a.kv_batch_stride = d.Tk * 2 * C;
+    a.o = s.ctx; a.ldo = C; a.o_batch_stride = d.T * C; a.lse = s.lse;
+    TRY(attention_fwd(a, st));
+  }
+  // output projection + drop-path + residual (MS:346-351)
+  {
+    GemmDesc g = linear_fwd(s.ctx, C, p.wo, C, rows_all, C, C, p.bo, s.x1, C, 0);
+    g.residual = xcat; g.ldr = C;
+    g.row_scale = p.drop_scale_attn; g.rows_per_scale = (int)d.T;
+    TRY(gemm_bf16(g, st));
+  }
+  // LN2 on the spatial rows only (MS:352-355)
+  TRY(layernorm_fwd(s.x1, 0, spatial_map(d), p.ln2_g, p.ln2_b, s.xn2, 1, s.mean2, s.rstd2, rows_sp, (int)C, 1e-5f, st));
+  // MixFFN
+  TRY(gemm_bf16(linear_fwd(s.xn2, C, p.w1, C, rows_sp, d.hidden, C, p.b1, s.h1, d.hidden, 1), st));
+  TRY(dwconv3x3(s.h1, p.dw_wt, p.dw_b, s.g, (int)d.B, (int)d.H, (int)d.W, (int)d.hidden, 0, st));
+  {
+    GemmDesc g = linear_fwd(s.g, d.hidden, p.w2, d.hidden, rows_sp, C, d.hidden, p.b2, out, C, 0);
+    g.residual = s.x1; g.ldr = C; g.res_map = spatial_map(d);
+    g.row_scale = p.drop_scale_mlp; g.rows_per_scale = (int)d.N;
+    TRY(gemm_bf16(g, st));
+  }
+  if (d.P > 0 && front_out != nullptr)
+    TRY(scale_cast(s.x1, 0, front_map(d.P, d.N), front_out, 0, id, nullptr, 1, d.B * d.P, (int)C, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sfk_layer_grads& gr, const float* x,
+                   const float* dout, const float* dfront_out, float* dx, float* dfront, void* saved_buf, size_t saved_bytes,
+                   void* scratch_buf, size_t scratch_bytes, cudaStream_t st) {
+  const Dims d = make_dims(dd);
+  TRY(check_dims(d));
+  Arena sa(saved_buf, saved_bytes);
+  Saved s = carve_saved(sa, d);
+  SFK_REQUIRE(sa.off <= saved_bytes, "layer_backward: saved arena too small");
+  Arena sc(scratch_buf, scratch_bytes);
+  const long long C = d.C, Hd = d.hidden, rows_all = d.B * d.T, rows_sp = d.B * d.N, rows_kv = d.B * d.Tk;
+  const RowMap id;
+  const float* xcat = d.P > 0 ? s.xcat : x;
+
+  __nv_bfloat16* dmlp = sc.take<__nv_bfloat16>(rows_sp * C);
+  __nv_bfloat16* dg = sc.take<__nv_bfloat16>(rows_sp * Hd);
+  __nv_bfloat16* dpre = sc.take<__nv_bfloat16>(rows_sp * Hd);
+  __nv_bfloat16* dh1 = sc.take<__nv_bfloat16>(rows_sp * Hd);
+  __nv_bfloat16* dxn2 = sc.take<__nv_bfloat16>(rows_sp * C);
+  float* dx1 = sc.take<float>(rows_all * C);
+  __nv_bfloat16* da = sc.take<__nv_bfloat16>(rows_all * C);
+  __nv_bfloat16* dctx = sc.take<__nv_bfloat16>(rows_all * C);
+  float* dq32 = sc.take<float>(rows_all * C);
+  __nv_bfloat16* dq16 = sc.take<__nv_bfloat16>(rows_all * C);
+  float* dkv32 = sc.take<float>(rows_kv * 2 * C);
+  __nv_bfloat16* dkv16 = sc.take<__nv_bfloat16>(rows_kv * 2 * C);
+  float* delta = sc.take<float>(d.B * d.heads * d.T);
+  float* dxn1 = sc.take<float>(rows_all * C);
+  __nv_bfloat16* dxn1t = sc.take<__nv_bfloat16>(rows_all * C);
+  float* dw_stage = sc.take<float>(10 * Hd);
+  SFK_REQUIRE(sc.off <= scratch_bytes, "layer_backward: scratch arena too small (%zu < %zu)", scratch_bytes, sc.off);
+
+  // ---- MixFFN branch ----
+  TRY(scale_cast(dout, 0, id, dmlp, 1, id, p.drop_scale_mlp, (int)d.N, rows_sp, (int)C, st));
+  TRY(gemm_bf16(linear_dgrad(dmlp, C, p.w2, Hd, rows_sp, C, Hd, dg, Hd, 1), st));
+  if (gr.dw2) TRY(gemm_bf16(linear_wgrad(dmlp, C, s.g, Hd, rows_sp, C, Hd, gr.dw2, Hd), st));
+  if (gr.db2) TRY(colsum(dmlp, 1, C, gr.db2, rows_sp, (int)C, st));
+  {
+    const bool want = gr.ddw != nullptr;
+    if (want) {
+      cudaError_t e = cudaMemsetAsync(dw_stage, 0, (size_t)9 * Hd * sizeof(float), st);
+      SFK_REQUIRE(e == cudaSuccess, "layer_backward: memset failed");
+    }
+    // depthwise bias gradient accumulates straight into the parameter gradient; the weight goes through a tap-major stage
+    TRY(dwconv3x3_gelu_bwd(s.h1, p.dw_wt, p.dw_b, dg, dpre, want ? dw_stage : nullptr, want ? gr.ddb : nullptr, (int)d.B,
+                           (int)d.H, (int)d.W, (int)Hd, st));
+    if (want) TRY(dw_wgrad_from_tap(dw_stage, gr.ddw, (int)Hd, st));
+  }
+  TRY(dwconv3x3(dpre, p.dw_wt, nullptr, dh1, (int)d.B, (int)d.H, (int)d.W, (int)Hd, 1, st));
+  TRY(gemm_bf16(linear_dgrad(dh1, Hd, p.w1, C, rows_sp, Hd, C, dxn2, C, 1), st));
+  if (gr.dw1) TRY(gemm_bf16(linear_wgrad(dh1, Hd, s.xn2, C, rows_sp, Hd, C, gr.dw1, C), st));
+  if (gr.db1) TRY(colsum(dh1, 1, Hd, gr.db1, rows_sp, (int)Hd, st));
+  // LN2 backward + residual gradient -> dx1 (spatial rows); front rows of dx1 come from the returned cls/prompt rows
+  TRY(layernorm_bwd(dxn2, 1, s.x1, 0, spatial_map(d), s.mean2, s.rstd2, p.ln2_g, dout, id, dx1, 0, spatial_map(d), gr.dln2_g,
+                    gr.dln2_b, rows_sp, (int)C, st));
+  if (d.P > 0) {
+    if (dfront_out != nullptr) {
+      TRY(scale_cast(dfront_out, 0, id, dx1, 0, front_map(d.P, d.N), nullptr, 1, d.B * d.P, (int)C, st));
+    } else {
+      for (long long b = 0; b < d.B; ++b) {
+        cudaError_t e = cudaMemsetAsync(dx1 + b * d.T * C, 0, (size_t)d.P * C * sizeof(float), st);
+        SFK_REQUIRE(e == cudaSuccess, "layer_backward: memset failed");
+      }
+    }
+  }
+  // ---- attention branch ----
+  TRY(scale_cast(dx1, 0, id, da, 1, id, p.drop_scale_attn, (int)d.T, rows_all, (int)C, st));
+  TRY(gemm_bf16(linear_dgrad(da, C, p.wo, C, rows_all, C, C, dctx, C, 1), st));
+  if (gr.dwo) TRY(gemm_bf16(linear_wgrad(da, C, s.ctx, C, rows_all, C, C, gr.dwo, C), st));
+  if (gr.dbo) TRY(colsum(da, 1, C, gr.dbo, rows_all, (int)C, st));
+  {
+    cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)rows_all * C * sizeof(float), st);
+    SFK_REQUIRE(e == cudaSuccess, "layer_backward: memset failed");
+    e = cudaMemsetAsync(dkv32, 0, (size_t)rows_kv * 2 * C * sizeof(float), st);
+    SFK_REQUIRE(e == cudaSuccess, "layer_backward: memset failed");
+    AttentionBwdDesc a;
+    a.B = (int)d.B; a.heads = (int)d.heads; a.T = (int)d.T; a.Tk = (int)d.Tk; a.D = (int)d.D;
+    a.scale = 1.0f / sqrtf((float)d.D);
+    a.q = s.q; a.ldq = C; a.q_batch_stride = d.T * C;
+    a.k = s.kv; a.v = s.kv + C; a.ldkv = 2 * C; a.kv_batch_stride = d.Tk * 2 * C;
+    a.o = s.ctx; a.ldo = C; a.o_batch_stride = d.T * C; a.lse = s.lse;
+    a.dO = dctx; a.delta = delta;
+    a.dq = dq32; a.ld_dq = C; a.dq_batch_stride = d.T * C;
+    a.dk = dkv32; a.dv = dkv32 + C; a.ld_dkv = 2 * C; a.dkv_batch_stride = d.Tk * 2 * C;
+    TRY(attention_bwd(a, st));
+    TRY(scale_cast(dq32, 0, id, dq16, 1, id, nullptr, 1, rows_all, (int)C, st));
+    TRY(scale_cast(dkv32, 0, id, dkv16, 1, id, nullptr, 1, rows_kv, (int)(2 * C), st));
+  }
+  // K | V projections
+  if (gr.dwk) TRY(gemm_bf16(linear_wgrad(dkv16, 2 * C, s.kvn, C, rows_kv, C, C, gr.dwk, C), st));
+  if (gr.dwv) TRY(gemm_bf16(linear_wgrad(dkv16 + C, 2 * C, s.kvn, C, rows_kv, C, C, gr.dwv, C), st));
+  if (gr.dbk) TRY(colsum(dkv16, 1, 2 * C, gr.dbk, rows_kv, (int)C, st));
+  if (gr.dbv) TRY(colsum(dkv16 + C, 1, 2 * C, gr.dbv, rows_kv, (int)C, st));
+  if (d.sr > 1) {
+    const long long Ksr = d.sr * d.sr * C, rows_red = d.B * d.Nkv;
+    __nv_bfloat16* dkvn = sc.take<__nv_bfloat16>(rows_kv * C);
+    __nv_bfloat16* dsr = sc.take<__nv_bfloat16>(rows_kv * C);
+    __nv_bfloat16* dsr_c = d.P > 0 ? sc.take<__nv_bfloat16>(rows_red * C) : nullptr;
+    __nv_bfloat16* A = sc.take<__nv_bfloat16>(rows_red * Ksr);
+    __nv_bfloat16* dA = sc.take<__nv_bfloat16>(rows_red * Ksr);
+    float* dwsr = sc.take<float>(C * Ksr);
+    SFK_REQUIRE(sc.off <= scratch_bytes, "layer_backward: scratch arena too small (%zu < %zu)", scratch_bytes, sc.off);
+    TRY(gemm_bf16(linear_dgrad(dkv16, 2 * C, p.wkv, C, rows_kv, 2 * C, C, dkvn, C, 1), st));
+    TRY(layernorm_bwd(dkvn, 1, s.sr_out, 0, id, s.mean_sr, s.rstd_sr, p.lnsr_g, nullptr, id, dsr, 1, id, gr.dlnsr_g, gr.dlnsr_b,
+                      rows_kv, (int)C, st));
+    const __nv_bfloat16* dsr_sp = dsr;
+    if (d.P > 0) {
+      TRY(scale_cast(dsr, 1, kv_spatial_map(d), dsr_c, 1, id, nullptr, 1, rows_red, (int)C, st));
+      dsr_sp = dsr_c;
+      // prompt rows feed LN1's output gradient directly
+      TRY(scale_cast(dsr, 1, front_map(d.P, d.Nkv), dxn1, 0, front_map(d.P, d.N), nullptr, 1, d.B * d.P, (int)C, st));
+    }
+    TRY(gemm_bf16(linear_dgrad(dsr_sp, C, p.wsr, Ksr, rows_red, C, Ksr, dA, Ksr, 1), st));
+    TRY(col2im_nhwc(dA, dxn1, (int)d.B, (int)d.H, (int)d.W, (int)C, (int)d.sr, (int)d.sr, 0, d.T, d.P, 0, st));
+    if (gr.dwsr) {
+      cudaError_t e = cudaMemsetAsync(dwsr, 0, (size_t)C * Ksr * sizeof(float), st);
+      SFK_REQUIRE(e == cudaSuccess, "layer_backward: memset failed");
+      TRY(im2col_nhwc(s.xn1, A, (int)d.B, (int)d.H, (int)d.W, (int)C, (int)d.sr, (int)d.sr, 0, d.T, d.P, st));
+      TRY(gemm_bf16(linear_wgrad(dsr_sp, C, A, Ksr, rows_red, C, Ksr, dwsr, Ksr), st));
+      TRY(conv_wgrad_ohwi_to_oihw(dwsr, gr.dwsr, (int)C, (int)C, (int)d.sr, (int)d.sr, Ksr, st));
+    }
+    if (gr.dbsr) TRY(colsum(dsr_sp, 1, C, gr.dbsr, rows_red, (int)C, st));
+  } else {
+    TRY(gemm_bf16(linear_dgrad(dkv16, 2 * C, p.wkv, C, rows_kv, 2 * C, C, dxn1, C, 0), st));
+  }
+  // Q projection: dxn1_total = dq · Wq + dxn1
+  {
+    GemmDesc g = linear_dgrad(dq16, C, p.wq, C, rows_all, C, C, dxn1t, C, 1);
+    g.residual = dxn1; g.ldr = C;
+    TRY(gemm_bf16(g, st));
+  }
+  if (gr.dwq) TRY(gemm_bf16(linear_wgrad(dq16, C, s.xn1, C, rows_all, C, C, gr.dwq, C), st));
+  if (gr.dbq) TRY(colsum(dq16, 1, C, gr.dbq, rows_all, (int)C, st));
+  // LN1 backward + residual gradient
+  if (d.P == 0) {
+    TRY(layernorm_bwd(dxn1t, 1, xcat, 0, id, s.mean1, s.rstd1, p.ln1_g, dx1, id, dx, 0, id, gr.dln1_g, gr.dln1_b, rows_all, (int)C,
+                      st));
+  } else {
+    float* dxcat = sc.take<float>(rows_all * C);
+    SFK_REQUIRE(sc.off <= scratch_bytes, "layer_backward: scratch arena too small (%zu < %zu)", scratch_bytes, sc.off);
+    TRY(layernorm_bwd(dxn1t, 1, xcat, 0, id, s.mean1, s.rstd1, p.ln1_g, dx1, id, dxcat, 0, id, gr.dln1_g, gr.dln1_b, rows_all,
+                      (int)C, st));
+    TRY(scale_cast(dxcat, 0, spatial_map(d), dx, 0, id, nullptr, 1, rows_sp, (int)C, st));
+    if (dfront != nullptr) TRY(scale_cast(dxcat, 0, front_map(d.P, d.N), dfront, 0, id, nullptr, 1, d.B * d.P, (int)C, st));
+  }
+  return 0;
+}
+
+}  // namespace sfk
+
+extern "C" {
+
+size_t sfk_layer_saved_bytes(const sfk_layer_dims* dims) { return sfk::layer_saved_bytes(*dims); }
+size_t sfk_layer_scratch_bytes(const sfk_layer_dims* dims) { return sfk::layer_scratch_bytes(*dims); }
+
+int sfk_layer_fwd(const sfk_layer_dims* dims, const sfk_layer_params* params, const float* x, const float* front, float* out,
+                  float* front_out, void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes, sfk_stream_t stream) {
+  return sfk::layer_forward(*dims, *params, x, front, out, front_out, saved, saved_bytes, scratch, scratch_bytes,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int sfk_layer_bwd(const sfk_layer_dims* dims, const sfk_layer_params* params, const sfk_layer_grads* grads, const float* x,
+                  const float* dout, const float* dfront_out, float* dx, float* dfront, void* saved, size_t saved_bytes,
+                  void* scratch, size_t scratch_bytes, sfk_stream_t stream) {
+  return sfk::layer_backward(*dims, *params, *grads, x, dout, dfront_out, dx, dfront, saved, saved_bytes, scratch, scratch_bytes,
+                             static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

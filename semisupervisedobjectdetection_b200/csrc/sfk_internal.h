@@ -96,4 +96,54 @@ int cast_2d(const float* src, long long lds, void* dst, long long ldd, long long
 int dw_weight_to_tap(const float* w, float* wt, int C, cudaStream_t stream);
 int dw_wgrad_from_tap(const float* dwt, float* dw, int C, cudaStream_t stream);
 
+
+// ---- decode.cu ----
+int upsample_concat(const void* in, void* out, int B, int h, int w, int C, int H, int W, long long ld_out, int ch_off,
+                    cudaStream_t stream);
+int upsample_concat_bwd(const void* dout, void* din, int B, int h, int w, int C, int H, int W, long long ld_out, int ch_off,
+                        cudaStream_t stream);
+int add_sample_bias(void* out, const float* vec, long long rows, int rows_per_sample, int C, cudaStream_t stream);
+size_t bn_stats_workspace_bytes(long long M, int C);
+int bn_batch_stats(const void* x, long long M, int C, float eps, float momentum, float* mean, float* rstd, float* running_mean,
+                   float* running_var, float* workspace, size_t workspace_bytes, cudaStream_t stream);
+int bn_eval_stats(const float* rm, const float* rv, float eps, float* mean, float* rstd, int C, cudaStream_t stream);
+int bn_relu_cls_fwd(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta, const float* wc,
+                    const float* bc, float* logits, long long M, int C, int NL, int pix_per_sample, float drop_p,
+                    unsigned long long seed, cudaStream_t stream);
+int bn_relu_cls_bwd(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta, const float* wc,
+                    const float* dlogits, float* sums, float* dwc, float* dbc, void* dx, long long M, int C, int NL,
+                    int pix_per_sample, float drop_p, unsigned long long seed, int train_stats, cudaStream_t stream);
+
+// ---- loss.cu ----
+int upsample_nchw_fwd(const float* x, float* y, long long planes, int h, int w, int H, int W, int act, cudaStream_t stream);
+int upsample_nchw_bwd(const float* dy, const float* yact, float* dx, long long planes, int h, int w, int H, int W,
+                      int accumulate, cudaStream_t stream);
+size_t dice_workspace_bytes(int N);
+int dice_fwd(const float* p, long long p_stride, const void* g, int g_is_i64, long long g_stride, int N, long long P,
+             int hard_threshold, float smooth, float* workspace, float* sums, float* loss, cudaStream_t stream);
+int dice_bwd(const float* p, long long p_stride, const void* g, int g_is_i64, long long g_stride, const float* sums,
+             const float* dloss, float smooth, float* dp, long long dp_stride, int N, long long P, int accumulate,
+             cudaStream_t stream);
+size_t loss_workspace_bytes();
+int bce_valid_fwd(const float* z, const long long* labels, long long ignore_index, long long n, float* workspace, float* out,
+                  cudaStream_t stream);
+int bce_valid_bwd(const float* z, const long long* labels, long long ignore_index, const float* dloss, float* dz, long long n,
+                  cudaStream_t stream);
+int ce_ignore_fwd(const float* z, const long long* labels, long long ignore_index, int N, int L, long long P, float* workspace,
+                  float* out, cudaStream_t stream);
+int ce_ignore_bwd(const float* z, const long long* labels, long long ignore_index, const float* out, const float* dloss,
+                  float* dz, int N, int L, long long P, cudaStream_t stream);
+int mse_fwd(const float* a, const float* b, long long n, float denom, float* workspace, float* out, cudaStream_t stream);
+int mse_bwd(const float* a, const float* b, const float* dloss, float denom, float* da, float* db, long long n,
+            cudaStream_t stream);
+size_t pseudo_workspace_bytes(int N);
+int pseudo_label_threshold(const float* p, long long* pseudo, float* stats, int N, long long P, float thr_hi, float thr_lo,
+                           float conf_thr, float min_pixels, int allow_throw, float* workspace, cudaStream_t stream);
+int denoise_labels(const float* t0, const float* gt, float* out, long long n, cudaStream_t stream);
+
+// ---- optim.cu ----
+int clip_adam_l2(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                 float wd, float clip, int step, cudaStream_t stream);
+int ema_lerp(float* t, const float* s, long long n, float decay, cudaStream_t stream);
+
 }  // namespace sfk

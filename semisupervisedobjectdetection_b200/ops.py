@@ -1,0 +1,149 @@
+"""Host-side glue between PyTorch tensors and the libsfk C-ABI.
+
+PyTorch provides device memory, streams and the autograd graph; every arithmetic kernel is in libsfk.so.  Nothing here
+falls back to PyTorch math: a missing library or a non-sm_100 device raises (see _lib.ensure_device).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+# ---------------------------------------------------------------------------------------------------------------
+# workspaces
+# ---------------------------------------------------------------------------------------------------------------
+_scratch: dict = {}
+WEIGHT_EPOCH = 0  # bumped whenever libsfk writes parameters in place (optimiser step, EMA), invalidating bf16 shadows
+LAUNCHES = 0      # number of libsfk entry-point calls (each enqueues >= 1 kernel); bench.py reports it
+
+
+def bump_weight_epoch() -> None:
+    global WEIGHT_EPOCH
+    WEIGHT_EPOCH += 1
+
+
+def lib():
+    L.ensure_device()
+    return L.load()
+
+
+def call(fn_name: str, *args) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
+    rc = getattr(lib(), fn_name)(*args)
+    if rc != 0:
+        raise L.SfkError(f"{fn_name} failed (rc={rc}): {L.last_error()}")
+
+
+def scratch(nbytes: int, device: torch.device, slot: str = "main") -> torch.Tensor:
+    """Reusable byte arena (grows on demand). Safe because all libsfk work of a process is ordered on one stream."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
+    buf = _scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        _scratch[key] = buf
+    return buf
+
+
+def stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise L.SfkError(f"{name}: expected a CUDA tensor (libsfk has no CPU path)")
+    if t.dtype != dtype:
+        raise L.SfkError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def grad_buffer(p: torch.nn.Parameter) -> Optional[torch.Tensor]:
+    """fp32 gradient buffer the wgrad kernels accumulate into (None when the parameter is frozen)."""
+    if not p.requires_grad:
+        return None
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    p._sfk_live = True  # FusedClipAdam only updates parameters whose gradient was produced (Adam skips grad=None)
+    return p.grad
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# raw (non-autograd) wrappers used by the modules
+# ---------------------------------------------------------------------------------------------------------------
+def gemm(a, b, M, N, K, *, lda=None, ldb=None, a_mn=0, b_mn=0, alpha=1.0, bias=None, residual=None, ldr=0, row_scale=None,
+         rows_per_scale=1, out=None, ldo=None, out_bf16=True, atomic_add=False, relu=False, splits=0, block_n=0):
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    call("sfk_gemm_bf16", _p(a), lda if lda is not None else a.stride(0), a_mn, _p(b), ldb if ldb is not None else b.stride(0),
+         b_mn, M, N, K, alpha, _p(bias), _p(residual), ldr, _p(row_scale), rows_per_scale, _p(out),
+         ldo if ldo is not None else out.stride(0), int(out_bf16), int(atomic_add), int(relu), splits, block_n, stream())
+    return out
+
+
+def cast_bf16(src: torch.Tensor, cols_padded: Optional[int] = None) -> torch.Tensor:
+    """fp32 [rows, cols] -> bf16 [rows, cols_padded] (zero padded)."""
+    src2 = src.reshape(src.shape[0], -1)
+    rows, cols = src2.shape
+    cp = cols_padded or cols
+    dst = torch.empty(rows, cp, device=src.device, dtype=torch.bfloat16)
+    call("sfk_cast_2d", _p(src2), src2.stride(0), _p(dst), cp, rows, cols, cp, stream())
+    return dst
+
+
+def layernorm_fwd(x, gamma, beta, out_bf16=True, need_stats=True, eps=1e-5):
+    rows, C = x.numel() // x.shape[-1], x.shape[-1]
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32) if need_stats else None
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32) if need_stats else None
+    call("sfk_layernorm_fwd", _p(x), int(x.dtype == torch.bfloat16), 0, 0, 0, _p(gamma), _p(beta), _p(y), int(out_bf16), _p(mean),
+         _p(rstd), rows, C, eps, stream())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dgamma, dbeta, dres=None, out_bf16=False):
+    rows, C = x.numel() // x.shape[-1], x.shape[-1]
+    dx = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)
+    call("sfk_layernorm_bwd", _p(dy), int(dy.dtype == torch.bfloat16), _p(x), int(x.dtype == torch.bfloat16), _p(mean), _p(rstd),
+         _p(gamma), _p(dres), _p(dx), int(out_bf16), _p(dgamma), _p(dbeta), rows, C, stream())
+    return dx
+
+
+def colsum_into(x: torch.Tensor, out: torch.Tensor, rows: int, C: int, ld: Optional[int] = None):
+    call("sfk_colsum", _p(x), int(x.dtype == torch.bfloat16), ld if ld is not None else C, _p(out), rows, C, stream())
+
+
+def scale_cast(x: torch.Tensor, out_dtype, scale=None, rows_per_scale=1):
+    C = x.shape[-1]
+    rows = x.numel() // C
+    y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
+    call("sfk_scale_cast", _p(x), int(x.dtype == torch.bfloat16), _p(y), int(out_dtype == torch.bfloat16), _p(scale), rows_per_scale,
+         rows, C, stream())
+    return y
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ctypes mirrors of the structs in include/sfk.h
+# ---------------------------------------------------------------------------------------------------------------
+class LayerDims(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in ("B", "H", "W", "C", "heads", "sr", "hidden", "ptl")]
+
+
+_PARAM_FIELDS = ("wq", "wkv", "wo", "wsr", "w1", "w2", "bq", "bkv", "bo", "bsr", "b1", "b2", "ln1_g", "ln1_b", "ln2_g", "ln2_b",
+                 "lnsr_g", "lnsr_b", "dw_wt", "dw_b", "drop_scale_attn", "drop_scale_mlp")
+_GRAD_FIELDS = ("dwq", "dwk", "dwv", "dwo", "dwsr", "dw1", "dw2", "dbq", "dbk", "dbv", "dbo", "dbsr", "db1", "db2", "dln1_g",
+                "dln1_b", "dln2_g", "dln2_b", "dlnsr_g", "dlnsr_b", "ddw", "ddb")
+
+
+class LayerParams(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in _PARAM_FIELDS]
+
+
+class LayerGrads(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in _GRAD_FIELDS]

@@ -1,0 +1,128 @@
+"""Teacher-student glue of main_segformer/segFormer_semi_teacherstudent_main.py (TS) on libsfk kernels:
+threshold_pseudo_masks (TS:24-56), the denoise-label trick (TS:110-118), the loss mix (TS:125-126), the reference-faithful
+labeled / unlabeled iterations (TS:80-127) and the north-star EMA-teacher step (teacher <- d*teacher + (1-d)*student;
+d = 0 reproduces the hard reset of TS:202-204).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import loss as myLoss
+from . import ops
+from .optim import ema_update
+
+PESUDO_MAKS_THRESHOLD = 0.7  # (sic) TS:18
+CONFIDENT_THRESHOLD = 0.7    # TS:19
+
+loss_func = myLoss.SegmentationLoss(1, loss_type='dice', activation='none')  # TS:253
+
+
+def pseudo_label_stats(masks: torch.Tensor, allow_throw_sample: bool = True, threshold: Optional[float] = None,
+                       confident_threshold: Optional[float] = None):
+    """Device part of threshold_pseudo_masks: returns (pseudo int64 [N,...], stats f32 [N,5]) with
+    stats[n] = {sum|p|, confidence, #(p >= thr), per-sample Dice loss against its own pseudo mask, keep flag}."""
+    thr = PESUDO_MAKS_THRESHOLD if threshold is None else threshold
+    cthr = CONFIDENT_THRESHOLD if confident_threshold is None else confident_threshold
+    masks = ops._chk(masks.detach(), torch.float32, "probabilities")
+    N = masks.shape[0]
+    P = masks[0].numel()
+    pseudo = torch.empty(masks.shape, device=masks.device, dtype=torch.int64)
+    stats = torch.empty(N, 5, device=masks.device, dtype=torch.float32)
+    lib = ops.lib()
+    ws = ops.scratch(lib.sfk_pseudo_workspace_bytes(N), masks.device, "loss")
+    # comparisons run in fp32 against float32(thr) and float32(1 - thr) (1 - thr evaluated in double first), like torch
+    ops.call("sfk_pseudo_label_threshold", masks.data_ptr(), pseudo.data_ptr(), stats.data_ptr(), N, P, float(thr), float(1 - thr),
+             float(cthr), 1000.0, int(allow_throw_sample), ws.data_ptr(), ops.stream())
+    return pseudo, stats
+
+
+def threshold_pseudo_masks(img, masks, allow_throw_sample=True):
+    """TS:24-56. Returns (confident_img | None, confident_mask (int64) | None, confident_predicted | [], confidence [N],
+    mean per-sample Dice loss).  One host read of the N keep flags replaces the reference's 2N per-sample syncs."""
+    pseudo, stats = pseudo_label_stats(masks, allow_throw_sample)
+    confidence = stats[:, 1].clone()
+    keep = stats[:, 4] > 0.5
+    idx = torch.nonzero(keep).flatten()
+    if idx.numel() == 0:
+        return None, None, [], confidence, torch.tensor(float("nan"), device=masks.device)
+    mean_loss = stats[idx, 3].sum() / idx.numel()
+    mean_loss.requires_grad_(True)  # the reference's accumulator is a requires_grad leaf copy (TS:41); grads reach nothing (M10)
+    return img[idx], pseudo[idx], masks[idx], confidence, mean_loss
+
+
+def denoise_teacher_probs(teacher_probs: torch.Tensor, ground_truth: torch.Tensor) -> torch.Tensor:
+    """TS:111-114: clamp(t + 0.2*gt - 0.1, 0, 1)."""
+    t = ops._chk(teacher_probs.detach(), torch.float32, "teacher probabilities")
+    g = ops._chk(ground_truth, torch.float32, "ground truth")
+    out = torch.empty_like(t)
+    ops.call("sfk_denoise_labels", t.data_ptr(), g.data_ptr(), out.data_ptr(), t.numel(), ops.stream())
+    return out
+
+
+def unlabeled_iteration(teacher, img, train_teacher: bool = False):
+    """TS:80-95. Teacher forward under no_grad, thresholding, optional (weight-neutral, M10) teacher step."""
+    with torch.no_grad():
+        img = img.to(device=teacher.device, dtype=torch.float32)
+        predicted = teacher.predict(img)
+    out = threshold_pseudo_masks(img, predicted)
+    if out[0] is not None and train_teacher:
+        teacher.train_from_loss(out[4])
+    return out
+
+
+def labeled_iteration(teacher, student, img, ground_truth, supervise_weight: float = 0.8, denoise_label: bool = True):
+    """TS:99-127: teacher fwd+bwd+Adam on its denoised pseudo labels, then student fwd+bwd+Adam on
+    w * Dice(student, gt) + (1 - w) * Dice(student, teacher mask)."""
+    img = img.to(device=teacher.device, dtype=torch.float32)
+    ground_truth = ground_truth.to(device=teacher.device, dtype=torch.float32)
+    if not denoise_label:
+        teacher_loss_gt, _ = teacher.train_one_epoch(img, ground_truth)
+        with torch.no_grad():
+            teacher_masks = teacher.predict(img)
+    else:
+        t0 = teacher.predict(img)
+        t = denoise_teacher_probs(t0, ground_truth)
+        _, conf_mask, _, _, _ = threshold_pseudo_masks(img, t, allow_throw_sample=False)
+        teacher_loss_gt = loss_func(t0, conf_mask)
+        teacher_masks = conf_mask
+        teacher.train_from_loss(teacher_loss_gt)
+    student_loss, student_pred = student.predict(img, ground_truth)
+    self_sup = loss_func(student_pred, teacher_masks)
+    loss = supervise_weight * student_loss + (1 - supervise_weight) * self_sup
+    student.train_from_loss(loss)
+    return loss, teacher_loss_gt, student_loss, self_sup
+
+
+def ema_teacher_student_step(teacher, student, img_labeled, ground_truth, img_unlabeled, supervise_weight: float = 0.8,
+                             ema_decay: float = 0.99, grad_sync=None):
+    """North-star variant: EMA teacher forward on labeled + unlabeled tiles -> confidence-thresholded pseudo labels ->
+    student forward/backward on both -> fused clip+Adam -> rank-local EMA teacher update.
+    `grad_sync`: optional callable run between backward and the optimiser step (data-parallel all-reduce)."""
+    dev = student.device
+    img_l = img_labeled.to(device=dev, dtype=torch.float32)
+    img_u = img_unlabeled.to(device=dev, dtype=torch.float32)
+    gt = ground_truth.to(device=dev, dtype=torch.float32)
+    imgs = torch.cat([img_l, img_u], dim=0)
+    nl = img_l.shape[0]
+    with torch.no_grad():
+        t_probs = teacher.predict(imgs)
+    t_l = denoise_teacher_probs(t_probs[:nl], gt)
+    pseudo_l, _ = pseudo_label_stats(t_l, allow_throw_sample=False)
+    pseudo_u, stats_u = pseudo_label_stats(t_probs[nl:].contiguous(), allow_throw_sample=True)
+    keep_u = (stats_u[:, 4] > 0.5)
+    # static shapes: rejected unlabeled tiles stay in the batch with an all-zero target and zero weight
+    s_probs = student.predict(imgs)
+    sup = loss_func(s_probs[:nl], gt.to(torch.int64))
+    self_l = loss_func(s_probs[:nl], pseudo_l)
+    w_u = keep_u.float().mean()
+    self_u = loss_func(s_probs[nl:], pseudo_u * keep_u.view(-1, 1, 1).to(torch.int64))
+    loss = supervise_weight * sup + (1 - supervise_weight) * (self_l + w_u * self_u) * 0.5
+    student.optimizer.zero_grad()
+    loss.backward()
+    if grad_sync is not None:
+        grad_sync()
+    student.optimizer.step()
+    ema_update(teacher.optimizer, student.optimizer, ema_decay)
+    return loss
