@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the north-star metric: MiT-b5 512x512 teacher-student training step, images/sec (BASELINE.json).
+
+    python bench.py --gpus N --steps K --warmup W                 # this repo's libsfk path (torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference algorithm (CPU oracle port) on host cores
+
+One "step" = one EMA-teacher semi-supervised iteration on 8 labeled + 8 unlabeled synthetic 512x512 tiles per GPU:
+EMA-teacher forward on all 16 tiles -> denoise + confidence-thresholded pseudo labels -> student forward/backward on all
+16 tiles with Dice losses -> gradient all-reduce (N > 1) -> fused clip+Adam -> EMA teacher update  (SURVEY.md §8d config 3,
+variant ii).  Weights are random-init MiT-b5 (no checkpoint offline), data is synthetic.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "mit_b5_512_teacher_student_train_images_per_sec"
+UNIT = "images/s"
+TILE = 512
+N_LABELED, N_UNLABELED = 8, 8
+FWD_GFLOP_PER_IMG = 219.27          # SURVEY.md §8d / BASELINE.md §3 (MiT-b5 512^2 forward, 2*MAC)
+STEP_GFLOP_PER_IMG = 219.27 + 657.8  # teacher forward + student forward/backward on every tile
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md)
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU oracle step (the reference algorithm restated in oracle/; used for cpu_baseline and --impl reference)
+# ---------------------------------------------------------------------------------------------------------------
+def make_oracle_step(n_l: int, n_u: int, tile: int, threads: int):
+    import torch
+    from oracle import segformer_oracle as O
+    torch.set_num_threads(threads)
+    cfg = O.OracleConfig.mit_b5(num_labels=1)
+    g = torch.Generator().manual_seed(0)
+    tmpl = O.state_dict_template(cfg)
+    student = {}
+    for k, v in tmpl.items():
+        if not v.is_floating_point():
+            student[k] = v
+        elif k.endswith("running_var") or (("layer_norm" in k or "batch_norm" in k) and k.endswith("weight")):
+            student[k] = torch.ones_like(v)
+        elif k.endswith(".bias") or k.endswith("running_mean"):
+            student[k] = torch.zeros_like(v)
+        else:
+            student[k] = torch.randn(v.shape, generator=g) * 0.02
+    teacher = {k: v.clone() for k, v in student.items()}
+    train_keys = [k for k, v in student.items() if v.is_floating_point() and "running_" not in k and "cls_proj" not in k]
+    state = {k: (torch.zeros_like(student[k]), torch.zeros_like(student[k])) for k in train_keys}
+    img_l = torch.rand(n_l, 3, tile, tile, generator=g)
+    img_u = torch.rand(n_u, 3, tile, tile, generator=g)
+    gt = (torch.rand(n_l, tile, tile, generator=g) > 0.9).float()
+    step_no = [0]
+
+    def step():
+        step_no[0] += 1
+        imgs = torch.cat([img_l, img_u])
+        with torch.no_grad():
+            lt, _, _ = O.forward_logits(imgs, teacher, cfg, bn_training=True)
+            t_probs = O.predict_probs(lt, (tile, tile))
+        t_l = O.denoise_teacher_probs(t_probs[:n_l], gt)
+        pseudo_l = torch.where(t_l >= O.PSEUDO_MASK_THRESHOLD, 1, 0)
+        t_u = t_probs[n_l:]
+        flat = t_u.reshape(n_u, -1)
+        conf = ((flat >= 0.7) | (flat <= 1 - 0.7)).sum(1) / flat.shape[1]
+        keep = (flat.abs().sum(1) > 1000) & (conf >= 0.7)
+        pseudo_u = torch.where(t_u >= 0.7, 1, 0) * keep.view(-1, 1, 1).long()
+        params = {k: (v.clone().requires_grad_(True) if k in state else v) for k, v in student.items()}
+        ls, _, _ = O.forward_logits(imgs, params, cfg, bn_training=True)
+        s_probs = O.predict_probs(ls, (tile, tile))
+        loss = 0.8 * O.segmentation_loss(s_probs[:n_l], gt.long(), "dice") + 0.2 * 0.5 * (
+            O.segmentation_loss(s_probs[:n_l], pseudo_l, "dice") + keep.float().mean() * O.segmentation_loss(s_probs[n_l:], pseudo_u, "dice"))
+        loss.backward()
+        with torch.no_grad():
+            for k in train_keys:
+                gk = params[k].grad
+                if gk is None:
+                    continue
+                m, v = state[k]
+                p2, m2, v2 = O.clip_adam_l2_step(student[k], gk, m, v, step_no[0], 3e-5, 5e-5)
+                student[k], state[k] = p2, (m2, v2)
+                teacher[k] = O.ema_update(teacher[k], student[k], 0.99)
+        return float(loss.detach())
+
+    return step
+
+
+def time_oracle(steps: int, warmup: int, budget_s: float, n_l=1, n_u=1):
+    threads = os.cpu_count() or 1
+    step = make_oracle_step(n_l, n_u, TILE, threads)
+    t_start = time.perf_counter()
+    done_w = 0
+    for _ in range(warmup):
+        step()
+        done_w += 1
+        if time.perf_counter() - t_start > budget_s * 0.3:
+            break
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        step()
+        done += 1
+        if time.perf_counter() - t_start > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return dict(value=(n_l + n_u) * done / dt, steps=done, warmup=done_w, seconds=dt, cores=threads,
+                sample=f"{done} step(s) of the same teacher-student step on {n_l} labeled + {n_u} unlabeled 512x512 tiles, "
+                       f"MiT-b5 fp32, torch CPU {threads} threads (oracle/segformer_oracle.py port of the reference)")
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = time_oracle(args.steps, args.warmup, budget_s=200.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
+            "warmup": r["warmup"], "ms_per_step": 1000.0 * r["seconds"] / max(1, r["steps"]), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "MiT-b5 512x512 EMA teacher-student train step (CPU oracle port of the reference algorithm)",
+                       "tiles_per_step": 2},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# libsfk arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_sfk(args):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+
+    from semisupervisedobjectdetection_b200 import _lib as L
+    from semisupervisedobjectdetection_b200 import ddp, ops
+    from semisupervisedobjectdetection_b200 import teacher_student as TS
+    from semisupervisedobjectdetection_b200.wrapper import SegFormerModel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    torch.manual_seed(1234)  # identical initial weights on every rank (also broadcast in ddp.attach)
+    variant = args.variant
+    student = SegFormerModel(None, lr=3e-5, weight_decay=5e-5, scheduler=0.97, device=dev, variant=variant)
+    teacher = SegFormerModel(None, lr=5e-7, weight_decay=5e-5, scheduler=0.97, device=dev, variant=variant)
+    teacher.load_state_dict(student.state_dict())
+    ops.bump_weight_epoch()
+    teacher.train()
+    student.train()
+    for p in teacher.model.parameters():
+        p.requires_grad_(False)
+    bucketer = ddp.attach(student) if world > 1 else None
+
+    tile = args.tile
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_l = torch.rand(N_LABELED, 3, tile, tile, generator=g).pin_memory()
+    host_u = torch.rand(N_UNLABELED, 3, tile, tile, generator=g).pin_memory()
+    host_gt = (torch.rand(N_LABELED, tile, tile, generator=g) > 0.9).float().pin_memory()
+    dev_l, dev_u, dev_gt = host_l.to(dev), host_u.to(dev), host_gt.to(dev)
+
+    def sync_fn():
+        if bucketer is not None:
+            bucketer.finish()
+
+    def step(l, u, gt):
+        if bucketer is not None:
+            bucketer.begin_step()
+        return TS.ema_teacher_student_step(teacher, student, l, gt, u, supervise_weight=0.8, ema_decay=0.99, grad_sync=sync_fn)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    lib = L.load()
+    imgs_per_step = (N_LABELED + N_UNLABELED) * world
+    # ---- resident-input throughput ----
+    for _ in range(args.warmup):
+        step(dev_l, dev_u, dev_gt)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = lib.sfk_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof = {}
+    e0.record()
+    for i in range(args.steps):
+        if i == args.steps - 1 and rank == 0:
+            lib.sfk_profile_gemm_begin()
+        loss = step(dev_l, dev_u, dev_gt)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = lib.sfk_launch_count() - launches0
+    if rank == 0:
+        t_ms, t_fl, t_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
+        lib.sfk_profile_gemm_end(ctypes.byref(t_ms), ctypes.byref(t_fl), ctypes.byref(t_n))
+        prof = dict(ms=t_ms.value, flops=t_fl.value, launches=t_n.value)
+    clocks = sampler.stop() if sampler else None
+    # ---- end-to-end through the public API with host (pinned) inputs and a host read of the loss ----
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(host_l.to(dev, non_blocking=True), host_u.to(dev, non_blocking=True), host_gt.to(dev, non_blocking=True))
+        loss_host = float(loss.detach())  # D2H of the step's result
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    achieved_tf = prof["flops"] / (prof["ms"] * 1e-3) / 1e12 if prof.get("ms") else None
+    gemm_share = prof["ms"] / ms if prof.get("ms") else None
+    cpu = time_oracle(1, 0, budget_s=60.0) if world == 1 and not args.no_cpu_baseline else None
+    h2d = host_l.numel() * 4 + host_u.numel() * 4 + host_gt.numel() * 4
+    step_tflop = STEP_GFLOP_PER_IMG * (N_LABELED + N_UNLABELED) / 1e3
+    line = {
+        "metric": METRIC, "value": imgs_per_step / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"MiT-{variant.split('-')[-1]} {tile}x{tile} EMA teacher-student train step: teacher fwd + student "
+                               f"fwd/bwd on {N_LABELED} labeled + {N_UNLABELED} unlabeled tiles per GPU, Dice losses, fused "
+                               "clip+Adam, EMA update (SURVEY 8d config 3-ii)",
+                   "tiles_per_gpu_per_step": N_LABELED + N_UNLABELED, "parallelism": f"dp{world}",
+                   "stochastic": "drop-path 0.1, dropout 0.1, BatchNorm batch stats (reference defaults)",
+                   "l2": "per-step working set (activations ~10 GB) >> 126 MB L2; no explicit flush needed",
+                   "step_tflop_per_gpu": step_tflop,
+                   "end_to_end_frac_of_sustained_peak": step_tflop / (ms * 1e-3) / pk["tf_sustained"]},
+        "e2e": {"value": imgs_per_step / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": achieved_tf, "peak": pk["tf_sustained"],
+                     "unit": "TFLOP/s", "frac": (achieved_tf / pk["tf_sustained"]) if achieved_tf else None, "traffic": None,
+                     "peak_source": pk["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
+                     "launches_per_step": prof.get("launches"), "share_of_step": gemm_share,
+                     "how": "CUDA events around every GEMM launch of the last timed step; achieved = sum(2MNK) / sum(duration)"},
+        "loss": loss_host,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": "port", "sample": cpu["sample"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sfk", choices=["sfk", "reference"])
+    ap.add_argument("--variant", default="nvidia/mit-b5")
+    ap.add_argument("--tile", type=int, default=TILE)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "sfk":
+        args.warmup = 3  # timing rules: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_sfk(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -521,6 +521,8 @@ class SegformerEncoder(nn.Module):
         self.block = nn.ModuleList(blocks)
         self.layer_norm = nn.ModuleList([nn.LayerNorm(config.hidden_sizes[i]) for i in range(config.num_encoder_blocks)])
         self._anchor = _GradAnchor()
+        self._ddp_bucketer = None        # set by ddp.attach(): overlaps the gradient all-reduce with backward
+        self._ddp_stage_offsets = None
 
     def _forward_tokens(self, pixel_values):
         """Fast path: returns ([(tokens bf16 [B,N_i,C_i], H_i, W_i)] per stage, cls list | None)."""
@@ -532,6 +534,10 @@ class SegformerEncoder(nn.Module):
         stages, block_cls = [], []
         for idx, (emb, blk, norm) in enumerate(zip(self.patch_embeddings, self.block, self.layer_norm)):
             hidden, H, W = emb._forward_tokens(x_in, is_image, Hin, Win)
+            if self._ddp_bucketer is not None and hidden.requires_grad:
+                # when this gradient exists, every gradient of this stage's blocks and of everything after it is final
+                bucketer, off = self._ddp_bucketer, self._ddp_stage_offsets[idx]
+                hidden.register_hook(lambda g, b=bucketer, o=off: b.notify(o))
             block_cls.append(None)
             running_cls = None
             pt = self.prompt_tokens[idx]

@@ -49,6 +49,7 @@ def scratch(nbytes: int, device: torch.device, slot: str = "main") -> torch.Tens
 
 
 def stream() -> int:
+    L.ensure_device()  # raises SfkError (never falls back) when there is no sm_100 device
     return torch.cuda.current_stream().cuda_stream
 
 

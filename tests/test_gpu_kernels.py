@@ -1,0 +1,29 @@
+"""GPU: per-kernel parity of libsfk (called through the C-ABI) against plain PyTorch fp32 on the same seeded inputs.
+Each group runs tools/check_*.py in its own process so that a device trap in one kernel cannot poison the others.
+Tolerances (relative to the reference tensor's max): fp32-out kernels 1e-4..1e-5, bf16-out kernels 1e-2..3e-2."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(script, group, timeout=600):
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", script), group], cwd=ROOT, capture_output=True, text=True,
+                       timeout=timeout)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-40:])
+    assert r.returncode == 0 and "ALLOK" in r.stdout, f"{script} {group} failed:\n{tail}"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("group", ["nt", "nn", "tn", "epi"])
+def test_gemm_tcgen05_layouts(group):
+    _run("check_gemm.py", group)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("group", ["ln", "dwconv", "im2col", "attn_fwd", "attn_bwd", "decode", "loss", "optim"])
+def test_ops(group):
+    _run("check_ops.py", group)

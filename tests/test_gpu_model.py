@@ -1,0 +1,164 @@
+"""GPU: whole-path parity — libsfk SegFormer vs the golden fixtures (outputs of the real reference) and vs the oracle,
+pseudo-label thresholding bit-exactness, optimiser / EMA steps, and size-independent properties at the full
+BASELINE.json size (MiT-b5, 512x512)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import segformer_oracle as O
+from oracle import synth
+from tests import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def test_model_matches_reference_goldens():
+    """Forward logits / hidden states / probabilities / losses and backward gradients for every golden case
+    (eval, 128^2, 2-D and 3-D prompts, cls tokens, CE, BN train mode); bf16 tolerance: max rel err <= 5e-2 on gradients,
+    <= 2e-2 on logits (north_star)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_model.py"), "golden"], cwd=ROOT, capture_output=True,
+                       text=True, timeout=900)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-30:])
+    assert r.returncode == 0 and "GOLDEN ALLOK" in r.stdout, tail
+
+
+def _b0_wrapper(num_labels=1, lr=1e-3, wd=5e-5):
+    from semisupervisedobjectdetection_b200.wrapper import SegFormerModel
+    w = SegFormerModel(None, lr=lr, weight_decay=wd, scheduler=0.97, device="cuda:0", num_labels=num_labels, variant="nvidia/mit-b0")
+    ocfg = O.OracleConfig.mit_b0(num_labels=num_labels)
+    sd = synth.synth_state_dict(O.state_dict_template(ocfg))
+    w.model.load_state_dict(sd, strict=True)
+    return w, ocfg, sd
+
+
+def test_threshold_pseudo_masks_bit_exact():
+    from semisupervisedobjectdetection_b200 import teacher_student as TS
+    for tag, (n, hw, sharp) in {"mixed": (6, 64, 6.0), "all_conf": (2, 48, 40.0), "none_conf": (2, 48, 0.3)}.items():
+        logits = (synth.uniform01(f"thr/{tag}", (n, hw, hw)) - 0.5) * sharp
+        if tag == "mixed":
+            logits[1] = logits[1] * 0.05
+            logits[4] = -20.0
+        probs = torch.sigmoid(logits)
+        img = synth.uniform01(f"thr/{tag}/img", (n, 3, hw, hw))
+        for allow in (True, False):
+            gold = helpers.load_golden("loss_threshold")[f"threshold/{tag}/allow{int(allow)}"]
+            ci, cm, cp, conf, loss = TS.threshold_pseudo_masks(img.cuda(), probs.cuda(), allow_throw_sample=allow)
+            assert torch.equal(conf.cpu(), gold["confidence"])          # bit-exact fp32
+            if gold["kept_masks"] is None:
+                assert ci is None and cm is None and torch.isnan(loss)
+            else:
+                assert cm.dtype == torch.int64 and torch.equal(cm.cpu(), gold["kept_masks"])   # bit-exact int64
+                assert torch.equal(ci.cpu(), gold["kept_imgs"]) and torch.equal(cp.cpu(), gold["kept_probs"])
+                assert abs(float(loss) - float(gold["loss"])) < 1e-5
+
+
+def test_losses_match_reference_goldens():
+    from semisupervisedobjectdetection_b200.loss import SegmentationLoss
+    gold = helpers.load_golden("loss_threshold")
+    p = synth.uniform01("loss/p", (3, 64, 64)).cuda()
+    g = (synth.uniform01("loss/g", (3, 64, 64)) > 0.5).cuda()
+    for kind in ("dice", "dice_argmax"):
+        f = SegmentationLoss(1, loss_type=kind, activation="none")
+        assert abs(float(f(p, g.to(torch.int64))) - float(gold[f"{kind}/int64"])) < 1e-5
+        assert abs(float(f(p, g.float())) - float(gold[f"{kind}/float"])) < 1e-5
+    img = synth.uniform01("loss/img", (3, 3, 64, 64)).cuda()
+    rec = synth.uniform01("loss/rec", (3, 3, 64, 64)).cuda()
+    assert abs(float(SegmentationLoss(1, loss_type="mse")(img, rec)) / float(gold["mse"]) - 1) < 1e-5
+    pr = p.clone().requires_grad_(True)
+    SegmentationLoss(1, loss_type="dice", activation="none")(pr, g.to(torch.int64)).backward()
+    assert torch.allclose(pr.grad.cpu(), gold["dice/grad"], atol=1e-9, rtol=1e-4)
+
+
+def test_train_one_epoch_matches_oracle_adam_step():
+    """SFM:146-162 path: eval-mode forward (M7), Dice, backward, clip(1.2) + Adam(0.5,0.999,L2) — one full step."""
+    w, ocfg, sd = _b0_wrapper()
+    x = synth.uniform01("step/x", (2, 3, 64, 64))
+    mask = (synth.uniform01("step/mask", (2, 64, 64)) > 0.7).float()
+    loss, probs = w.train_one_epoch(x, mask)
+    sd_o = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v) for k, v in sd.items()}
+    logits, _, _ = O.forward_logits(x, sd_o, ocfg)
+    loss_o = O.segmentation_loss(O.predict_probs(logits, (64, 64)), mask.to(torch.int64), "dice")
+    loss_o.backward()
+    assert abs(float(loss) - float(loss_o)) < 1e-3 * abs(float(loss_o))
+    named = dict(w.model.named_parameters())
+    for k in ("segformer.encoder.block.1.0.mlp.dense1.weight", "decode_head.linear_fuse.weight",
+              "segformer.encoder.patch_embeddings.0.proj.weight", "decode_head.classifier.bias"):
+        g = sd_o[k].grad
+        p2, _, _ = O.clip_adam_l2_step(sd[k], g, torch.zeros_like(g), torch.zeros_like(g), 1, 1e-3, 5e-5)
+        got = named[k].detach().cpu()
+        # first Adam step moves every weight by ~lr*sign(g); compare the update direction/magnitude
+        upd_got, upd_ref = got - sd[k], p2 - sd[k]
+        big = upd_ref.abs() > 0.5e-3
+        agree = (torch.sign(upd_got[big]) == torch.sign(upd_ref[big])).float().mean()
+        assert agree > 0.97, (k, float(agree))
+    # parameters that received no gradient (unused cls_proj) must be untouched, like torch.optim.Adam with grad=None
+    k = "decode_head.linear_c.0.cls_proj.weight"
+    assert torch.equal(named[k].detach().cpu(), sd[k])
+
+
+def test_ema_update_and_hard_reset():
+    from semisupervisedobjectdetection_b200.optim import ema_update
+    t, _, _ = _b0_wrapper()
+    s, _, _ = _b0_wrapper()
+    with torch.no_grad():
+        for p in s.model.parameters():
+            p.add_(0.25)
+    t0 = {k: v.detach().clone() for k, v in t.model.named_parameters()}
+    ema_update(t.optimizer, s.optimizer, 0.75)
+    for k, p in t.model.named_parameters():
+        want = O.ema_update(t0[k], dict(s.model.named_parameters())[k].detach(), 0.75)
+        assert torch.allclose(p.detach(), want, atol=1e-6)
+    ema_update(t.optimizer, s.optimizer, 0.0)   # d = 0 == teacher.load_state_dict(student.state_dict()) (TS:202-204)
+    for (k, p), (_, q) in zip(t.model.named_parameters(), s.model.named_parameters()):
+        assert torch.equal(p.detach(), q.detach()), k
+
+
+def test_frozen_encoder_prompt_tuning_step():
+    """segFormer_transfer_learning_main.py:202-205: freeze blocks 0,1, add 10 prompt tokens per stage, train."""
+    w, ocfg, sd = _b0_wrapper()
+    w.frozen_encoder(layers=[0, 1])
+    w.add_prompt_token([10, 10, 10, 10])
+    before = {k: v.detach().clone() for k, v in w.model.named_parameters()}
+    x = synth.uniform01("pt/x", (2, 3, 64, 64))
+    mask = (synth.uniform01("pt/mask", (2, 64, 64)) > 0.7).float()
+    loss, _ = w.train_one_epoch(x, mask)
+    assert torch.isfinite(loss)
+    for k, p in w.model.named_parameters():
+        changed = not torch.equal(p.detach(), before[k])
+        if ".block.0." in k or ".block.1." in k or "cls_proj" in k:
+            assert not changed, k            # frozen / unused parameters stay put
+        elif "patch_embeddings.0.proj.weight" in k or "block.2.0.mlp.dense1.weight" in k or "decode_head.linear_fuse" in k:
+            assert changed, k                # dgrad still flows through the frozen blocks
+
+
+def test_full_size_properties_b5_512():
+    """BASELINE.json size (MiT-b5, 512x512): size-independent properties instead of an oracle run."""
+    from semisupervisedobjectdetection_b200 import teacher_student as TS
+    from semisupervisedobjectdetection_b200.wrapper import SegFormerModel
+    torch.manual_seed(0)
+    w = SegFormerModel(None, lr=3e-5, weight_decay=5e-5, scheduler=0.97, device="cuda:0")
+    w.model.eval()
+    x = torch.rand(2, 3, 512, 512)
+    with torch.no_grad():
+        p1 = w.predict(x)
+        p2 = w.predict(x)
+        pb = w.predict(torch.cat([x, x.flip(0)]))
+    assert p1.shape == (2, 512, 512) and torch.isfinite(p1).all() and (p1 >= 0).all() and (p1 <= 1).all()
+    assert torch.equal(p1, p2)                                   # deterministic / idempotent in eval mode
+    assert torch.allclose(pb[:2], p1, atol=2e-3) and torch.allclose(pb[2:].flip(0), p1, atol=2e-3)   # batch independence
+    pseudo, stats = TS.pseudo_label_stats(p1, allow_throw_sample=True)
+    # checksum-of-checksums: the kernel's per-sample counts equal an independent recount of its own int64 masks
+    assert torch.equal(pseudo.sum(dim=(1, 2)).float(), stats[:, 2])
+    conf_re = ((p1 >= 0.7) | (p1 <= 1 - 0.7)).sum(dim=(1, 2)) / p1[0].numel()
+    assert torch.equal(conf_re, stats[:, 1])
+    assert torch.equal(pseudo, torch.where(p1 >= 0.7, 1, 0))
+    # one training step at full size stays finite and changes the weights
+    w.model.train()
+    before = w.optimizer.flat_p.clone()
+    loss, _ = w.train_one_epoch(x, (torch.rand(2, 512, 512) > 0.9).float())
+    assert torch.isfinite(loss) and torch.isfinite(w.optimizer.flat_p).all()
+    assert not torch.equal(before, w.optimizer.flat_p)

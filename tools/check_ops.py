@@ -1,5 +1,5 @@
 """GPU bring-up check of the non-GEMM ops against plain PyTorch fp32. Usage: python tools/check_ops.py <group>
-groups: ln | dwconv | im2col | attn_fwd | attn_bwd | attn_perf"""
+groups: ln | dwconv | im2col | attn_fwd | attn_bwd | decode | loss | optim | attn_perf"""
 import math
 import os
 import sys
@@ -173,6 +173,143 @@ def main():
                 allok &= report(f"attn_bwd dq B{B} h{heads} T{T} Tk{Tk} D{D}", dq, qr.grad, 3e-2)
                 allok &= report("   dk", dkv[..., :C], kvr.grad[..., :C], 3e-2)
                 allok &= report("   dv", dkv[..., C:], kvr.grad[..., C:], 3e-2)
+
+    elif group == "decode":
+        for (B, h, w, C, H, W) in [(2, 8, 8, 64, 32, 32), (1, 16, 16, 32, 32, 32), (2, 4, 4, 128, 32, 32), (2, 32, 32, 64, 32, 32), (1, 3, 5, 64, 12, 20)]:
+            x = torch.randn(B, h, w, C, device=dev).bfloat16()
+            out = torch.zeros(B, H, W, 2 * C, device=dev, dtype=torch.bfloat16)
+            L.check(lib.sfk_upsample_concat(x.data_ptr(), out.data_ptr(), B, h, w, C, H, W, 2 * C, C, L.stream_ptr()))
+            xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+            ref = F.interpolate(xr, size=(H, W), mode="bilinear", align_corners=False)
+            allok &= report(f"upsample_concat {h}x{w}->{H}x{W} C{C}", out[..., C:], ref.permute(0, 2, 3, 1), 1e-2)
+            allok &= report("   untouched slice", out[..., :C], torch.zeros(B, H, W, C, device=dev), 1.0)
+            dout = torch.randn(B, H, W, 2 * C, device=dev).bfloat16()
+            ref.backward(dout[..., C:].float().permute(0, 3, 1, 2))
+            din = torch.empty(B, h, w, C, device=dev, dtype=torch.bfloat16)
+            L.check(lib.sfk_upsample_concat_bwd(dout.data_ptr(), din.data_ptr(), B, h, w, C, H, W, 2 * C, C, L.stream_ptr()))
+            allok &= report("upsample_concat_bwd", din, xr.grad.permute(0, 2, 3, 1), 1e-2)
+        for (M, C, NL, pix, train) in [(2 * 256, 64, 1, 256, 1), (3 * 100, 128, 3, 100, 1), (2 * 256, 768, 1, 256, 0), (512, 256, 2, 128, 1)]:
+            x = (torch.randn(M, C, device=dev) * 1.5 + 0.3).bfloat16()
+            gamma = torch.rand(C, device=dev) + 0.5
+            beta = torch.randn(C, device=dev) * 0.2
+            wc = torch.randn(NL, C, device=dev) * 0.1
+            bc = torch.randn(NL, device=dev)
+            rm = torch.randn(C, device=dev) * 0.1
+            rv = torch.rand(C, device=dev) + 0.5
+            rm2, rv2 = rm.clone(), rv.clone()
+            mean = torch.empty(C, device=dev)
+            rstd = torch.empty(C, device=dev)
+            if train:
+                wsb = lib.sfk_bn_stats_workspace_bytes(M, C)
+                ws = torch.empty(wsb, device=dev, dtype=torch.uint8)
+                L.check(lib.sfk_bn_batch_stats(x.data_ptr(), M, C, 1e-5, 0.1, mean.data_ptr(), rstd.data_ptr(), rm2.data_ptr(),
+                                               rv2.data_ptr(), ws.data_ptr(), wsb, L.stream_ptr()))
+            else:
+                L.check(lib.sfk_bn_eval_stats(rm.data_ptr(), rv.data_ptr(), 1e-5, mean.data_ptr(), rstd.data_ptr(), C, L.stream_ptr()))
+            Bn = M // pix
+            logits = torch.empty(Bn, NL, pix, device=dev)
+            L.check(lib.sfk_bn_relu_cls_fwd(x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                            wc.data_ptr(), bc.data_ptr(), logits.data_ptr(), M, C, NL, pix, 0.0, 0, L.stream_ptr()))
+            xr = x.float().clone().requires_grad_(True)
+            gr, br, wr, bcr = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True), wc.clone().requires_grad_(True), bc.clone().requires_grad_(True)
+            rm3, rv3 = rm.clone(), rv.clone()
+            xn = xr.reshape(Bn, pix, C).permute(0, 2, 1).unsqueeze(-1)  # [B,C,pix,1]
+            y = F.relu(F.batch_norm(xn, rm3, rv3, gr, br, training=bool(train), momentum=0.1, eps=1e-5))
+            ref = F.conv2d(y, wr.reshape(NL, C, 1, 1), bcr).squeeze(-1)  # [B,NL,pix]
+            allok &= report(f"bn_relu_cls fwd M{M} C{C} NL{NL} train{train}", logits, ref, 2e-3)
+            if train:
+                allok &= report("   running_mean", rm2, rm3, 1e-4)
+                allok &= report("   running_var", rv2, rv3, 1e-4)
+            dl = torch.randn(Bn, NL, pix, device=dev)
+            ref.backward(dl)
+            sums = torch.empty(2, C, device=dev)
+            dwc = torch.zeros(NL, C, device=dev)
+            dbc = torch.zeros(NL, device=dev)
+            dx = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
+            L.check(lib.sfk_bn_relu_cls_bwd(x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                            wc.data_ptr(), dl.data_ptr(), sums.data_ptr(), dwc.data_ptr(), dbc.data_ptr(), dx.data_ptr(),
+                                            M, C, NL, pix, 0.0, 0, train, L.stream_ptr()))
+            allok &= report("bn_relu_cls bwd dx", dx, xr.grad, 2e-2)
+            allok &= report("   dgamma", sums[1], gr.grad, 2e-3)
+            allok &= report("   dbeta", sums[0], br.grad, 2e-3)
+            allok &= report("   dwc", dwc, wr.grad, 2e-3)
+            allok &= report("   dbc", dbc, bcr.grad, 2e-3)
+    elif group == "loss":
+        for (B, C, h, w, H, W, act) in [(2, 1, 16, 16, 64, 64, 1), (2, 3, 16, 16, 64, 64, 0), (1, 2, 7, 9, 28, 36, 1), (2, 1, 128, 128, 512, 512, 1)]:
+            x = torch.randn(B, C, h, w, device=dev) * 2
+            y = torch.empty(B, C, H, W, device=dev)
+            L.check(lib.sfk_upsample_nchw_fwd(x.data_ptr(), y.data_ptr(), B * C, h, w, H, W, act, L.stream_ptr()))
+            xr = x.clone().requires_grad_(True)
+            ref = F.interpolate(xr, size=(H, W), mode="bilinear", align_corners=False)
+            if act:
+                ref = torch.sigmoid(ref)
+            allok &= report(f"upsample_nchw fwd {h}x{w}->{H}x{W} act{act}", y, ref, 1e-5)
+            dy = torch.randn(B, C, H, W, device=dev)
+            ref.backward(dy)
+            dx = torch.empty_like(x)
+            L.check(lib.sfk_upsample_nchw_bwd(dy.data_ptr(), y.data_ptr() if act else None, dx.data_ptr(), B * C, h, w, H, W, 0, L.stream_ptr()))
+            allok &= report("upsample_nchw bwd", dx, xr.grad, 1e-4)
+        ws = torch.empty(lib.sfk_loss_workspace_bytes(), device=dev, dtype=torch.uint8)
+        z = torch.randn(2, 64, 64, device=dev) * 3
+        lab = (torch.rand(2, 64, 64, device=dev) > 0.5).long()
+        lab[torch.rand(2, 64, 64, device=dev) > 0.9] = 255
+        out = torch.empty(2, device=dev)
+        L.check(lib.sfk_bce_valid_fwd(z.data_ptr(), lab.data_ptr(), 255, z.numel(), ws.data_ptr(), out.data_ptr(), L.stream_ptr()))
+        zr = z.clone().requires_grad_(True)
+        valid = ((lab >= 0) & (lab != 255)).float()
+        ref = (F.binary_cross_entropy_with_logits(zr, lab.float(), reduction="none") * valid).mean()
+        allok &= report("bce_valid fwd", out[0:1], ref.reshape(1), 1e-5)
+        ref.backward()
+        dz = torch.empty_like(z)
+        one = torch.ones(1, device=dev)
+        L.check(lib.sfk_bce_valid_bwd(z.data_ptr(), lab.data_ptr(), 255, one.data_ptr(), dz.data_ptr(), z.numel(), L.stream_ptr()))
+        allok &= report("bce_valid bwd", dz, zr.grad, 1e-5)
+        z = torch.randn(2, 4, 32, 32, device=dev) * 3
+        lab = torch.randint(0, 4, (2, 32, 32), device=dev)
+        lab[torch.rand(2, 32, 32, device=dev) > 0.9] = 255
+        L.check(lib.sfk_ce_ignore_fwd(z.data_ptr(), lab.data_ptr(), 255, 2, 4, 32 * 32, ws.data_ptr(), out.data_ptr(), L.stream_ptr()))
+        zr = z.clone().requires_grad_(True)
+        ref = F.cross_entropy(zr, lab, ignore_index=255)
+        allok &= report("ce_ignore fwd", out[0:1], ref.reshape(1), 1e-5)
+        ref.backward()
+        dz = torch.empty_like(z)
+        L.check(lib.sfk_ce_ignore_bwd(z.data_ptr(), lab.data_ptr(), 255, out.data_ptr(), one.data_ptr(), dz.data_ptr(), 2, 4, 32 * 32, L.stream_ptr()))
+        allok &= report("ce_ignore bwd", dz, zr.grad, 1e-5)
+        t0 = torch.rand(1000, device=dev)
+        gt = (torch.rand(1000, device=dev) > 0.5).float()
+        o = torch.empty_like(t0)
+        L.check(lib.sfk_denoise_labels(t0.data_ptr(), gt.data_ptr(), o.data_ptr(), 1000, L.stream_ptr()))
+        t = t0 + 0.2 * gt
+        t -= 0.1
+        t = torch.where(t > 1, torch.ones_like(t), t)
+        t = torch.where(t < 0, torch.zeros_like(t), t)
+        ok = bool(torch.equal(o, t))
+        print(f"{'OK ' if ok else 'BAD'} denoise_labels bit-exact vs torch op sequence", flush=True)
+        allok &= ok
+    elif group == "optim":
+        n = 100003
+        p = torch.randn(n, device=dev)
+        g = torch.randn(n, device=dev) * 2
+        m = torch.zeros(n, device=dev)
+        v = torch.zeros(n, device=dev)
+        pr, mr, vr = p.clone(), m.clone(), v.clone()
+        for step in (1, 2, 3):
+            L.check(lib.sfk_clip_adam_l2(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.5, 0.999, 1e-8, 5e-5, 1.2,
+                                         step, L.stream_ptr()))
+            gg = g.clamp(-1.2, 1.2) + 5e-5 * pr
+            mr = 0.5 * mr + 0.5 * gg
+            vr = 0.999 * vr + 0.001 * gg * gg
+            pr = pr - (1e-3 / (1 - 0.5 ** step)) * (mr / (vr.sqrt() / math.sqrt(1 - 0.999 ** step) + 1e-8))
+        allok &= report("clip_adam_l2 3 steps", p, pr, 1e-5)
+        t = torch.randn(n, device=dev)
+        s2 = torch.randn(n, device=dev)
+        ref = 0.9 * t + 0.1 * s2
+        L.check(lib.sfk_ema_lerp(t.data_ptr(), s2.data_ptr(), n, 0.9, L.stream_ptr()))
+        allok &= report("ema_lerp", t, ref, 1e-6)
+        L.check(lib.sfk_ema_lerp(t.data_ptr(), s2.data_ptr(), n, 0.0, L.stream_ptr()))
+        ok = bool(torch.equal(t, s2))
+        print(f"{'OK ' if ok else 'BAD'} ema_lerp decay=0 is a bit-exact copy", flush=True)
+        allok &= ok
     elif group == "attn_perf":
         for (name, B, heads, T, Tk, D) in [("stage1", 16, 1, 16384, 256, 64), ("stage2", 16, 2, 4096, 256, 64),
                                           ("stage3", 16, 5, 1024, 256, 64), ("stage4", 16, 8, 256, 256, 64)]:
