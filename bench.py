@@ -213,7 +213,7 @@ def run_sfk(args):
     student = SegFormerModel(None, lr=3e-5, weight_decay=5e-5, scheduler=0.97, device=dev, variant=variant)
     teacher = SegFormerModel(None, lr=5e-7, weight_decay=5e-5, scheduler=0.97, device=dev, variant=variant)
     teacher.load_state_dict(student.state_dict())
-    ops.bump_weight_epoch()
+    teacher.optimizer.sync_shadow()
     teacher.train()
     student.train()
     for p in teacher.model.parameters():

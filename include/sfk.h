@@ -204,11 +204,12 @@ int sfk_pseudo_label_threshold(const float* p, void* pseudo_i64, float* stats, i
 int sfk_denoise_labels(const float* t0, const float* gt, float* out, long long n, sfk_stream_t stream);
 
 /* ---- optimiser (SFM:32-37,158-162) and teacher refresh --------------------------------------------------------- */
-/* clip_grad_value_(clip) then Adam with L2 weight decay over flat f32 buffers; step is 1-based */
-int sfk_clip_adam_l2(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                     float eps, float weight_decay, float clip, int step, sfk_stream_t stream);
-/* t = decay*t + (1-decay)*s */
-int sfk_ema_lerp(float* t, const float* s, long long n, float decay, sfk_stream_t stream);
+/* clip_grad_value_(clip) then Adam with L2 weight decay over flat f32 buffers; step is 1-based.
+ * w_bf16 (optional, same element layout): bf16 shadow of the updated weights written in the same pass. */
+int sfk_clip_adam_l2(float* p, const float* g, float* m, float* v, void* w_bf16, long long n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, float clip, int step, sfk_stream_t stream);
+/* t = decay*t + (1-decay)*s ; t_bf16 (optional): bf16 shadow of the updated t */
+int sfk_ema_lerp(float* t, const float* s, void* t_bf16, long long n, float decay, sfk_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -67,7 +67,7 @@ int sfk_layernorm_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, co
 
 int sfk_dwconv3x3(const void* x, const float* wt, const float* bias, void* y, int B, int H, int W, int C, int mode,
                   sfk_stream_t stream) {
-  return dwconv3x3(x, wt, bias, y, B, H, W, C, mode, static_cast<cudaStream_t>(stream));
+  return dwconv3x3(x, wt, bias, y, nullptr, B, H, W, C, mode, static_cast<cudaStream_t>(stream));
 }
 int sfk_dwconv3x3_gelu_bwd(const void* x, const float* wt, const float* bias, const void* dg, void* dpre, float* dwt,
                            float* dbias, int B, int H, int W, int C, sfk_stream_t stream) {
@@ -191,12 +191,12 @@ int sfk_pseudo_label_threshold(const float* p, void* pseudo_i64, float* stats, i
 int sfk_denoise_labels(const float* t0, const float* gt, float* out, long long n, sfk_stream_t stream) {
   return denoise_labels(t0, gt, out, n, ST);
 }
-int sfk_clip_adam_l2(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                     float eps, float weight_decay, float clip, int step, sfk_stream_t stream) {
-  return clip_adam_l2(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, clip, step, ST);
+int sfk_clip_adam_l2(float* p, const float* g, float* m, float* v, void* w_bf16, long long n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, float clip, int step, sfk_stream_t stream) {
+  return clip_adam_l2(p, g, m, v, w_bf16, n, lr, beta1, beta2, eps, weight_decay, clip, step, ST);
 }
-int sfk_ema_lerp(float* t, const float* s, long long n, float decay, sfk_stream_t stream) {
-  return ema_lerp(t, s, n, decay, ST);
+int sfk_ema_lerp(float* t, const float* s, void* t_bf16, long long n, float decay, sfk_stream_t stream) {
+  return ema_lerp(t, s, t_bf16, n, decay, ST);
 }
 #undef ST
 

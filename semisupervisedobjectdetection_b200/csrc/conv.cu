@@ -11,17 +11,46 @@ namespace sfk {
 
 // ------------------------------------------------------------------------------------------------
 // depthwise 3x3, stride 1, pad 1.  x: bf16 [B,H,W,C].  wt: fp32 [9][C] (tap-major copy of weight[C,1,3,3]).
-// Each thread produces SEG consecutive outputs along W for VEC channels, loading a 3 x (SEG+2) window once.
+// Mapping: a warp = 32 consecutive channel groups (VEC channels each) of ONE (b, y, 4-pixel segment) position, so every
+// load/store instruction of a warp is one contiguous 256/512-byte run; the 8 warps of a block walk different positions.
+// Each thread produces SEG consecutive outputs along W, loading its 3 x (SEG+2) window once (4.5 loads per output).
+// Per-thread channel sums (bias gradients) are reduced across the block in shared memory -> one atomic per channel/block.
 // ------------------------------------------------------------------------------------------------
 static constexpr int DW_SEG = 4;
 
+// erf with |err| <= 1.5e-7 (Abramowitz-Stegun 7.1.26) from one rcp and one ex2; `e` = exp(-x*x) is passed in so the
+// GELU derivative can reuse it for the Gaussian pdf.
+__device__ __forceinline__ float erf_from_exp(float ax, float e) {
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  return 1.0f - p * t * e;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float e = __expf(-z * z);
+  const float er = copysignf(erf_from_exp(fabsf(z), e), x);
+  return 0.5f * x * (1.0f + er);
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  const float z = x * 0.70710678118654752440f;
+  const float e = __expf(-z * z);  // == exp(-x^2/2)
+  const float er = copysignf(erf_from_exp(fabsf(z), e), x);
+  return fmaf(x * 0.39894228040143267794f, e, 0.5f * (1.0f + er));
+}
+
 template <int VEC> struct VecIO;
 template <> struct VecIO<8> {
-  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* f) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p);
+  typedef uint4 packed;
+  static __device__ __forceinline__ packed ldp(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ packed zero() { return make_uint4(0, 0, 0, 0); }
+  static __device__ __forceinline__ void unpack(const packed& u, float* f) {
     float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
   }
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* f) { unpack(ldp(p), f); }
   static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* f) {
     uint4 u;
     u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
@@ -30,11 +59,14 @@ template <> struct VecIO<8> {
   }
 };
 template <> struct VecIO<4> {
-  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* f) {
-    const uint2 u = *reinterpret_cast<const uint2*>(p);
+  typedef uint2 packed;
+  static __device__ __forceinline__ packed ldp(const __nv_bfloat16* p) { return *reinterpret_cast<const uint2*>(p); }
+  static __device__ __forceinline__ packed zero() { return make_uint2(0, 0); }
+  static __device__ __forceinline__ void unpack(const packed& u, float* f) {
     float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
     f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
   }
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* f) { unpack(ldp(p), f); }
   static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* f) {
     uint2 u;
     u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
@@ -42,206 +74,242 @@ template <> struct VecIO<4> {
   }
 };
 
-// mode 0: y = gelu(conv(x) + bias)     mode 1: y = conv_flipped(x)  (input gradient of the conv)
-template <int MODE>
-__global__ void __launch_bounds__(256) dwconv3x3_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
-                                                        const float* __restrict__ bias, __nv_bfloat16* __restrict__ y, int B,
-                                                        int H, int W, int C) {
-  constexpr int VEC = 8;
-  const int CG = C / VEC;
-  const int nseg = (W + DW_SEG - 1) / DW_SEG;
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long total = (long long)B * H * nseg * CG;
-  if (idx >= total) return;
-  const int cg = (int)(idx % CG);
-  long long t = idx / CG;
-  const int seg = (int)(t % nseg);
-  t /= nseg;
-  const int yy = (int)(t % H);
-  const int b = (int)(t / H);
-  const int c0 = cg * VEC;
-  const int x0 = seg * DW_SEG;
-
-  float w[9][VEC];
+// block-level reduction of per-thread channel partials: sh[cg_local*VEC + v] accumulates over the 8 warps
+template <int VEC, int NV>
+__device__ __forceinline__ void dw_block_commit(float (&acc)[NV][VEC], float* sh, float* const* outs, int c0, int C, bool lane_ok) {
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < NV * 32 * VEC; i += 256) sh[i] = 0.f;
+  __syncthreads();
+  if (lane_ok) {
 #pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const int kk = MODE == 1 ? 8 - k : k;
-    const float4 a = __ldg(reinterpret_cast<const float4*>(wt + (long long)kk * C + c0));
-    const float4 bq = __ldg(reinterpret_cast<const float4*>(wt + (long long)kk * C + c0 + 4));
-    w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
-    w[k][4] = bq.x; w[k][5] = bq.y; w[k][6] = bq.z; w[k][7] = bq.w;
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) atomicAdd(&sh[(k * 32 + lane) * VEC + v], acc[k][v]);
   }
-  float acc[DW_SEG][VEC];
-#pragma unroll
-  for (int o = 0; o < DW_SEG; ++o)
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) acc[o][v] = 0.f;
-  if (MODE == 0) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c0));
-    const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
-#pragma unroll
-    for (int o = 0; o < DW_SEG; ++o) {
-      acc[o][0] = a.x; acc[o][1] = a.y; acc[o][2] = a.z; acc[o][3] = a.w;
-      acc[o][4] = bq.x; acc[o][5] = bq.y; acc[o][6] = bq.z; acc[o][7] = bq.w;
-    }
-  }
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int sy = yy + r - 1;
-    if (sy < 0 || sy >= H) continue;
-    const __nv_bfloat16* rowp = x + ((long long)(b * H + sy) * W) * C + c0;
-#pragma unroll
-    for (int j = 0; j < DW_SEG + 2; ++j) {
-      const int sx = x0 + j - 1;
-      if (sx < 0 || sx >= W) continue;
-      float f[VEC];
-      VecIO<VEC>::ld(rowp + (long long)sx * C, f);
-#pragma unroll
-      for (int tt = 0; tt < 3; ++tt) {
-        const int o = j - tt;  // output position that sees column j through tap tt
-        if (o >= 0 && o < DW_SEG) {
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[o][v] = fmaf(w[r * 3 + tt][v], f[v], acc[o][v]);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int o = 0; o < DW_SEG; ++o) {
-    if (x0 + o >= W) break;
-    if (MODE == 0) {
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) acc[o][v] = gelu_erf(acc[o][v]);
-    }
-    VecIO<VEC>::st(y + ((long long)(b * H + yy) * W + x0 + o) * C + c0, acc[o]);
+  __syncthreads();
+  const int cbase = c0 - lane * VEC;  // first channel of this block
+  for (int i = threadIdx.x; i < NV * 32 * VEC; i += 256) {
+    const int k = i / (32 * VEC), j = i % (32 * VEC);
+    if (cbase + j < C) atomicAdd(outs[k] + cbase + j, sh[i]);
   }
 }
 
-int dwconv3x3(const void* x, const float* wt, const float* bias, void* y, int B, int H, int W, int C, int mode,
+// mode 0: y = gelu(conv(x) + bias)     mode 1: y = conv_flipped(x)  (input gradient of the conv); colsum (+)= sum_pixels y
+template <int MODE>
+__global__ void __launch_bounds__(256, 2) dwconv3x3_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
+                                                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                           float* __restrict__ colsum, int B, int H, int W, int C,
+                                                           int pos_per_block) {
+  constexpr int VEC = 8;
+  __shared__ float sh[32 * VEC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = (blockIdx.x * 32 + lane) * VEC;
+  const bool lane_ok = c0 < C;
+  const int nseg = (W + DW_SEG - 1) / DW_SEG;
+  const long long npos = (long long)B * H * nseg;
+  const long long p0 = (long long)blockIdx.y * pos_per_block;
+  long long p1 = p0 + pos_per_block;
+  if (p1 > npos) p1 = npos;
+  float w[9][VEC];
+  float bs[VEC];
+  float csum[1][VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) { bs[v] = 0.f; csum[0][v] = 0.f; }
+  if (lane_ok) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const int kk = MODE == 1 ? 8 - k : k;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(wt + (long long)kk * C + c0));
+      const float4 bq = __ldg(reinterpret_cast<const float4*>(wt + (long long)kk * C + c0 + 4));
+      w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
+      w[k][4] = bq.x; w[k][5] = bq.y; w[k][6] = bq.z; w[k][7] = bq.w;
+    }
+    if (MODE == 0) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c0));
+      const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
+      bs[0] = a.x; bs[1] = a.y; bs[2] = a.z; bs[3] = a.w; bs[4] = bq.x; bs[5] = bq.y; bs[6] = bq.z; bs[7] = bq.w;
+    }
+    for (long long pos = p0 + warp; pos < p1; pos += 8) {
+      const int seg = (int)(pos % nseg);
+      const long long t = pos / nseg;
+      const int yy = (int)(t % H);
+      const int b = (int)(t / H);
+      const int x0 = seg * DW_SEG;
+      float acc[DW_SEG][VEC];
+#pragma unroll
+      for (int o = 0; o < DW_SEG; ++o)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[o][v] = bs[v];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int sy = yy + r - 1;
+        if (sy < 0 || sy >= H) continue;
+        const __nv_bfloat16* rowp = x + ((long long)(b * H + sy) * W) * C + c0;
+#pragma unroll
+        for (int j = 0; j < DW_SEG + 2; ++j) {
+          const int sx = x0 + j - 1;
+          if (sx < 0 || sx >= W) continue;
+          float f[VEC];
+          VecIO<VEC>::ld(rowp + (long long)sx * C, f);
+#pragma unroll
+          for (int tt = 0; tt < 3; ++tt) {
+            const int o = j - tt;  // output position that sees column j through tap tt
+            if (o >= 0 && o < DW_SEG) {
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) acc[o][v] = fmaf(w[r * 3 + tt][v], f[v], acc[o][v]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < DW_SEG; ++o) {
+        if (x0 + o >= W) break;
+        if (MODE == 0) {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[o][v] = gelu_fast(acc[o][v]);
+        } else {
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) csum[0][v] += acc[o][v];
+        }
+        VecIO<VEC>::st(y + ((long long)(b * H + yy) * W + x0 + o) * C + c0, acc[o]);
+      }
+    }
+  }
+  if (MODE == 1 && colsum != nullptr) {
+    float* outs[1] = {colsum};
+    dw_block_commit<VEC, 1>(csum, sh, outs, c0, C, lane_ok);
+  }
+}
+
+static void dw_grid(int C, int vec, long long npos, dim3& grid, int& ppb) {
+  const int gx = (C / vec + 31) / 32;
+  long long gy = ((long long)num_sms() * 8 + gx - 1) / gx;   // ~8 blocks per SM in flight across the grid
+  if (gy < 1) gy = 1;
+  long long per = (npos + gy - 1) / gy;
+  if (per < 8) per = 8;
+  per = (per + 7) / 8 * 8;
+  gy = (npos + per - 1) / per;
+  ppb = (int)per;
+  grid = dim3(gx, (unsigned)gy);
+}
+
+int dwconv3x3(const void* x, const float* wt, const float* bias, void* y, float* colsum, int B, int H, int W, int C, int mode,
               cudaStream_t stream) {
   SFK_REQUIRE(C % 8 == 0, "dwconv3x3: C=%d must be a multiple of 8", C);
-  const long long total = (long long)B * H * ((W + DW_SEG - 1) / DW_SEG) * (C / 8);
-  if (total == 0) return 0;
-  const unsigned grid = (unsigned)((total + 255) / 256);
+  const long long npos = (long long)B * H * ((W + DW_SEG - 1) / DW_SEG);
+  if (npos == 0) return 0;
+  dim3 grid;
+  int ppb;
+  dw_grid(C, 8, npos, grid, ppb);
   if (mode == 0)
-    dwconv3x3_kernel<0><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, wt, bias, (__nv_bfloat16*)y, B, H, W, C);
+    dwconv3x3_kernel<0><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, wt, bias, (__nv_bfloat16*)y, nullptr, B, H, W, C, ppb);
   else
-    dwconv3x3_kernel<1><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, wt, nullptr, (__nv_bfloat16*)y, B, H, W, C);
+    dwconv3x3_kernel<1><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, wt, nullptr, (__nv_bfloat16*)y, colsum, B, H, W, C, ppb);
   return check_launch("dwconv3x3_kernel");
 }
 
 // Backward stage 1: recompute pre = conv(x)+bias, dpre = dg * gelu'(pre); accumulate dW[9][C] and db[C].
-// Each thread walks POS consecutive (b, y, seg) positions for VEC=4 channels and issues its atomics once.
-template <int DUMMY>
-__global__ void __launch_bounds__(256) dwconv3x3_gelu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
-                                                                 const float* __restrict__ bias,
-                                                                 const __nv_bfloat16* __restrict__ dg,
-                                                                 __nv_bfloat16* __restrict__ dpre, float* __restrict__ dwt,
-                                                                 float* __restrict__ dbias, int B, int H, int W, int C,
-                                                                 int pos_per_thread) {
+// Window kept packed (bf16) to stay under 128 registers -> 2 blocks (16 warps) per SM.
+__global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
+                                                                    const float* __restrict__ bias,
+                                                                    const __nv_bfloat16* __restrict__ dg,
+                                                                    __nv_bfloat16* __restrict__ dpre, float* __restrict__ dwt,
+                                                                    float* __restrict__ dbias, int B, int H, int W, int C,
+                                                                    int pos_per_block) {
   constexpr int VEC = 4;
-  const int CG = C / VEC;
+  __shared__ float sh[10 * 32 * VEC];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c0 = (blockIdx.x * 32 + lane) * VEC;
+  const bool lane_ok = c0 < C;
   const int nseg = (W + DW_SEG - 1) / DW_SEG;
   const long long npos = (long long)B * H * nseg;
-  const long long nchunks = (npos + pos_per_thread - 1) / pos_per_thread;
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= nchunks * CG) return;
-  const int cg = (int)(idx % CG);
-  const long long chunk = idx / CG;
-  const int c0 = cg * VEC;
-  float w[9][VEC], dw[9][VEC], db[VEC], bs[VEC];
-#pragma unroll
-  for (int k = 0; k < 9; ++k) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(wt + (long long)k * C + c0));
-    w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) dw[k][v] = 0.f;
-  }
-  {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c0));
-    bs[0] = a.x; bs[1] = a.y; bs[2] = a.z; bs[3] = a.w;
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) db[v] = 0.f;
-  }
-  long long p1 = (chunk + 1) * pos_per_thread;
+  const long long p0 = (long long)blockIdx.y * pos_per_block;
+  long long p1 = p0 + pos_per_block;
   if (p1 > npos) p1 = npos;
-  for (long long pos = chunk * pos_per_thread; pos < p1; ++pos) {
-    const int seg = (int)(pos % nseg);
-    const long long t = pos / nseg;
-    const int yy = (int)(t % H);
-    const int b = (int)(t / H);
-    const int x0 = seg * DW_SEG;
-    float win[3][DW_SEG + 2][VEC];
+  float w[9][VEC], acc[10][VEC], bs[VEC];  // acc[0..8] = dW taps, acc[9] = dbias
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int sy = yy + r - 1;
-      const bool vy = sy >= 0 && sy < H;
+  for (int k = 0; k < 10; ++k)
 #pragma unroll
-      for (int j = 0; j < DW_SEG + 2; ++j) {
-        const int sx = x0 + j - 1;
-        if (vy && sx >= 0 && sx < W) {
-          VecIO<VEC>::ld(x + ((long long)(b * H + sy) * W + sx) * C + c0, win[r][j]);
-        } else {
+    for (int v = 0; v < VEC; ++v) acc[k][v] = 0.f;
+  if (lane_ok) {
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) win[r][j][v] = 0.f;
+    for (int k = 0; k < 9; ++k) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(wt + (long long)k * C + c0));
+      w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
+    }
+    {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c0));
+      bs[0] = a.x; bs[1] = a.y; bs[2] = a.z; bs[3] = a.w;
+    }
+    for (long long pos = p0 + warp; pos < p1; pos += 8) {
+      const int seg = (int)(pos % nseg);
+      const long long t = pos / nseg;
+      const int yy = (int)(t % H);
+      const int b = (int)(t / H);
+      const int x0 = seg * DW_SEG;
+      VecIO<VEC>::packed win[3][DW_SEG + 2];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int sy = yy + r - 1;
+        const bool vy = sy >= 0 && sy < H;
+#pragma unroll
+        for (int j = 0; j < DW_SEG + 2; ++j) {
+          const int sx = x0 + j - 1;
+          win[r][j] = (vy && sx >= 0 && sx < W) ? VecIO<VEC>::ldp(x + ((long long)(b * H + sy) * W + sx) * C + c0)
+                                                : VecIO<VEC>::zero();
         }
       }
-    }
 #pragma unroll
-    for (int o = 0; o < DW_SEG; ++o) {
-      if (x0 + o >= W) break;
-      float pre[VEC];
+      for (int o = 0; o < DW_SEG; ++o) {
+        if (x0 + o >= W) break;
+        float f[9][VEC];
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) pre[v] = bs[v];
+        for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int r = 0; r < 3; ++r)
+          for (int tt = 0; tt < 3; ++tt) VecIO<VEC>::unpack(win[r][o + tt], f[r * 3 + tt]);
+        float pre[VEC];
 #pragma unroll
-        for (int tt = 0; tt < 3; ++tt)
+        for (int v = 0; v < VEC; ++v) pre[v] = bs[v];
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) pre[v] = fmaf(w[r * 3 + tt][v], win[r][o + tt][v], pre[v]);
-      const long long off = ((long long)(b * H + yy) * W + x0 + o) * C + c0;
-      float g[VEC], d[VEC];
-      VecIO<VEC>::ld(dg + off, g);
+        for (int k = 0; k < 9; ++k)
 #pragma unroll
-      for (int v = 0; v < VEC; ++v) {
-        d[v] = g[v] * gelu_erf_grad(pre[v]);
-        db[v] += d[v];
+          for (int v = 0; v < VEC; ++v) pre[v] = fmaf(w[k][v], f[k][v], pre[v]);
+        const long long off = ((long long)(b * H + yy) * W + x0 + o) * C + c0;
+        float g[VEC], d[VEC];
+        VecIO<VEC>::ld(dg + off, g);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+          d[v] = g[v] * gelu_grad_fast(pre[v]);
+          acc[9][v] += d[v];
+        }
+        VecIO<VEC>::st(dpre + off, d);
+#pragma unroll
+        for (int k = 0; k < 9; ++k)
+#pragma unroll
+          for (int v = 0; v < VEC; ++v) acc[k][v] = fmaf(d[v], f[k][v], acc[k][v]);
       }
-      VecIO<VEC>::st(dpre + off, d);
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int tt = 0; tt < 3; ++tt)
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) dw[r * 3 + tt][v] = fmaf(d[v], win[r][o + tt][v], dw[r * 3 + tt][v]);
     }
   }
   if (dwt != nullptr) {
+    float* outs[10];
 #pragma unroll
-    for (int k = 0; k < 9; ++k)
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) atomicAdd(dwt + (long long)k * C + c0 + v, dw[k][v]);
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) atomicAdd(dbias + c0 + v, db[v]);
+    for (int k = 0; k < 9; ++k) outs[k] = dwt + (long long)k * C;
+    outs[9] = dbias;
+    dw_block_commit<VEC, 10>(acc, sh, outs, c0, C, lane_ok);
   }
 }
 
 int dwconv3x3_gelu_bwd(const void* x, const float* wt, const float* bias, const void* dg, void* dpre, float* dwt,
                        float* dbias, int B, int H, int W, int C, cudaStream_t stream) {
   SFK_REQUIRE(C % 8 == 0, "dwconv3x3_gelu_bwd: C=%d must be a multiple of 8", C);
-  const int CG = C / 4;
+  SFK_REQUIRE((dwt == nullptr) == (dbias == nullptr), "dwconv3x3_gelu_bwd: pass both or neither of dwt / dbias");
   const long long npos = (long long)B * H * ((W + DW_SEG - 1) / DW_SEG);
   if (npos == 0) return 0;
-  // enough threads to fill the machine (~16 warps/SM), as few atomics as possible
-  long long want_threads = (long long)num_sms() * 2048;
-  long long chunks = want_threads / CG;
-  if (chunks < 1) chunks = 1;
-  int ppt = (int)((npos + chunks - 1) / chunks);
-  if (ppt < 1) ppt = 1;
-  chunks = (npos + ppt - 1) / ppt;
-  const long long total = chunks * CG;
-  dwconv3x3_gelu_bwd_kernel<0><<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(
-      (const __nv_bfloat16*)x, wt, bias, (const __nv_bfloat16*)dg, (__nv_bfloat16*)dpre, dwt, dbias, B, H, W, C, ppt);
+  dim3 grid;
+  int ppb;
+  dw_grid(C, 4, npos, grid, ppb);
+  dwconv3x3_gelu_bwd_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, wt, bias, (const __nv_bfloat16*)dg,
+                                                      (__nv_bfloat16*)dpre, dwt, dbias, B, H, W, C, ppb);
   return check_launch("dwconv3x3_gelu_bwd_kernel");
 }
 

@@ -231,7 +231,7 @@ int layer_forward(const sfk_layer_dims& dd, const sfk_layer_params& p, const flo
   TRY(layernorm_fwd(s.x1, 0, spatial_map(d), p.ln2_g, p.ln2_b, s.xn2, 1, s.mean2, s.rstd2, rows_sp, (int)C, 1e-5f, st));
   // MixFFN
   TRY(gemm_bf16(linear_fwd(s.xn2, C, p.w1, C, rows_sp, d.hidden, C, p.b1, s.h1, d.hidden, 1), st));
-  TRY(dwconv3x3(s.h1, p.dw_wt, p.dw_b, s.g, (int)d.B, (int)d.H, (int)d.W, (int)d.hidden, 0, st));
+  TRY(dwconv3x3(s.h1, p.dw_wt, p.dw_b, s.g, nullptr, (int)d.B, (int)d.H, (int)d.W, (int)d.hidden, 0, st));
   {
     GemmDesc g = linear_fwd(s.g, d.hidden, p.w2, d.hidden, rows_sp, C, d.hidden, p.b2, out, C, 0);
     g.residual = s.x1; g.ldr = C; g.res_map = spatial_map(d);
@@ -276,10 +276,10 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
   SFK_REQUIRE(sc.off <= scratch_bytes, "layer_backward: scratch arena too small (%zu < %zu)", scratch_bytes, sc.off);
 
   // ---- MixFFN branch ----
-  TRY(scale_cast(dout, 0, id, dmlp, 1, id, p.drop_scale_mlp, (int)d.N, rows_sp, (int)C, st));
+  // drop-path backward + bf16 cast, fused with the dense2 bias gradient (column sums of dmlp)
+  TRY(scale_cast_sum(dout, 0, id, dmlp, 1, id, p.drop_scale_mlp, (int)d.N, rows_sp, (int)C, gr.db2, nullptr, 0, st));
   TRY(gemm_bf16(linear_dgrad(dmlp, C, p.w2, Hd, rows_sp, C, Hd, dg, Hd, 1), st));
   if (gr.dw2) TRY(gemm_bf16(linear_wgrad(dmlp, C, s.g, Hd, rows_sp, C, Hd, gr.dw2, Hd), st));
-  if (gr.db2) TRY(colsum(dmlp, 1, C, gr.db2, rows_sp, (int)C, st));
   {
     const bool want = gr.ddw != nullptr;
     if (want) {
@@ -291,10 +291,10 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
                            (int)d.H, (int)d.W, (int)Hd, st));
     if (want) TRY(dw_wgrad_from_tap(dw_stage, gr.ddw, (int)Hd, st));
   }
-  TRY(dwconv3x3(dpre, p.dw_wt, nullptr, dh1, (int)d.B, (int)d.H, (int)d.W, (int)Hd, 1, st));
+  // input gradient of the depthwise conv; the dense1 bias gradient (column sums of dh1) is produced by the same pass
+  TRY(dwconv3x3(dpre, p.dw_wt, nullptr, dh1, gr.db1, (int)d.B, (int)d.H, (int)d.W, (int)Hd, 1, st));
   TRY(gemm_bf16(linear_dgrad(dh1, Hd, p.w1, C, rows_sp, Hd, C, dxn2, C, 1), st));
   if (gr.dw1) TRY(gemm_bf16(linear_wgrad(dh1, Hd, s.xn2, C, rows_sp, Hd, C, gr.dw1, C), st));
-  if (gr.db1) TRY(colsum(dh1, 1, Hd, gr.db1, rows_sp, (int)Hd, st));
   // LN2 backward + residual gradient -> dx1 (spatial rows); front rows of dx1 come from the returned cls/prompt rows
   TRY(layernorm_bwd(dxn2, 1, s.x1, 0, spatial_map(d), s.mean2, s.rstd2, p.ln2_g, dout, id, dx1, 0, spatial_map(d), gr.dln2_g,
                     gr.dln2_b, rows_sp, (int)C, st));
@@ -309,10 +309,9 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
     }
   }
   // ---- attention branch ----
-  TRY(scale_cast(dx1, 0, id, da, 1, id, p.drop_scale_attn, (int)d.T, rows_all, (int)C, st));
+  TRY(scale_cast_sum(dx1, 0, id, da, 1, id, p.drop_scale_attn, (int)d.T, rows_all, (int)C, gr.dbo, nullptr, 0, st));
   TRY(gemm_bf16(linear_dgrad(da, C, p.wo, C, rows_all, C, C, dctx, C, 1), st));
   if (gr.dwo) TRY(gemm_bf16(linear_wgrad(da, C, s.ctx, C, rows_all, C, C, gr.dwo, C), st));
-  if (gr.dbo) TRY(colsum(da, 1, C, gr.dbo, rows_all, (int)C, st));
   {
     cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)rows_all * C * sizeof(float), st);
     SFK_REQUIRE(e == cudaSuccess, "layer_backward: memset failed");
@@ -328,14 +327,20 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
     a.dq = dq32; a.ld_dq = C; a.dq_batch_stride = d.T * C;
     a.dk = dkv32; a.dv = dkv32 + C; a.ld_dkv = 2 * C; a.dkv_batch_stride = d.Tk * 2 * C;
     TRY(attention_bwd(a, st));
-    TRY(scale_cast(dq32, 0, id, dq16, 1, id, nullptr, 1, rows_all, (int)C, st));
-    TRY(scale_cast(dkv32, 0, id, dkv16, 1, id, nullptr, 1, rows_kv, (int)(2 * C), st));
+    // fp32 -> bf16 for the projection dgrad/wgrad GEMMs, fused with the q / k / v bias gradients
+    TRY(scale_cast_sum(dq32, 0, id, dq16, 1, id, nullptr, 1, rows_all, (int)C, gr.dbq, nullptr, 0, st));
+    if (gr.dbk != nullptr && gr.dbv != nullptr)
+      TRY(scale_cast_sum(dkv32, 0, id, dkv16, 1, id, nullptr, 1, rows_kv, (int)(2 * C), gr.dbk, gr.dbv, (int)C, st));
+    else
+      TRY(scale_cast(dkv32, 0, id, dkv16, 1, id, nullptr, 1, rows_kv, (int)(2 * C), st));
   }
   // K | V projections
   if (gr.dwk) TRY(gemm_bf16(linear_wgrad(dkv16, 2 * C, s.kvn, C, rows_kv, C, C, gr.dwk, C), st));
   if (gr.dwv) TRY(gemm_bf16(linear_wgrad(dkv16 + C, 2 * C, s.kvn, C, rows_kv, C, C, gr.dwv, C), st));
-  if (gr.dbk) TRY(colsum(dkv16, 1, 2 * C, gr.dbk, rows_kv, (int)C, st));
-  if (gr.dbv) TRY(colsum(dkv16 + C, 1, 2 * C, gr.dbv, rows_kv, (int)C, st));
+  if ((gr.dbk == nullptr) != (gr.dbv == nullptr)) {  // only one of the two biases trainable: separate column sums
+    if (gr.dbk) TRY(colsum(dkv16, 1, 2 * C, gr.dbk, rows_kv, (int)C, st));
+    if (gr.dbv) TRY(colsum(dkv16 + C, 1, 2 * C, gr.dbv, rows_kv, (int)C, st));
+  }
   if (d.sr > 1) {
     const long long Ksr = d.sr * d.sr * C, rows_red = d.B * d.Nkv;
     __nv_bfloat16* dkvn = sc.take<__nv_bfloat16>(rows_kv * C);
@@ -375,7 +380,6 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
     TRY(gemm_bf16(g, st));
   }
   if (gr.dwq) TRY(gemm_bf16(linear_wgrad(dq16, C, s.xn1, C, rows_all, C, C, gr.dwq, C), st));
-  if (gr.dbq) TRY(colsum(dq16, 1, C, gr.dbq, rows_all, (int)C, st));
   // LN1 backward + residual gradient
   if (d.P == 0) {
     TRY(layernorm_bwd(dxn1t, 1, xcat, 0, id, s.mean1, s.rstd1, p.ln1_g, dx1, id, dx, 0, id, gr.dln1_g, gr.dln1_b, rows_all, (int)C,

@@ -242,38 +242,82 @@ int layernorm_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, RowMap
 }
 
 // ------------------------------------------------------------------------------------------------
-// y_bf16[row, :] = x_f32[map(row), :] * scale[row / rows_per_scale]   (drop-path backward / plain cast)
+// y[out_map(row), :] = x[in_map(row), :] * scale[row / rows_per_scale]  with dtype conversion (drop-path backward, casts),
+// optionally fused with the column sums of y (bias gradients):  colsum0[c] += sum_rows y[row, c] for c < split,
+// colsum1[c - split] += ... for c >= split.
+// Mapping: every thread owns one fixed 4-column chunk and walks rows, so the column sums live in registers; a warp reads
+// 32 consecutive chunks (512 B) of one row.
 // ------------------------------------------------------------------------------------------------
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) scale_cast_kernel(const TIn* __restrict__ x, RowMap in_map, TOut* __restrict__ y,
                                                          RowMap out_map, const float* __restrict__ scale, int rows_per_scale,
-                                                         long long rows, int C4) {
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= rows * C4) return;
-  const long long row = idx / C4;
-  const int c = (int)(idx - row * C4) * 4;
-  float4 v = Ld4<TIn>::ld(x + map_row(row, in_map) * (C4 * 4LL) + c);
-  if (scale) {
-    const float s = scale[row / rows_per_scale];
-    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+                                                         long long rows, int C4, int cwb, int rows_per_block,
+                                                         float* __restrict__ colsum0, float* __restrict__ colsum1, int split) {
+  __shared__ float sh[256 * 4];
+  const int lanes_r = 256 / cwb;                 // row lanes per block
+  const int rl = threadIdx.x / cwb;              // this thread's row lane
+  const int c4 = blockIdx.x * cwb + (threadIdx.x % cwb);
+  const bool active = rl < lanes_r && c4 < C4;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    long long r1 = r0 + rows_per_block;
+    if (r1 > rows) r1 = rows;
+    const long long ldc = (long long)C4 * 4;
+    for (long long row = r0 + rl; row < r1; row += lanes_r) {
+      float4 v = Ld4<TIn>::ld(x + map_row(row, in_map) * ldc + c4 * 4);
+      if (scale) {
+        const float sc = scale[row / rows_per_scale];
+        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+      }
+      Ld4<TOut>::st(y + map_row(row, out_map) * ldc + c4 * 4, v);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
   }
-  Ld4<TOut>::st(y + map_row(row, out_map) * (C4 * 4LL) + c, v);
+  if (colsum0 == nullptr) return;
+  *reinterpret_cast<float4*>(&sh[threadIdx.x * 4]) = acc;
+  __syncthreads();
+  if (threadIdx.x < cwb && c4 < C4) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < lanes_r; ++r) {
+      const float4 u = *reinterpret_cast<const float4*>(&sh[(r * cwb + threadIdx.x) * 4]);
+      t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+    }
+    const int c = c4 * 4;
+    float* dst = c < split ? colsum0 + c : colsum1 + (c - split);
+    atomicAdd(dst, t.x); atomicAdd(dst + 1, t.y); atomicAdd(dst + 2, t.z); atomicAdd(dst + 3, t.w);
+  }
 }
 
-int scale_cast(const void* x, int x_bf16, RowMap in_map, void* y, int y_bf16, RowMap out_map, const float* scale,
-               int rows_per_scale, long long rows, int C, cudaStream_t stream) {
-  SFK_REQUIRE(C % 4 == 0, "scale_cast: C=%d must be a multiple of 4", C);
+int scale_cast_sum(const void* x, int x_bf16, RowMap in_map, void* y, int y_bf16, RowMap out_map, const float* scale,
+                   int rows_per_scale, long long rows, int C, float* colsum0, float* colsum1, int split, cudaStream_t stream) {
+  SFK_REQUIRE(C % 4 == 0 && split % 4 == 0, "scale_cast: C=%d and split must be multiples of 4", C);
   if (rows == 0) return 0;
-  const long long n = rows * (C / 4);
-  const unsigned grid = (unsigned)((n + 255) / 256);
+  const int C4 = C / 4;
+  const int cwb = C4 < 256 ? C4 : 256;
+  const int gx = (C4 + cwb - 1) / cwb;
+  const int lanes_r = 256 / cwb;
+  long long gy = ((long long)num_sms() * 8 + gx - 1) / gx;
+  long long rpb = (rows + gy - 1) / gy;
+  if (rpb < lanes_r) rpb = lanes_r;
+  gy = (rows + rpb - 1) / rpb;
   if (rows_per_scale <= 0) rows_per_scale = 1;
-#define LAUNCH(TI, TO) scale_cast_kernel<TI, TO><<<grid, 256, 0, stream>>>((const TI*)x, in_map, (TO*)y, out_map, scale, rows_per_scale, rows, C / 4)
+  if (colsum0 != nullptr && colsum1 == nullptr) { colsum1 = colsum0; split = C; }
+  dim3 grid(gx, (unsigned)gy);
+#define LAUNCH(TI, TO)                                                                                                       \
+  scale_cast_kernel<TI, TO><<<grid, 256, 0, stream>>>((const TI*)x, in_map, (TO*)y, out_map, scale, rows_per_scale, rows, C4, \
+                                                      cwb, (int)rpb, colsum0, colsum1, split)
   if (x_bf16 && y_bf16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
   else if (x_bf16) LAUNCH(__nv_bfloat16, float);
   else if (y_bf16) LAUNCH(float, __nv_bfloat16);
   else LAUNCH(float, float);
 #undef LAUNCH
   return check_launch("scale_cast_kernel");
+}
+
+int scale_cast(const void* x, int x_bf16, RowMap in_map, void* y, int y_bf16, RowMap out_map, const float* scale,
+               int rows_per_scale, long long rows, int C, cudaStream_t stream) {
+  return scale_cast_sum(x, x_bf16, in_map, y, y_bf16, out_map, scale, rows_per_scale, rows, C, nullptr, nullptr, 0, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -74,13 +74,15 @@ int layernorm_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, RowMap
                   RowMap dx_map, float* dgamma, float* dbeta, long long rows, int C, cudaStream_t stream);
 int scale_cast(const void* x, int x_bf16, RowMap in_map, void* y, int y_bf16, RowMap out_map, const float* scale,
                int rows_per_scale, long long rows, int C, cudaStream_t stream);
+int scale_cast_sum(const void* x, int x_bf16, RowMap in_map, void* y, int y_bf16, RowMap out_map, const float* scale,
+                   int rows_per_scale, long long rows, int C, float* colsum0, float* colsum1, int split, cudaStream_t stream);
 int colsum(const void* x, int x_bf16, long long ld, float* out, long long rows, int C, cudaStream_t stream);
 int concat_front(const float* front, long long front_batch_stride, const float* x, float* out, int B, int P, int N, int C,
                  cudaStream_t stream);
 int front_grad_sum(const float* g, float* dfront, int B, int P, int T, int C, cudaStream_t stream);
 
 // ---- conv.cu ----
-int dwconv3x3(const void* x, const float* wt, const float* bias, void* y, int B, int H, int W, int C, int mode,
+int dwconv3x3(const void* x, const float* wt, const float* bias, void* y, float* colsum, int B, int H, int W, int C, int mode,
               cudaStream_t stream);
 int dwconv3x3_gelu_bwd(const void* x, const float* wt, const float* bias, const void* dg, void* dpre, float* dwt,
                        float* dbias, int B, int H, int W, int C, cudaStream_t stream);
@@ -142,8 +144,8 @@ int pseudo_label_threshold(const float* p, long long* pseudo, float* stats, int 
 int denoise_labels(const float* t0, const float* gt, float* out, long long n, cudaStream_t stream);
 
 // ---- optim.cu ----
-int clip_adam_l2(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-                 float wd, float clip, int step, cudaStream_t stream);
-int ema_lerp(float* t, const float* s, long long n, float decay, cudaStream_t stream);
+int clip_adam_l2(float* p, const float* g, float* m, float* v, void* w16, long long n, float lr, float beta1, float beta2,
+                 float eps, float wd, float clip, int step, cudaStream_t stream);
+int ema_lerp(float* t, const float* s, void* w16, long long n, float decay, cudaStream_t stream);
 
 }  // namespace sfk

@@ -381,20 +381,28 @@ class SegformerLayer(nn.Module):
             a, m = self.attention.self, self.mlp
             C = a.hidden_size
             sh = {}
-            sh["wq"] = ops.cast_bf16(a.query.weight.detach())
-            wkv = torch.empty(2 * C, C, device=a.key.weight.device, dtype=torch.bfloat16)
-            ops.call("sfk_cast_2d", a.key.weight.data_ptr(), C, wkv.data_ptr(), C, C, C, C, ops.stream())
-            ops.call("sfk_cast_2d", a.value.weight.data_ptr(), C, wkv[C:].data_ptr(), C, C, C, C, ops.stream())
+            sh["wq"] = ops.weight_bf16(a.query.weight)
+            wk, wv = ops.weight_bf16(a.key.weight), ops.weight_bf16(a.value.weight)
+            if wv.data_ptr() == wk.data_ptr() + 2 * C * C:   # adjacent in FusedClipAdam's flat shadow: a free [2C, C] view
+                wkv = torch.as_strided(wk, (2 * C, C), (C, 1))
+            else:
+                wkv = torch.empty(2 * C, C, device=a.key.weight.device, dtype=torch.bfloat16)
+                ops.call("sfk_cast_2d", a.key.weight.data_ptr(), C, wkv.data_ptr(), C, C, C, C, ops.stream())
+                ops.call("sfk_cast_2d", a.value.weight.data_ptr(), C, wkv[C:].data_ptr(), C, C, C, C, ops.stream())
             sh["wkv"] = wkv
-            sh["bkv"] = torch.cat([a.key.bias.detach(), a.value.bias.detach()]).contiguous()
-            sh["wo"] = ops.cast_bf16(self.attention.output.dense.weight.detach())
+            bk, bv = a.key.bias.detach(), a.value.bias.detach()
+            if bv.data_ptr() == bk.data_ptr() + 4 * C:
+                sh["bkv"] = torch.as_strided(bk, (2 * C,), (1,))
+            else:
+                sh["bkv"] = torch.cat([bk, bv]).contiguous()
+            sh["wo"] = ops.weight_bf16(self.attention.output.dense.weight)
             if a.sr_ratio > 1:
                 sr = a.sr_ratio
                 wsr = torch.empty(C, sr * sr * C, device=wkv.device, dtype=torch.bfloat16)
                 ops.call("sfk_conv_weight_ohwi", a.sr.weight.data_ptr(), wsr.data_ptr(), C, C, sr, sr, sr * sr * C, ops.stream())
                 sh["wsr"] = wsr
-            sh["w1"] = ops.cast_bf16(m.dense1.weight.detach())
-            sh["w2"] = ops.cast_bf16(m.dense2.weight.detach())
+            sh["w1"] = ops.weight_bf16(m.dense1.weight)
+            sh["w2"] = ops.weight_bf16(m.dense2.weight)
             hid = m.dense1.out_features
             wt = torch.empty(9, hid, device=wkv.device, dtype=torch.float32)
             ops.call("sfk_dw_weight_to_tap", m.dwconv.dwconv.weight.data_ptr(), wt.data_ptr(), hid, ops.stream())
@@ -792,8 +800,8 @@ class SegformerDecodeHead(SegformerPreTrainedModel):
         key = _versions(params)
         if self._sh_key != key:
             dec = self.config.decoder_hidden_size
-            self._sh = {"wc": [ops.cast_bf16(m.proj.weight.detach()) for m in self.linear_c],
-                        "wf": ops.cast_bf16(self.linear_fuse.weight.detach().reshape(dec, -1))}
+            self._sh = {"wc": [ops.weight_bf16(m.proj.weight) for m in self.linear_c],
+                        "wf": ops.weight_bf16(self.linear_fuse.weight)}
             self._sh_key = key
         return self._sh
 

@@ -98,6 +98,19 @@ def cast_bf16(src: torch.Tensor, cols_padded: Optional[int] = None) -> torch.Ten
     return dst
 
 
+def weight_bf16(p: torch.Tensor) -> torch.Tensor:
+    """bf16 [rows, cols] GEMM operand of an fp32 weight.  Parameters owned by FusedClipAdam carry an always-current view of
+    its flat bf16 shadow (refreshed by the Adam / EMA kernels); anything else is cast on the fly."""
+    w16 = getattr(p, "_sfk_w16", None)
+    if w16 is not None and w16.device == p.device:
+        if getattr(p, "_sfk_w16_version", -1) != p._version:   # written through PyTorch since the last sync
+            src = p.detach().reshape(p.shape[0], -1)
+            call("sfk_cast_2d", _p(src), src.stride(0), _p(w16), src.shape[1], src.shape[0], src.shape[1], src.shape[1], stream())
+            p._sfk_w16_version = p._version
+        return w16.view(p.shape[0], -1)
+    return cast_bf16(p.detach())
+
+
 def layernorm_fwd(x, gamma, beta, out_bf16=True, need_stats=True, eps=1e-5):
     rows, C = x.numel() // x.shape[-1], x.shape[-1]
     y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16 if out_bf16 else torch.float32)

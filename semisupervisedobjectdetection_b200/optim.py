@@ -15,6 +15,10 @@ import torch
 from . import ops
 
 
+_IN_LAYER_RANK = {"attention.self.key.weight": 0, "attention.self.value.weight": 1,   # adjacent -> one [2C, C] K|V GEMM operand
+                  "attention.self.key.bias": 2, "attention.self.value.bias": 3}         # adjacent -> one [2C] bias
+
+
 def _exec_order_key(name: str):
     """Sort key placing parameters in forward-execution order (so backward finalises gradients back-to-front)."""
     m = re.search(r"encoder\.patch_embeddings\.(\d+)\.", name)
@@ -22,7 +26,11 @@ def _exec_order_key(name: str):
         return (int(m.group(1)), 0, 0, name)
     m = re.search(r"encoder\.block\.(\d+)\.(\d+)\.", name)
     if m:
-        return (int(m.group(1)), 1, int(m.group(2)), name)
+        rank = 9
+        for suffix, r in _IN_LAYER_RANK.items():
+            if name.endswith(suffix):
+                rank = r
+        return (int(m.group(1)), 1, int(m.group(2)), rank, name)
     m = re.search(r"encoder\.layer_norm\.(\d+)\.", name)
     if m:
         return (int(m.group(1)), 2, 0, name)
@@ -56,6 +64,7 @@ class FusedClipAdam(torch.optim.Optimizer):
         self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_v = torch.zeros(total, device=dev, dtype=torch.float32)
+        self.flat_w16 = torch.zeros(total, device=dev, dtype=torch.bfloat16)  # bf16 GEMM shadow, same element layout
         self._offsets = offs
         self._params = ps
         for p, o in zip(ps, offs):
@@ -65,6 +74,15 @@ class FusedClipAdam(torch.optim.Optimizer):
             p.data = view
             p.grad = self.flat_g[o:o + n].view(p.shape)
             p._sfk_live = False
+            p._sfk_w16 = self.flat_w16[o:o + n].view(p.shape)
+        self.sync_shadow()
+
+    def sync_shadow(self):
+        """Recast the whole flat bf16 shadow from the fp32 masters (one launch); called after host-side weight writes."""
+        n = self.flat_p.numel()
+        ops.call("sfk_cast_2d", self.flat_p.data_ptr(), n, self.flat_w16.data_ptr(), n, 1, n, n, ops.stream())
+        for p in self._params:
+            p._sfk_w16_version = p._version
         ops.bump_weight_epoch()
 
     # --- gradient bookkeeping ---
@@ -101,7 +119,7 @@ class FusedClipAdam(torch.optim.Optimizer):
         clip = g["clip_value"] if g["clip_value"] is not None else 3.0e38
         for a, b in ranges:
             ops.call("sfk_clip_adam_l2", self.flat_p.data_ptr() + 4 * a, self.flat_g.data_ptr() + 4 * a, self.flat_m.data_ptr() + 4 * a,
-                     self.flat_v.data_ptr() + 4 * a, b - a, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                     self.flat_v.data_ptr() + 4 * a, self.flat_w16.data_ptr() + 2 * a, b - a, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
                      float(g["weight_decay"]), float(clip), self._step, ops.stream())
         ops.bump_weight_epoch()
         return None
@@ -115,6 +133,6 @@ def ema_update(teacher_opt: FusedClipAdam, student_opt: FusedClipAdam, decay: fl
     """teacher <- decay*teacher + (1-decay)*student over the whole flat buffer (decay = 0 is the hard reset of TS:202-204)."""
     if teacher_opt.flat_p.numel() != student_opt.flat_p.numel():
         raise ValueError("teacher and student have different parameter layouts")
-    ops.call("sfk_ema_lerp", teacher_opt.flat_p.data_ptr(), student_opt.flat_p.data_ptr(), teacher_opt.flat_p.numel(), float(decay),
-             ops.stream())
+    ops.call("sfk_ema_lerp", teacher_opt.flat_p.data_ptr(), student_opt.flat_p.data_ptr(), teacher_opt.flat_w16.data_ptr(),
+             teacher_opt.flat_p.numel(), float(decay), ops.stream())
     ops.bump_weight_epoch()

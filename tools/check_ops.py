@@ -293,20 +293,24 @@ def main():
         m = torch.zeros(n, device=dev)
         v = torch.zeros(n, device=dev)
         pr, mr, vr = p.clone(), m.clone(), v.clone()
+        w16 = torch.zeros(n, device=dev, dtype=torch.bfloat16)
         for step in (1, 2, 3):
-            L.check(lib.sfk_clip_adam_l2(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.5, 0.999, 1e-8, 5e-5, 1.2,
-                                         step, L.stream_ptr()))
+            L.check(lib.sfk_clip_adam_l2(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), w16.data_ptr(), n, 1e-3, 0.5, 0.999,
+                                         1e-8, 5e-5, 1.2, step, L.stream_ptr()))
             gg = g.clamp(-1.2, 1.2) + 5e-5 * pr
             mr = 0.5 * mr + 0.5 * gg
             vr = 0.999 * vr + 0.001 * gg * gg
             pr = pr - (1e-3 / (1 - 0.5 ** step)) * (mr / (vr.sqrt() / math.sqrt(1 - 0.999 ** step) + 1e-8))
         allok &= report("clip_adam_l2 3 steps", p, pr, 1e-5)
+        ok = bool(torch.equal(w16, p.bfloat16()))
+        print(f"{'OK ' if ok else 'BAD'} clip_adam_l2 bf16 shadow == bf16(p)", flush=True)
+        allok &= ok
         t = torch.randn(n, device=dev)
         s2 = torch.randn(n, device=dev)
         ref = 0.9 * t + 0.1 * s2
-        L.check(lib.sfk_ema_lerp(t.data_ptr(), s2.data_ptr(), n, 0.9, L.stream_ptr()))
+        L.check(lib.sfk_ema_lerp(t.data_ptr(), s2.data_ptr(), w16.data_ptr(), n, 0.9, L.stream_ptr()))
         allok &= report("ema_lerp", t, ref, 1e-6)
-        L.check(lib.sfk_ema_lerp(t.data_ptr(), s2.data_ptr(), n, 0.0, L.stream_ptr()))
+        L.check(lib.sfk_ema_lerp(t.data_ptr(), s2.data_ptr(), None, n, 0.0, L.stream_ptr()))
         ok = bool(torch.equal(t, s2))
         print(f"{'OK ' if ok else 'BAD'} ema_lerp decay=0 is a bit-exact copy", flush=True)
         allok &= ok
