@@ -51,6 +51,7 @@ template <int D>
 __global__ void __launch_bounds__(160, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttFwdParams p) {
+  pdl_sync();
   using Cfg = AttCfg<D>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -235,7 +236,7 @@ static int attn_fwd_launch(const AttentionDesc& a, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((a.T + ATT_BM - 1) / ATT_BM, a.heads, a.B);
-  attn_fwd_kernel<D><<<grid, 160, smem, stream>>>(tq, tk, tv, p);
+  launch_k(attn_fwd_kernel<D>, dim3(grid), dim3(160), smem, stream, tq, tk, tv, p);
   return check_launch("attn_fwd_kernel");
 }
 
@@ -253,6 +254,7 @@ int attention_fwd(const AttentionDesc& a, cudaStream_t stream) {
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO,
                                                          float* __restrict__ delta, int B, int T, int heads, int D,
                                                          long long ld, long long batch_stride) {
+  pdl_sync();
   // one thread per (b, t, h, 8-element chunk); reduce across the D/8 chunk lanes with shuffles
   const int chunks = D / 8;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -307,6 +309,7 @@ __global__ void __launch_bounds__(160, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                 const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                 const AttBwdParams p) {
+  pdl_sync();
   using Cfg = AttCfg<D>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -543,7 +546,7 @@ static int attn_bwd_launch(const AttentionBwdDesc& a, cudaStream_t stream) {
   // delta = rowsum(dO * O)
   {
     const long long total = (long long)a.B * a.T * a.heads * (D / 8);
-    attn_delta_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)a.o, (const __nv_bfloat16*)a.dO,
+    launch_k(attn_delta_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, (const __nv_bfloat16*)a.o, (const __nv_bfloat16*)a.dO,
                                                                            a.delta, a.B, a.T, a.heads, D, a.ldo,
                                                                            a.o_batch_stride);
     rc = check_launch("attn_delta_kernel");
@@ -572,7 +575,7 @@ static int attn_bwd_launch(const AttentionBwdDesc& a, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid(kv_blocks * qsplits, a.heads, a.B);
-  attn_bwd_kernel<D><<<grid, 160, smem, stream>>>(tq, tdo, tk, tv, p);
+  launch_k(attn_bwd_kernel<D>, dim3(grid), dim3(160), smem, stream, tq, tdo, tk, tv, p);
   return check_launch("attn_bwd_kernel");
 }
 

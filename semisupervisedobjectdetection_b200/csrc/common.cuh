@@ -202,6 +202,30 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(uint32_t m, uint32_
 }
 
 // ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): every kernel is launched with programmaticStreamSerialization and starts with
+// pdl_sync() = { griddepcontrol.launch_dependents; griddepcontrol.wait; }.  The next kernel of the stream is scheduled while
+// this one still runs (its launch latency and prologue overlap our tail) but touches memory only after we have completed.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_launch_dependents(); pdl_wait(); }
+
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface through check_launch()
+}
+
+// ----------------------------------------------------------------------------------------------
 // host: TMA descriptor encode through the runtime-resolved driver entry point (no -lcuda needed)
 // ----------------------------------------------------------------------------------------------
 // 2-D bf16 tensor, inner dimension contiguous. box_inner must be 64 (128 B) for SWIZZLE_128B.

@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_kernel(const __nv_bfloat16* 
                                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
                                                            float* __restrict__ colsum, int B, int H, int W, int C,
                                                            int pos_per_block) {
+  pdl_sync();
   constexpr int VEC = 8;
   __shared__ float sh[32 * VEC];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -202,9 +203,9 @@ int dwconv3x3(const void* x, const float* wt, const float* bias, void* y, float*
   int ppb;
   dw_grid(C, 8, npos, grid, ppb);
   if (mode == 0)
-    dwconv3x3_kernel<0><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, wt, bias, (__nv_bfloat16*)y, nullptr, B, H, W, C, ppb);
+    launch_k(dwconv3x3_kernel<0>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, bias, (__nv_bfloat16*)y, nullptr, B, H, W, C, ppb);
   else
-    dwconv3x3_kernel<1><<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, wt, nullptr, (__nv_bfloat16*)y, colsum, B, H, W, C, ppb);
+    launch_k(dwconv3x3_kernel<1>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, nullptr, (__nv_bfloat16*)y, colsum, B, H, W, C, ppb);
   return check_launch("dwconv3x3_kernel");
 }
 
@@ -216,6 +217,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_bwd_kernel(const __nv_b
                                                                     __nv_bfloat16* __restrict__ dpre, float* __restrict__ dwt,
                                                                     float* __restrict__ dbias, int B, int H, int W, int C,
                                                                     int pos_per_block) {
+  pdl_sync();
   constexpr int VEC = 4;
   __shared__ float sh[10 * 32 * VEC];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -308,7 +310,7 @@ int dwconv3x3_gelu_bwd(const void* x, const float* wt, const float* bias, const 
   dim3 grid;
   int ppb;
   dw_grid(C, 4, npos, grid, ppb);
-  dwconv3x3_gelu_bwd_kernel<<<grid, 256, 0, stream>>>((const __nv_bfloat16*)x, wt, bias, (const __nv_bfloat16*)dg,
+  launch_k(dwconv3x3_gelu_bwd_kernel, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, bias, (const __nv_bfloat16*)dg,
                                                       (__nv_bfloat16*)dpre, dwt, dbias, B, H, W, C, ppb);
   return check_launch("dwconv3x3_gelu_bwd_kernel");
 }
@@ -321,6 +323,7 @@ int dwconv3x3_gelu_bwd(const void* x, const float* wt, const float* bias, const 
 __global__ void __launch_bounds__(256) im2col_nhwc_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ A,
                                                           int B, int H, int W, int C, int K, int S, int P, int Ho, int Wo,
                                                           long long tok_stride, long long tok_offset) {
+  pdl_sync();
   const int C8 = C >> 3;
   const long long total = (long long)B * Ho * Wo * K * K * C8;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -346,7 +349,7 @@ int im2col_nhwc(const void* x, void* A, int B, int H, int W, int C, int K, int S
   const int Ho = (H + 2 * P - K) / S + 1, Wo = (W + 2 * P - K) / S + 1;
   const long long total = (long long)B * Ho * Wo * K * K * (C / 8);
   if (total == 0) return 0;
-  im2col_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)A, B, H, W,
+  launch_k(im2col_nhwc_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)A, B, H, W,
                                                                           C, K, S, P, Ho, Wo, tok_stride, tok_offset);
   return check_launch("im2col_nhwc_kernel");
 }
@@ -355,6 +358,7 @@ int im2col_nhwc(const void* x, void* A, int B, int H, int W, int C, int K, int S
 __global__ void __launch_bounds__(256) im2col_nchw_f32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ A, int B,
                                                               int Cin, int H, int W, int K, int S, int P, int Ho, int Wo,
                                                               int Kp) {
+  pdl_sync();
   const long long total = (long long)B * Ho * Wo * Kp;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;
@@ -378,7 +382,7 @@ int im2col_nchw_f32(const float* x, void* A, int B, int Cin, int H, int W, int K
   const int Ho = (H + 2 * P - K) / S + 1, Wo = (W + 2 * P - K) / S + 1;
   const long long total = (long long)B * Ho * Wo * Kp;
   if (total == 0) return 0;
-  im2col_nchw_f32_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, (__nv_bfloat16*)A, B, Cin, H, W, K, S, P, Ho,
+  launch_k(im2col_nchw_f32_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, x, (__nv_bfloat16*)A, B, Cin, H, W, K, S, P, Ho,
                                                                               Wo, Kp);
   return check_launch("im2col_nchw_f32_kernel");
 }
@@ -388,6 +392,7 @@ int im2col_nchw_f32(const float* x, void* A, int B, int Cin, int H, int W, int K
 __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const __nv_bfloat16* __restrict__ dA, float* __restrict__ dx, int B,
                                                           int H, int W, int C, int K, int S, int P, int Ho, int Wo,
                                                           long long tok_stride, long long tok_offset, int accumulate) {
+  pdl_sync();
   const int C4 = C >> 2;
   const long long total = (long long)B * H * W * C4;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -424,7 +429,7 @@ int col2im_nhwc(const void* dA, float* dx, int B, int H, int W, int C, int K, in
   const int Ho = (H + 2 * P - K) / S + 1, Wo = (W + 2 * P - K) / S + 1;
   const long long total = (long long)B * H * W * (C / 4);
   if (total == 0) return 0;
-  col2im_nhwc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)dA, dx, B, H, W, C, K, S, P, Ho,
+  launch_k(col2im_nhwc_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, (const __nv_bfloat16*)dA, dx, B, H, W, C, K, S, P, Ho,
                                                                           Wo, tok_stride, tok_offset, accumulate);
   return check_launch("col2im_nhwc_kernel");
 }
@@ -435,6 +440,7 @@ int col2im_nhwc(const void* dA, float* dx, int B, int H, int W, int C, int K, in
 // OIHW fp32 -> [O, (ky,kx,c)] bf16 (channels-last patch order), row pitch ldo
 __global__ void conv_weight_ohwi_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int O, int I, int KH,
                                         int KW, long long ldo) {
+  pdl_sync();
   const long long total = (long long)O * I * KH * KW;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;
@@ -450,13 +456,14 @@ __global__ void conv_weight_ohwi_kernel(const float* __restrict__ w, __nv_bfloat
 int conv_weight_ohwi(const float* w, void* out, int O, int I, int KH, int KW, long long ldo, cudaStream_t stream) {
   const long long total = (long long)O * I * KH * KW;
   if (total == 0) return 0;
-  conv_weight_ohwi_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(w, (__nv_bfloat16*)out, O, I, KH, KW, ldo);
+  launch_k(conv_weight_ohwi_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, w, (__nv_bfloat16*)out, O, I, KH, KW, ldo);
   return check_launch("conv_weight_ohwi_kernel");
 }
 
 // inverse for gradients: dW_oihw[o,c,ky,kx] += g[o, (ky,kx,c)] (fp32 -> fp32)
 __global__ void conv_wgrad_ohwi_to_oihw_kernel(const float* __restrict__ g, float* __restrict__ dw, int O, int I, int KH, int KW,
                                                long long ldg) {
+  pdl_sync();
   const long long total = (long long)O * I * KH * KW;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;
@@ -472,13 +479,14 @@ __global__ void conv_wgrad_ohwi_to_oihw_kernel(const float* __restrict__ g, floa
 int conv_wgrad_ohwi_to_oihw(const float* g, float* dw, int O, int I, int KH, int KW, long long ldg, cudaStream_t stream) {
   const long long total = (long long)O * I * KH * KW;
   if (total == 0) return 0;
-  conv_wgrad_ohwi_to_oihw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(g, dw, O, I, KH, KW, ldg);
+  launch_k(conv_wgrad_ohwi_to_oihw_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, g, dw, O, I, KH, KW, ldg);
   return check_launch("conv_wgrad_ohwi_to_oihw_kernel");
 }
 
 // generic 2-D strided transpose-free copy fp32 -> bf16 with row pitches (for weight shadows incl. K padding)
 __global__ void cast_2d_kernel(const float* __restrict__ src, long long lds, __nv_bfloat16* __restrict__ dst, long long ldd,
                                long long rows, int cols, int cols_padded) {
+  pdl_sync();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= rows * cols_padded) return;
   const int c = (int)(idx % cols_padded);
@@ -489,30 +497,32 @@ __global__ void cast_2d_kernel(const float* __restrict__ src, long long lds, __n
 int cast_2d(const float* src, long long lds, void* dst, long long ldd, long long rows, int cols, int cols_padded,
             cudaStream_t stream) {
   if (rows * cols_padded == 0) return 0;
-  cast_2d_kernel<<<(unsigned)((rows * cols_padded + 255) / 256), 256, 0, stream>>>(src, lds, (__nv_bfloat16*)dst, ldd, rows, cols,
+  launch_k(cast_2d_kernel, dim3((unsigned)((rows * cols_padded + 255) / 256)), dim3(256), 0, stream, src, lds, (__nv_bfloat16*)dst, ldd, rows, cols,
                                                                                   cols_padded);
   return check_launch("cast_2d_kernel");
 }
 
 // [C,1,3,3] fp32 -> tap-major [9][C] fp32 and back (gradient accumulate)
 __global__ void dw_weight_to_tap_kernel(const float* __restrict__ w, float* __restrict__ wt, int C) {
+  pdl_sync();
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx >= 9 * C) return;
   const int k = idx / C, c = idx % C;
   wt[idx] = w[c * 9 + k];
 }
 __global__ void dw_wgrad_from_tap_kernel(const float* __restrict__ dwt, float* __restrict__ dw, int C) {
+  pdl_sync();
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx >= 9 * C) return;
   const int c = idx / 9, k = idx % 9;
   dw[idx] += dwt[k * C + c];
 }
 int dw_weight_to_tap(const float* w, float* wt, int C, cudaStream_t stream) {
-  dw_weight_to_tap_kernel<<<(9 * C + 255) / 256, 256, 0, stream>>>(w, wt, C);
+  launch_k(dw_weight_to_tap_kernel, dim3((9 * C + 255) / 256), dim3(256), 0, stream, w, wt, C);
   return check_launch("dw_weight_to_tap_kernel");
 }
 int dw_wgrad_from_tap(const float* dwt, float* dw, int C, cudaStream_t stream) {
-  dw_wgrad_from_tap_kernel<<<(9 * C + 255) / 256, 256, 0, stream>>>(dwt, dw, C);
+  launch_k(dw_wgrad_from_tap_kernel, dim3((9 * C + 255) / 256), dim3(256), 0, stream, dwt, dw, C);
   return check_launch("dw_wgrad_from_tap_kernel");
 }
 

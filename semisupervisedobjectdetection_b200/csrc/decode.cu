@@ -23,6 +23,7 @@ __device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, 
 __global__ void __launch_bounds__(256) upsample_concat_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                               int B, int h, int w, int C, int H, int W, long long ld_out,
                                                               int ch_off) {
+  pdl_sync();
   const int C8 = C >> 3;
   const long long total = (long long)B * H * W * C8;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -67,7 +68,7 @@ int upsample_concat(const void* in, void* out, int B, int h, int w, int C, int H
   SFK_REQUIRE(C % 8 == 0 && ld_out % 8 == 0 && ch_off % 8 == 0, "upsample_concat: channel counts must be multiples of 8");
   const long long total = (long long)B * H * W * (C / 8);
   if (total == 0) return 0;
-  upsample_concat_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, h, w,
+  launch_k(upsample_concat_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, h, w,
                                                                               C, H, W, ld_out, ch_off);
   return check_launch("upsample_concat_kernel");
 }
@@ -77,6 +78,7 @@ int upsample_concat(const void* in, void* out, int B, int h, int w, int C, int H
 __global__ void __launch_bounds__(256) upsample_concat_bwd_kernel(const __nv_bfloat16* __restrict__ dout,
                                                                   __nv_bfloat16* __restrict__ din, int B, int h, int w, int C,
                                                                   int H, int W, long long ld_out, int ch_off) {
+  pdl_sync();
   const int C8 = C >> 3;
   const long long total = (long long)B * h * w * C8;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -142,7 +144,7 @@ int upsample_concat_bwd(const void* dout, void* din, int B, int h, int w, int C,
   SFK_REQUIRE(C % 8 == 0 && ld_out % 8 == 0 && ch_off % 8 == 0, "upsample_concat_bwd: channel counts must be multiples of 8");
   const long long total = (long long)B * h * w * (C / 8);
   if (total == 0) return 0;
-  upsample_concat_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)din,
+  launch_k(upsample_concat_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, (const __nv_bfloat16*)dout, (__nv_bfloat16*)din,
                                                                                   B, h, w, C, H, W, ld_out, ch_off);
   return check_launch("upsample_concat_bwd_kernel");
 }
@@ -150,6 +152,7 @@ int upsample_concat_bwd(const void* dout, void* din, int B, int h, int w, int C,
 // out[b*N + t, :] (bf16) += vec[b, :] (f32)     — cls_proj broadcast add (MS:720-723)
 __global__ void __launch_bounds__(256) add_sample_bias_kernel(__nv_bfloat16* __restrict__ out, const float* __restrict__ vec,
                                                               long long rows, int rows_per_sample, int C) {
+  pdl_sync();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   const int C2 = C >> 1;
   if (idx >= rows * C2) return;
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(256) add_sample_bias_kernel(__nv_bfloat16* __r
 int add_sample_bias(void* out, const float* vec, long long rows, int rows_per_sample, int C, cudaStream_t stream) {
   SFK_REQUIRE(C % 2 == 0, "add_sample_bias: C must be even");
   if (rows == 0) return 0;
-  add_sample_bias_kernel<<<(unsigned)((rows * (C / 2) + 255) / 256), 256, 0, stream>>>((__nv_bfloat16*)out, vec, rows,
+  launch_k(add_sample_bias_kernel, dim3((unsigned)((rows * (C / 2) + 255) / 256)), dim3(256), 0, stream, (__nv_bfloat16*)out, vec, rows,
                                                                                        rows_per_sample, C);
   return check_launch("add_sample_bias_kernel");
 }
@@ -173,6 +176,7 @@ int add_sample_bias(void* out, const float* vec, long long rows, int rows_per_sa
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) bn_partial_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ partial,
                                                          long long M, int C, int rows_per_block) {
+  pdl_sync();
   const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
   if (c >= C) return;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
@@ -193,6 +197,7 @@ __global__ void __launch_bounds__(128) bn_partial_kernel(const __nv_bfloat16* __
 __global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblocks, long long M, int C, float eps, float momentum,
                                    float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ running_mean,
                                    float* __restrict__ running_var) {
+  pdl_sync();
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= C) return;
   double s = 0.0, q = 0.0;
@@ -230,10 +235,10 @@ int bn_batch_stats(const void* x, long long M, int C, float eps, float momentum,
   SFK_REQUIRE(workspace_bytes >= (size_t)gy * 2 * C * sizeof(float), "bn_batch_stats: workspace too small");
   const int rpb = (int)((M + gy - 1) / gy);
   gy = (M + rpb - 1) / rpb;
-  bn_partial_kernel<<<dim3(gx, (unsigned)gy), 128, 0, stream>>>((const __nv_bfloat16*)x, workspace, M, C, rpb);
+  launch_k(bn_partial_kernel, dim3(dim3(gx, (unsigned)gy)), dim3(128), 0, stream, (const __nv_bfloat16*)x, workspace, M, C, rpb);
   int rc = check_launch("bn_partial_kernel");
   if (rc) return rc;
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, stream>>>(workspace, (int)gy, M, C, eps, momentum, mean, rstd, running_mean,
+  launch_k(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, stream, workspace, (int)gy, M, C, eps, momentum, mean, rstd, running_mean,
                                                           running_var);
   return check_launch("bn_finalize_kernel");
 }
@@ -241,13 +246,14 @@ int bn_batch_stats(const void* x, long long M, int C, float eps, float momentum,
 // eval mode: mean = running_mean, rstd = 1/sqrt(running_var + eps)
 __global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, float eps, float* __restrict__ mean,
                                      float* __restrict__ rstd, int C) {
+  pdl_sync();
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= C) return;
   mean[c] = rm[c];
   rstd[c] = 1.f / sqrtf(rv[c] + eps);
 }
 int bn_eval_stats(const float* rm, const float* rv, float eps, float* mean, float* rstd, int C, cudaStream_t stream) {
-  bn_eval_stats_kernel<<<(C + 127) / 128, 128, 0, stream>>>(rm, rv, eps, mean, rstd, C);
+  launch_k(bn_eval_stats_kernel, dim3((C + 127) / 128), dim3(128), 0, stream, rm, rv, eps, mean, rstd, C);
   return check_launch("bn_eval_stats_kernel");
 }
 
@@ -270,6 +276,7 @@ __global__ void __launch_bounds__(256) bn_relu_cls_fwd_kernel(const __nv_bfloat1
                                                               const float* __restrict__ bc, float* __restrict__ logits,
                                                               long long M, int C, int NL, int pix_per_sample, float drop_p,
                                                               unsigned long long seed) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + warp;
   if (row >= M) return;
@@ -305,7 +312,7 @@ int bn_relu_cls_fwd(const void* x, const float* mean, const float* rstd, const f
   SFK_REQUIRE(NL >= 1 && NL <= CLS_MAX_LABELS, "bn_relu_cls: num_labels=%d unsupported (1..%d)", NL, CLS_MAX_LABELS);
   SFK_REQUIRE(C % 2 == 0, "bn_relu_cls: C must be even");
   if (M == 0) return 0;
-  bn_relu_cls_fwd_kernel<0><<<(unsigned)((M + 7) / 8), 256, 0, stream>>>((const __nv_bfloat16*)x, mean, rstd, gamma, beta, wc, bc,
+  launch_k(bn_relu_cls_fwd_kernel<0>, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, stream, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, wc, bc,
                                                                          logits, M, C, NL, pix_per_sample, drop_p, seed);
   return check_launch("bn_relu_cls_fwd_kernel");
 }
@@ -324,6 +331,7 @@ __global__ void __launch_bounds__(256) bn_relu_cls_bwd_kernel(const __nv_bfloat1
                                                               __nv_bfloat16* __restrict__ dx, long long M, int C, int NL,
                                                               int pix_per_sample, float drop_p, unsigned long long seed,
                                                               int train_stats, int rows_per_block) {
+  pdl_sync();
   extern __shared__ float sh[];  // PASS 0: [2 + NL][C] block accumulators
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -405,12 +413,12 @@ int bn_relu_cls_bwd(const void* x, const float* mean, const float* rstd, const f
   }
   const size_t smem = (size_t)(2 + NL) * C * sizeof(float);
   SFK_REQUIRE(smem <= 48 * 1024, "bn_relu_cls_bwd: C*(2+NL) too large for shared memory");
-  bn_relu_cls_bwd_kernel<0><<<(unsigned)grid, 256, smem, stream>>>((const __nv_bfloat16*)x, mean, rstd, gamma, beta, wc, dlogits,
+  launch_k(bn_relu_cls_bwd_kernel<0>, dim3((unsigned)grid), dim3(256), smem, stream, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, wc, dlogits,
                                                                    sums, dwc, dbc, nullptr, M, C, NL, pix_per_sample, drop_p,
                                                                    seed, train_stats, rpb);
   int rc = check_launch("bn_relu_cls_bwd_kernel<0>");
   if (rc) return rc;
-  bn_relu_cls_bwd_kernel<1><<<(unsigned)grid, 256, 0, stream>>>((const __nv_bfloat16*)x, mean, rstd, gamma, beta, wc, dlogits, sums,
+  launch_k(bn_relu_cls_bwd_kernel<1>, dim3((unsigned)grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, wc, dlogits, sums,
                                                                 nullptr, nullptr, (__nv_bfloat16*)dx, M, C, NL, pix_per_sample,
                                                                 drop_p, seed, train_stats, rpb);
   return check_launch("bn_relu_cls_bwd_kernel<1>");

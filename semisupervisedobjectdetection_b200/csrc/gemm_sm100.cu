@@ -66,6 +66,7 @@ __device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, fl
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmKernelParams p) {
+  pdl_sync();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-B alignment is required by SWIZZLE_128B atoms; dynamic smem base is only 16-B aligned by contract.
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -399,7 +400,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   const long long units = (long long)p.m_tiles * p.n_tiles * p.splits;
   int grid = (int)(units < num_sms() ? units : num_sms());
   prof_gemm_begin(2.0 * (double)g.M * (double)g.N * (double)g.K, stream);
-  gemm_bf16_tcgen05_kernel<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, p);
+  launch_k(gemm_bf16_tcgen05_kernel, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, p);
   prof_gemm_end(stream);
   return check_launch("gemm_bf16_tcgen05_kernel");
 }

@@ -42,6 +42,7 @@ __device__ __forceinline__ void block_reduce(float (&v)[NV], float* sh /* [NV][8
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) upsample_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, long long planes,
                                                             int h, int w, int H, int W, int act) {
+  pdl_sync();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= planes * H * W) return;
   const int X = (int)(idx % W);
@@ -61,7 +62,7 @@ __global__ void __launch_bounds__(256) upsample_nchw_kernel(const float* __restr
 int upsample_nchw_fwd(const float* x, float* y, long long planes, int h, int w, int H, int W, int act, cudaStream_t stream) {
   const long long total = planes * H * W;
   if (total == 0) return 0;
-  upsample_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(x, y, planes, h, w, H, W, act);
+  launch_k(upsample_nchw_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, x, y, planes, h, w, H, W, act);
   return check_launch("upsample_nchw_kernel");
 }
 
@@ -69,6 +70,7 @@ int upsample_nchw_fwd(const float* x, float* y, long long planes, int h, int w, 
 __global__ void __launch_bounds__(256) upsample_nchw_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ yact,
                                                                 float* __restrict__ dx, long long planes, int h, int w, int H,
                                                                 int W, int accumulate) {
+  pdl_sync();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= planes * h * w) return;
   const int xi = (int)(idx % w);
@@ -110,7 +112,7 @@ int upsample_nchw_bwd(const float* dy, const float* yact, float* dx, long long p
                       int accumulate, cudaStream_t stream) {
   const long long total = planes * h * w;
   if (total == 0) return 0;
-  upsample_nchw_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(dy, yact, dx, planes, h, w, H, W, accumulate);
+  launch_k(upsample_nchw_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, dy, yact, dx, planes, h, w, H, W, accumulate);
   return check_launch("upsample_nchw_bwd_kernel");
 }
 
@@ -124,6 +126,7 @@ template <typename TG>
 __global__ void __launch_bounds__(256) dice_partial_kernel(const float* __restrict__ p, long long p_stride, const TG* __restrict__ g,
                                                            long long g_stride, float* __restrict__ partial, long long P,
                                                            int hard_threshold) {
+  pdl_sync();
   __shared__ float sh[3 * 8];
   const int n = blockIdx.y;
   const long long per = (P + gridDim.x - 1) / gridDim.x;
@@ -149,6 +152,7 @@ __global__ void __launch_bounds__(256) dice_partial_kernel(const float* __restri
 // sums[n] = {tp, fp, fn};  loss = 1 - mean_n score   (one block)
 __global__ void dice_finish_kernel(const float* __restrict__ partial, int N, int chunks, float smooth, float* __restrict__ sums,
                                    float* __restrict__ loss) {
+  pdl_sync();
   __shared__ float sc[256];
   float local = 0.f;
   for (int n = threadIdx.x; n < N; n += 256) {
@@ -176,12 +180,12 @@ int dice_fwd(const float* p, long long p_stride, const void* g, int g_is_i64, lo
   SFK_REQUIRE(N > 0 && N <= 65535 && P > 0, "dice: bad shape N=%d P=%lld", N, P);
   dim3 grid(RED_CHUNKS, N);
   if (g_is_i64)
-    dice_partial_kernel<long long><<<grid, 256, 0, stream>>>(p, p_stride, (const long long*)g, g_stride, workspace, P, hard_threshold);
+    launch_k(dice_partial_kernel<long long>, dim3(grid), dim3(256), 0, stream, p, p_stride, (const long long*)g, g_stride, workspace, P, hard_threshold);
   else
-    dice_partial_kernel<float><<<grid, 256, 0, stream>>>(p, p_stride, (const float*)g, g_stride, workspace, P, hard_threshold);
+    launch_k(dice_partial_kernel<float>, dim3(grid), dim3(256), 0, stream, p, p_stride, (const float*)g, g_stride, workspace, P, hard_threshold);
   int rc = check_launch("dice_partial_kernel");
   if (rc) return rc;
-  dice_finish_kernel<<<1, 256, 0, stream>>>(workspace, N, RED_CHUNKS, smooth, sums, loss);
+  launch_k(dice_finish_kernel, dim3(1), dim3(256), 0, stream, workspace, N, RED_CHUNKS, smooth, sums, loss);
   return check_launch("dice_finish_kernel");
 }
 
@@ -191,6 +195,7 @@ __global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__
                                                        long long g_stride, const float* __restrict__ sums,
                                                        const float* __restrict__ dloss, float smooth, float* __restrict__ dp,
                                                        long long dp_stride, int N, long long P, int accumulate) {
+  pdl_sync();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= (long long)N * P) return;
   const int n = (int)(idx / P);
@@ -213,10 +218,10 @@ int dice_bwd(const float* p, long long p_stride, const void* g, int g_is_i64, lo
   if (total == 0) return 0;
   const unsigned grid = (unsigned)((total + 255) / 256);
   if (g_is_i64)
-    dice_bwd_kernel<long long><<<grid, 256, 0, stream>>>(p, p_stride, (const long long*)g, g_stride, sums, dloss, smooth, dp,
+    launch_k(dice_bwd_kernel<long long>, dim3(grid), dim3(256), 0, stream, p, p_stride, (const long long*)g, g_stride, sums, dloss, smooth, dp,
                                                          dp_stride, N, P, accumulate);
   else
-    dice_bwd_kernel<float><<<grid, 256, 0, stream>>>(p, p_stride, (const float*)g, g_stride, sums, dloss, smooth, dp, dp_stride,
+    launch_k(dice_bwd_kernel<float>, dim3(grid), dim3(256), 0, stream, p, p_stride, (const float*)g, g_stride, sums, dloss, smooth, dp, dp_stride,
                                                      N, P, accumulate);
   return check_launch("dice_bwd_kernel");
 }
@@ -227,6 +232,7 @@ int dice_bwd(const float* p, long long p_stride, const void* g, int g_is_i64, lo
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) bce_partial_kernel(const float* __restrict__ z, const long long* __restrict__ labels,
                                                           long long ignore_index, float* __restrict__ partial, long long n) {
+  pdl_sync();
   __shared__ float sh[2 * 8];
   const long long per = (n + gridDim.x - 1) / gridDim.x;
   const long long i0 = (long long)blockIdx.x * per;
@@ -248,6 +254,7 @@ __global__ void __launch_bounds__(256) bce_partial_kernel(const float* __restric
 // loss = sum / denom ;  denom_mode 0: fixed denominator `denom`, 1: the summed count (CE mean over non-ignored)
 __global__ void sum_finish_kernel(const float* __restrict__ partial, int nblocks, int denom_mode, float denom,
                                   float* __restrict__ out /* [2]: loss, count */) {
+  pdl_sync();
   if (threadIdx.x != 0) return;
   float s = 0.f, c = 0.f;
   for (int i = 0; i < nblocks; ++i) { s += partial[i * 2]; c += partial[i * 2 + 1]; }
@@ -261,16 +268,17 @@ size_t loss_workspace_bytes() { return (size_t)SUM_BLOCKS * 2 * sizeof(float); }
 int bce_valid_fwd(const float* z, const long long* labels, long long ignore_index, long long n, float* workspace, float* out,
                   cudaStream_t stream) {
   SFK_REQUIRE(n > 0, "bce_valid: empty input");
-  bce_partial_kernel<<<SUM_BLOCKS, 256, 0, stream>>>(z, labels, ignore_index, workspace, n);
+  launch_k(bce_partial_kernel, dim3(SUM_BLOCKS), dim3(256), 0, stream, z, labels, ignore_index, workspace, n);
   int rc = check_launch("bce_partial_kernel");
   if (rc) return rc;
-  sum_finish_kernel<<<1, 32, 0, stream>>>(workspace, SUM_BLOCKS, 0, (float)n, out);
+  launch_k(sum_finish_kernel, dim3(1), dim3(32), 0, stream, workspace, SUM_BLOCKS, 0, (float)n, out);
   return check_launch("sum_finish_kernel");
 }
 
 __global__ void __launch_bounds__(256) bce_valid_bwd_kernel(const float* __restrict__ z, const long long* __restrict__ labels,
                                                             long long ignore_index, const float* __restrict__ dloss,
                                                             float* __restrict__ dz, long long n) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const long long y = labels[i];
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__(256) bce_valid_bwd_kernel(const float* __restr
 int bce_valid_bwd(const float* z, const long long* labels, long long ignore_index, const float* dloss, float* dz, long long n,
                   cudaStream_t stream) {
   if (n == 0) return 0;
-  bce_valid_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(z, labels, ignore_index, dloss, dz, n);
+  launch_k(bce_valid_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, z, labels, ignore_index, dloss, dz, n);
   return check_launch("bce_valid_bwd_kernel");
 }
 
@@ -289,6 +297,7 @@ int bce_valid_bwd(const float* z, const long long* labels, long long ignore_inde
 __global__ void __launch_bounds__(256) ce_partial_kernel(const float* __restrict__ z, const long long* __restrict__ labels,
                                                          long long ignore_index, float* __restrict__ partial, int N, int L,
                                                          long long P) {
+  pdl_sync();
   __shared__ float sh[2 * 8];
   const long long n = (long long)N * P;
   const long long per = (n + gridDim.x - 1) / gridDim.x;
@@ -315,10 +324,10 @@ __global__ void __launch_bounds__(256) ce_partial_kernel(const float* __restrict
 int ce_ignore_fwd(const float* z, const long long* labels, long long ignore_index, int N, int L, long long P, float* workspace,
                   float* out, cudaStream_t stream) {
   SFK_REQUIRE(N > 0 && L > 0 && P > 0, "ce_ignore: empty input");
-  ce_partial_kernel<<<SUM_BLOCKS, 256, 0, stream>>>(z, labels, ignore_index, workspace, N, L, P);
+  launch_k(ce_partial_kernel, dim3(SUM_BLOCKS), dim3(256), 0, stream, z, labels, ignore_index, workspace, N, L, P);
   int rc = check_launch("ce_partial_kernel");
   if (rc) return rc;
-  sum_finish_kernel<<<1, 32, 0, stream>>>(workspace, SUM_BLOCKS, 1, 1.f, out);
+  launch_k(sum_finish_kernel, dim3(1), dim3(32), 0, stream, workspace, SUM_BLOCKS, 1, 1.f, out);
   return check_launch("sum_finish_kernel");
 }
 
@@ -326,6 +335,7 @@ __global__ void __launch_bounds__(256) ce_ignore_bwd_kernel(const float* __restr
                                                             long long ignore_index, const float* __restrict__ out /* loss,count */,
                                                             const float* __restrict__ dloss, float* __restrict__ dz, int N, int L,
                                                             long long P) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= (long long)N * P) return;
   const long long b = i / P, px = i - b * P;
@@ -347,13 +357,14 @@ int ce_ignore_bwd(const float* z, const long long* labels, long long ignore_inde
                   float* dz, int N, int L, long long P, cudaStream_t stream) {
   const long long n = (long long)N * P;
   if (n == 0) return 0;
-  ce_ignore_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(z, labels, ignore_index, out, dloss, dz, N, L, P);
+  launch_k(ce_ignore_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, z, labels, ignore_index, out, dloss, dz, N, L, P);
   return check_launch("ce_ignore_bwd_kernel");
 }
 
 // MSE of LOSS:44-54:  mean_n( sum((gt-pred)^2) / (N*C) )  ==  sum_all / (N*C*N)
 __global__ void __launch_bounds__(256) sqdiff_partial_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                              float* __restrict__ partial, long long n) {
+  pdl_sync();
   __shared__ float sh[2 * 8];
   const long long per = (n + gridDim.x - 1) / gridDim.x;
   const long long i0 = (long long)blockIdx.x * per;
@@ -369,16 +380,17 @@ __global__ void __launch_bounds__(256) sqdiff_partial_kernel(const float* __rest
 }
 int mse_fwd(const float* a, const float* b, long long n, float denom, float* workspace, float* out, cudaStream_t stream) {
   SFK_REQUIRE(n > 0, "mse: empty input");
-  sqdiff_partial_kernel<<<SUM_BLOCKS, 256, 0, stream>>>(a, b, workspace, n);
+  launch_k(sqdiff_partial_kernel, dim3(SUM_BLOCKS), dim3(256), 0, stream, a, b, workspace, n);
   int rc = check_launch("sqdiff_partial_kernel");
   if (rc) return rc;
-  sum_finish_kernel<<<1, 32, 0, stream>>>(workspace, SUM_BLOCKS, 0, denom, out);
+  launch_k(sum_finish_kernel, dim3(1), dim3(32), 0, stream, workspace, SUM_BLOCKS, 0, denom, out);
   return check_launch("sum_finish_kernel");
 }
 // da = 2(a-b)/denom * dloss ; db = -da
 __global__ void __launch_bounds__(256) mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                       const float* __restrict__ dloss, float denom, float* __restrict__ da,
                                                       float* __restrict__ db, long long n) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const float d = 2.f * (a[i] - b[i]) / denom * dloss[0];
@@ -388,7 +400,7 @@ __global__ void __launch_bounds__(256) mse_bwd_kernel(const float* __restrict__ 
 int mse_bwd(const float* a, const float* b, const float* dloss, float denom, float* da, float* db, long long n,
             cudaStream_t stream) {
   if (n == 0) return 0;
-  mse_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(a, b, dloss, denom, da, db, n);
+  launch_k(mse_bwd_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, a, b, dloss, denom, da, db, n);
   return check_launch("mse_bwd_kernel");
 }
 
@@ -400,6 +412,7 @@ int mse_bwd(const float* a, const float* b, const float* dloss, float denom, flo
 __global__ void __launch_bounds__(256) pseudo_partial_kernel(const float* __restrict__ p, long long* __restrict__ pseudo,
                                                              float* __restrict__ partial, long long P, float thr_hi,
                                                              float thr_lo) {
+  pdl_sync();
   __shared__ float sh[4 * 8];
   const int n = blockIdx.y;
   const long long per = (P + gridDim.x - 1) / gridDim.x;
@@ -427,6 +440,7 @@ __global__ void __launch_bounds__(256) pseudo_partial_kernel(const float* __rest
 // stats[n] = { pixel_num, confidence, target_num, dice_loss_n, keep }
 __global__ void pseudo_finish_kernel(const float* __restrict__ partial, int N, int chunks, long long P, float conf_thr,
                                      float min_pixels, int allow_throw, float* __restrict__ stats) {
+  pdl_sync();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float px = 0.f, conf = 0.f, pos = 0.f, tp = 0.f;
@@ -446,16 +460,17 @@ size_t pseudo_workspace_bytes(int N) { return (size_t)N * RED_CHUNKS * 4 * sizeo
 int pseudo_label_threshold(const float* p, long long* pseudo, float* stats, int N, long long P, float thr_hi, float thr_lo,
                            float conf_thr, float min_pixels, int allow_throw, float* workspace, cudaStream_t stream) {
   SFK_REQUIRE(N > 0 && N <= 65535 && P > 0, "pseudo_label_threshold: bad shape N=%d P=%lld", N, P);
-  pseudo_partial_kernel<<<dim3(RED_CHUNKS, N), 256, 0, stream>>>(p, pseudo, workspace, P, thr_hi, thr_lo);
+  launch_k(pseudo_partial_kernel, dim3(dim3(RED_CHUNKS, N)), dim3(256), 0, stream, p, pseudo, workspace, P, thr_hi, thr_lo);
   int rc = check_launch("pseudo_partial_kernel");
   if (rc) return rc;
-  pseudo_finish_kernel<<<(N + 63) / 64, 64, 0, stream>>>(workspace, N, RED_CHUNKS, P, conf_thr, min_pixels, allow_throw, stats);
+  launch_k(pseudo_finish_kernel, dim3((N + 63) / 64), dim3(64), 0, stream, workspace, N, RED_CHUNKS, P, conf_thr, min_pixels, allow_throw, stats);
   return check_launch("pseudo_finish_kernel");
 }
 
 // denoise-label trick (TS:111-114): t = clamp(t0 + 0.2*gt - 0.1, 0, 1) with the reference op order
 __global__ void __launch_bounds__(256) denoise_kernel(const float* __restrict__ t0, const float* __restrict__ gt,
                                                       float* __restrict__ out, long long n) {
+  pdl_sync();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   float t = __fadd_rn(t0[i], __fmul_rn(0.2f, gt[i]));  // no FMA contraction: torch rounds the product first
@@ -466,7 +481,7 @@ __global__ void __launch_bounds__(256) denoise_kernel(const float* __restrict__ 
 }
 int denoise_labels(const float* t0, const float* gt, float* out, long long n, cudaStream_t stream) {
   if (n == 0) return 0;
-  denoise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(t0, gt, out, n);
+  launch_k(denoise_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, stream, t0, gt, out, n);
   return check_launch("denoise_kernel");
 }
 

@@ -10,6 +10,7 @@ __global__ void __launch_bounds__(256) clip_adam_l2_kernel(float* __restrict__ p
                                                            float* __restrict__ v, __nv_bfloat16* __restrict__ w16, long long n,
                                                            float lr, float beta1, float beta2, float eps, float wd, float clip,
                                                            float bc1, float bc2_sqrt) {
+  pdl_sync();
   const long long i4 = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
   if (i4 >= n) return;
   if (i4 + 4 <= n) {
@@ -60,13 +61,14 @@ int clip_adam_l2(float* p, const float* g, float* m, float* v, void* w16, long l
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
   const long long threads = (n + 3) / 4;
-  clip_adam_l2_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(p, g, m, v, (__nv_bfloat16*)w16, n, lr, beta1, beta2, eps,
+  launch_k(clip_adam_l2_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, stream, p, g, m, v, (__nv_bfloat16*)w16, n, lr, beta1, beta2, eps,
                                                                              wd, clip, bc1, bc2_sqrt);
   return check_launch("clip_adam_l2_kernel");
 }
 
 __global__ void __launch_bounds__(256) ema_lerp_kernel(float* __restrict__ t, const float* __restrict__ s,
                                                        __nv_bfloat16* __restrict__ w16, long long n, float decay) {
+  pdl_sync();
   const long long i4 = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
   if (i4 >= n) return;
   if (i4 + 4 <= n) {
@@ -96,7 +98,7 @@ int ema_lerp(float* t, const float* s, void* w16, long long n, float decay, cuda
               "ema_lerp: buffers must be 16-byte aligned");
   if (n == 0) return 0;
   const long long threads = (n + 3) / 4;
-  ema_lerp_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(t, s, (__nv_bfloat16*)w16, n, decay);
+  launch_k(ema_lerp_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, stream, t, s, (__nv_bfloat16*)w16, n, decay);
   return check_launch("ema_lerp_kernel");
 }
 

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const TIn* __restrict__ x, 
                                                      const float* __restrict__ beta, TOut* __restrict__ y,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                      long long rows, int C, float eps) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + warp;
   if (row >= rows) return;
@@ -94,7 +95,7 @@ int layernorm_fwd(const void* x, int x_bf16, RowMap in_map, const float* gamma, 
   SFK_REQUIRE(C % 4 == 0 && C <= 4 * 32 * LN_CHUNK_LIMIT, "layernorm: C=%d unsupported (need C %% 4 == 0, C <= 1024)", C);
   if (rows == 0) return 0;
   const unsigned grid = (unsigned)((rows + 7) / 8);
-#define LAUNCH_N(TI, TO, NCH) ln_fwd_kernel<TI, TO, NCH><<<grid, 256, 0, stream>>>((const TI*)x, in_map, gamma, beta, (TO*)y, mean, rstd, rows, C, eps)
+#define LAUNCH_N(TI, TO, NCH) launch_k(ln_fwd_kernel<TI, TO, NCH>, dim3(grid), dim3(256), 0, stream, (const TI*)x, in_map, gamma, beta, (TO*)y, mean, rstd, rows, C, eps)
 #define LAUNCH(TI, TO)                                   \
   do {                                                   \
     if (C <= 128) LAUNCH_N(TI, TO, 1);                   \
@@ -122,6 +123,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDy* __restrict__ dy,
                                                      RowMap dres_map, TDx* __restrict__ dx, RowMap dx_map,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows,
                                                      int C, int rows_per_block) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = C >> 2;
   float4 gacc[LN_MAX_CHUNKS], bacc[LN_MAX_CHUNKS], g[LN_MAX_CHUNKS];
@@ -215,7 +217,7 @@ int layernorm_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, RowMap
   const size_t smem = (size_t)8 * 2 * C * sizeof(float);
 #define LAUNCH_N(TD, TX, TO, NCH)                                                                                       \
   if (smem > 48 * 1024) cudaFuncSetAttribute(ln_bwd_kernel<TD, TX, TO, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-  ln_bwd_kernel<TD, TX, TO, NCH><<<(unsigned)grid, 256, smem, stream>>>((const TD*)dy, (const TX*)x, x_map, mean, rstd, gamma, \
+  launch_k(ln_bwd_kernel<TD, TX, TO, NCH>, dim3((unsigned)grid), dim3(256), smem, stream, (const TD*)dy, (const TX*)x, x_map, mean, rstd, gamma, \
                                                                         dres, dres_map, (TO*)dx, dx_map, dgamma, dbeta, rows, \
                                                                         C, rows_per_block)
 #define LAUNCH(TD, TX, TO)                               \
@@ -253,6 +255,7 @@ __global__ void __launch_bounds__(256) scale_cast_kernel(const TIn* __restrict__
                                                          RowMap out_map, const float* __restrict__ scale, int rows_per_scale,
                                                          long long rows, int C4, int cwb, int rows_per_block,
                                                          float* __restrict__ colsum0, float* __restrict__ colsum1, int split) {
+  pdl_sync();
   __shared__ float sh[256 * 4];
   const int lanes_r = 256 / cwb;                 // row lanes per block
   const int rl = threadIdx.x / cwb;              // this thread's row lane
@@ -305,7 +308,7 @@ int scale_cast_sum(const void* x, int x_bf16, RowMap in_map, void* y, int y_bf16
   if (colsum0 != nullptr && colsum1 == nullptr) { colsum1 = colsum0; split = C; }
   dim3 grid(gx, (unsigned)gy);
 #define LAUNCH(TI, TO)                                                                                                       \
-  scale_cast_kernel<TI, TO><<<grid, 256, 0, stream>>>((const TI*)x, in_map, (TO*)y, out_map, scale, rows_per_scale, rows, C4, \
+  launch_k(scale_cast_kernel<TI, TO>, dim3(grid), dim3(256), 0, stream, (const TI*)x, in_map, (TO*)y, out_map, scale, rows_per_scale, rows, C4, \
                                                       cwb, (int)rpb, colsum0, colsum1, split)
   if (x_bf16 && y_bf16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
   else if (x_bf16) LAUNCH(__nv_bfloat16, float);
@@ -326,6 +329,7 @@ int scale_cast(const void* x, int x_bf16, RowMap in_map, void* y, int y_bf16, Ro
 template <typename T>
 __global__ void __launch_bounds__(128) colsum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out,
                                                      long long rows, int C, int rows_per_block) {
+  pdl_sync();
   const int c = (blockIdx.x * 128 + threadIdx.x) * 2;
   if (c >= C) return;
   const long long r0 = (long long)blockIdx.y * rows_per_block;
@@ -355,8 +359,8 @@ int colsum(const void* x, int x_bf16, long long ld, float* out, long long rows, 
   if (rpb < 32) rpb = 32;
   gy = (rows + rpb - 1) / rpb;
   dim3 grid(gx, (unsigned)gy);
-  if (x_bf16) colsum_kernel<__nv_bfloat16><<<grid, 128, 0, stream>>>((const __nv_bfloat16*)x, ld, out, rows, C, rpb);
-  else colsum_kernel<float><<<grid, 128, 0, stream>>>((const float*)x, ld, out, rows, C, rpb);
+  if (x_bf16) launch_k(colsum_kernel<__nv_bfloat16>, dim3(grid), dim3(128), 0, stream, (const __nv_bfloat16*)x, ld, out, rows, C, rpb);
+  else launch_k(colsum_kernel<float>, dim3(grid), dim3(128), 0, stream, (const float*)x, ld, out, rows, C, rpb);
   return check_launch("colsum_kernel");
 }
 
@@ -367,6 +371,7 @@ int colsum(const void* x, int x_bf16, long long ld, float* out, long long rows, 
 __global__ void __launch_bounds__(256) concat_front_kernel(const float* __restrict__ front, long long front_batch_stride,
                                                            const float* __restrict__ x, float* __restrict__ out, int B, int P,
                                                            int N, int C4) {
+  pdl_sync();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   const long long total = (long long)B * (P + N) * C4;
   if (idx >= total) return;
@@ -385,12 +390,13 @@ int concat_front(const float* front, long long front_batch_stride, const float* 
   SFK_REQUIRE(C % 4 == 0, "concat_front: C must be a multiple of 4");
   const long long total = (long long)B * (P + N) * (C / 4);
   if (total == 0) return 0;
-  concat_front_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(front, front_batch_stride, x, out, B, P, N, C / 4);
+  launch_k(concat_front_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, front, front_batch_stride, x, out, B, P, N, C / 4);
   return check_launch("concat_front_kernel");
 }
 
 // dfront[P,C] (+)= sum_b g[b, 0:P, :] (shared prompt rows: MS:451 repeat -> sum over batch)
 __global__ void front_grad_sum_kernel(const float* __restrict__ g, float* __restrict__ dfront, int B, int P, int T, int C) {
+  pdl_sync();
   const int idx = blockIdx.x * 256 + threadIdx.x;
   if (idx >= P * C) return;
   const int t = idx / C, c = idx % C;
@@ -401,7 +407,7 @@ __global__ void front_grad_sum_kernel(const float* __restrict__ g, float* __rest
 
 int front_grad_sum(const float* g, float* dfront, int B, int P, int T, int C, cudaStream_t stream) {
   if (P * C == 0) return 0;
-  front_grad_sum_kernel<<<(P * C + 255) / 256, 256, 0, stream>>>(g, dfront, B, P, T, C);
+  launch_k(front_grad_sum_kernel, dim3((P * C + 255) / 256), dim3(256), 0, stream, g, dfront, B, P, T, C);
   return check_launch("front_grad_sum_kernel");
 }
 

@@ -383,7 +383,8 @@ class SegformerLayer(nn.Module):
             sh = {}
             sh["wq"] = ops.weight_bf16(a.query.weight)
             wk, wv = ops.weight_bf16(a.key.weight), ops.weight_bf16(a.value.weight)
-            if wv.data_ptr() == wk.data_ptr() + 2 * C * C:   # adjacent in FusedClipAdam's flat shadow: a free [2C, C] view
+            same = wk.untyped_storage().data_ptr() == wv.untyped_storage().data_ptr()
+            if same and wv.data_ptr() == wk.data_ptr() + 2 * C * C:   # adjacent in FusedClipAdam's flat shadow: a free [2C, C] view
                 wkv = torch.as_strided(wk, (2 * C, C), (C, 1))
             else:
                 wkv = torch.empty(2 * C, C, device=a.key.weight.device, dtype=torch.bfloat16)
@@ -391,7 +392,7 @@ class SegformerLayer(nn.Module):
                 ops.call("sfk_cast_2d", a.value.weight.data_ptr(), C, wkv[C:].data_ptr(), C, C, C, C, ops.stream())
             sh["wkv"] = wkv
             bk, bv = a.key.bias.detach(), a.value.bias.detach()
-            if bv.data_ptr() == bk.data_ptr() + 4 * C:
+            if bk.untyped_storage().data_ptr() == bv.untyped_storage().data_ptr() and bv.data_ptr() == bk.data_ptr() + 4 * C:
                 sh["bkv"] = torch.as_strided(bk, (2 * C,), (1,))
             else:
                 sh["bkv"] = torch.cat([bk, bv]).contiguous()

@@ -59,7 +59,7 @@ class FusedClipAdam(torch.optim.Optimizer):
         offs, total = [], 0
         for p in ps:
             offs.append(total)
-            total += (p.numel() + 3) // 4 * 4  # keep every parameter 16-byte aligned
+            total += (p.numel() + 7) // 8 * 8  # every parameter 16-byte aligned in the bf16 shadow too (TMA operand base)
         self.flat_p = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
         self.flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
@@ -98,7 +98,7 @@ class FusedClipAdam(torch.optim.Optimizer):
         ranges, cur = [], None
         for p, o in zip(self._params, self._offsets):
             live = p.requires_grad and getattr(p, "_sfk_live", False)
-            end = o + (p.numel() + 3) // 4 * 4
+            end = o + (p.numel() + 7) // 8 * 8
             if live:
                 if cur is not None and cur[1] == o:
                     cur[1] = end
