@@ -254,11 +254,13 @@ def run_sfk(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     prof = {}
     e0.record()
+    t_cpu0 = time.perf_counter()
     for i in range(args.steps):
         if i == args.steps - 1 and rank == 0:
             lib.sfk_profile_gemm_begin()
         loss = step(dev_l, dev_u, dev_gt)
     e1.record()
+    cpu_enqueue_ms = 1000.0 * (time.perf_counter() - t_cpu0) / args.steps  # host time to enqueue a step (no sync inside)
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
     launches = lib.sfk_launch_count() - launches0
@@ -266,6 +268,8 @@ def run_sfk(args):
         t_ms, t_fl, t_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
         lib.sfk_profile_gemm_end(ctypes.byref(t_ms), ctypes.byref(t_fl), ctypes.byref(t_n))
         prof = dict(ms=t_ms.value, flops=t_fl.value, launches=t_n.value)
+        if args.gemm_csv:
+            lib.sfk_profile_gemm_dump(args.gemm_csv.encode())
     clocks = sampler.stop() if sampler else None
     # ---- end-to-end through the public API with host (pinned) inputs and a host read of the loss ----
     barrier()
@@ -305,6 +309,7 @@ def run_sfk(args):
         "e2e": {"value": imgs_per_step / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),
+        "cpu_enqueue_ms_per_step": cpu_enqueue_ms,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": achieved_tf, "peak": pk["tf_sustained"],
                      "unit": "TFLOP/s", "frac": (achieved_tf / pk["tf_sustained"]) if achieved_tf else None, "traffic": None,
@@ -329,6 +334,7 @@ def main():
     ap.add_argument("--variant", default="nvidia/mit-b5")
     ap.add_argument("--tile", type=int, default=TILE)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gemm-csv", default=None, help="write per-launch GEMM shapes and durations of the profiled step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "sfk":
         args.warmup = 3  # timing rules: at least 3 warm-up steps

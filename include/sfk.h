@@ -42,6 +42,8 @@ long long sfk_launch_count(void);
 /* Live timing of the dominant kernel: CUDA events around every GEMM launch between begin and end (end synchronises). */
 int sfk_profile_gemm_begin(void);
 int sfk_profile_gemm_end(double* total_ms, double* total_flops, long long* launches);
+/* After sfk_profile_gemm_end: one CSV line per profiled GEMM launch (M,N,K,flags,microseconds). */
+int sfk_profile_gemm_dump(const char* path);
 
 /* ---- dense contractions (tcgen05 + TMA + TMEM) ------------------------------------------------------------
  * D[M,N] = alpha * (A · B^T) (+ bias[N]) (* row_scale[row / rows_per_scale]) (+ residual[M,N] f32) (relu)

@@ -54,6 +54,8 @@ _CTYPE = {
 
 def _ctype_of(decl: str):
     decl = decl.strip()
+    if "char*" in decl.replace(" ", ""):
+        return ctypes.c_char_p
     if "*" in decl:
         return ctypes.c_void_p
     base = re.sub(r"\b(const|unsigned)\b", "", decl)

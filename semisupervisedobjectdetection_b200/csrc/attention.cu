@@ -51,7 +51,7 @@ template <int D>
 __global__ void __launch_bounds__(160, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, const AttFwdParams p) {
-  pdl_sync();
+  pdl_launch_dependents();
   using Cfg = AttCfg<D>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -74,6 +74,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_fence_init();
   }
   if (warp == 4) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  pdl_wait();  // setup above overlaps the previous kernel's tail
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(160, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                 const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                 const AttBwdParams p) {
-  pdl_sync();
+  pdl_launch_dependents();
   using Cfg = AttCfg<D>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -350,6 +351,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_fence_init();
   }
   if (warp == 4) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  pdl_wait();  // setup above overlaps the previous kernel's tail
   tc_fence_before();
   __syncthreads();
   tc_fence_after();

@@ -24,6 +24,7 @@ int  check_launch(const char* what);  // returns 0 or negative error, records me
 
 int num_sms();
 void prof_gemm_begin(double flops, cudaStream_t st);
+void prof_gemm_shape(long long M, long long N, long long K, long long flags);
 void prof_gemm_end(cudaStream_t st);
 
 // ----------------------------------------------------------------------------------------------

@@ -66,7 +66,7 @@ __device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, fl
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmKernelParams p) {
-  pdl_sync();
+  pdl_launch_dependents();  // let the next kernel of the stream get scheduled; it waits for our completion itself
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-B alignment is required by SWIZZLE_128B atoms; dynamic smem base is only 16-B aligned by contract.
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -102,6 +102,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     tmem_alloc(tmem_slot, TMEM_COLS);
     tmem_relinquish();
   }
+  // barrier init / TMEM allocation / descriptor prefetch above overlap the previous kernel's tail (PDL);
+  // nothing before this point touches global memory produced by it.
+  pdl_wait();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -399,6 +402,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   }
   const long long units = (long long)p.m_tiles * p.n_tiles * p.splits;
   int grid = (int)(units < num_sms() ? units : num_sms());
+  prof_gemm_shape(g.M, g.N, g.K, (g.a_mn ? 1 : 0) | (g.b_mn ? 2 : 0) | (g.atomic_add ? 4 : 0) | (p.splits << 8) | ((long long)p.block_n << 20));
   prof_gemm_begin(2.0 * (double)g.M * (double)g.N * (double)g.K, stream);
   launch_k(gemm_bf16_tcgen05_kernel, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, p);
   prof_gemm_end(stream);

@@ -113,8 +113,14 @@ struct ProfState {
   size_t used = 0;
   double flops = 0.0;
   long long launches = 0;
+  std::vector<long long> shapes;  // M, N, K, flags per launch
 };
 static ProfState g_prof;
+
+void prof_gemm_shape(long long M, long long N, long long K, long long flags) {
+  if (!g_prof.on) return;
+  g_prof.shapes.push_back(M); g_prof.shapes.push_back(N); g_prof.shapes.push_back(K); g_prof.shapes.push_back(flags);
+}
 
 void prof_gemm_begin(double flops, cudaStream_t st) {
   if (!g_prof.on) return;
@@ -146,6 +152,23 @@ int sfk_profile_gemm_begin(void) {
   sfk::g_prof.used = 0;
   sfk::g_prof.flops = 0.0;
   sfk::g_prof.launches = 0;
+  sfk::g_prof.shapes.clear();
+  return 0;
+}
+
+/* After sfk_profile_gemm_end: write one CSV line per profiled GEMM launch (M,N,K,flags,microseconds). */
+int sfk_profile_gemm_dump(const char* path) {
+  FILE* f = fopen(path, "w");
+  if (!f) { sfk::set_error("profile: cannot open %s", path); return -1; }
+  fprintf(f, "M,N,K,flags,us\n");
+  size_t n = sfk::g_prof.used / 2;
+  for (size_t i = 0; i < n && 4 * i + 3 < sfk::g_prof.shapes.size(); ++i) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, sfk::g_prof.ev[2 * i], sfk::g_prof.ev[2 * i + 1]);
+    fprintf(f, "%lld,%lld,%lld,%lld,%.3f\n", sfk::g_prof.shapes[4 * i], sfk::g_prof.shapes[4 * i + 1], sfk::g_prof.shapes[4 * i + 2],
+            sfk::g_prof.shapes[4 * i + 3], t * 1000.f);
+  }
+  fclose(f);
   return 0;
 }
 

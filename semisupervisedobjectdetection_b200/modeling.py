@@ -62,6 +62,11 @@ def _versions(params) -> tuple:
     return tuple(p._version for p in params) + (ops.WEIGHT_EPOCH, params[0].data_ptr())
 
 
+def sh_ptr(p) -> int:
+    w16 = getattr(p, "_sfk_w16", None)
+    return -1 if w16 is None else w16.data_ptr()
+
+
 def _any_requires_grad(*tensors) -> bool:
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
@@ -91,6 +96,23 @@ def drop_path_scale(batch: int, drop_prob: float, training: bool, device) -> Opt
         return None
     keep = 1.0 - drop_prob
     return torch.floor(keep + torch.rand(batch, device=device, dtype=torch.float32)) / keep
+
+
+_KEEP_CACHE: dict = {}
+
+
+def drop_path_scales_batched(batch: int, drop_probs, training: bool, device):
+    """All per-sample drop-path multipliers of one forward pass in three tensor ops instead of four per layer:
+    returns a list (one entry per layer) of None or a [2, batch] tensor (attention branch, MLP branch; MS:350,358)."""
+    if not training or all(p == 0.0 for p in drop_probs):
+        return [None] * len(drop_probs)
+    ck = (tuple(drop_probs), str(device))
+    keep = _KEEP_CACHE.get(ck)
+    if keep is None:  # built once: a host->device copy per forward would serialise the stream
+        keep = torch.tensor([1.0 - p for p in drop_probs], dtype=torch.float32).view(-1, 1, 1).to(device)
+        _KEEP_CACHE[ck] = keep
+    scales = torch.floor(keep + torch.rand(len(drop_probs), 2, batch, device=device, dtype=torch.float32)) / keep
+    return [None if p == 0.0 else scales[i] for i, p in enumerate(drop_probs)]
 
 
 class SegformerDropPath(nn.Module):
@@ -380,6 +402,18 @@ class SegformerLayer(nn.Module):
         if self._sh_key != key:
             a, m = self.attention.self, self.mlp
             C = a.hidden_size
+            sh = self._sh
+            flat_ok = sh is not None and sh.get("flat", False) and self._sh_key[-1] == key[-1] and self._sh_key[:-2] == key[:-2]
+            if flat_ok:
+                # only libsfk's weight epoch moved (optimiser / EMA step): the Linear operands are live views of the flat bf16
+                # shadow; just re-run the two layout permutations into their existing buffers
+                if a.sr_ratio > 1:
+                    sr = a.sr_ratio
+                    ops.call("sfk_conv_weight_ohwi", a.sr.weight.data_ptr(), sh["wsr"].data_ptr(), C, C, sr, sr, sr * sr * C, ops.stream())
+                ops.call("sfk_dw_weight_to_tap", m.dwconv.dwconv.weight.data_ptr(), sh["dw_wt"].data_ptr(), m.dense1.out_features,
+                         ops.stream())
+                self._sh_key = key
+                return sh
             sh = {}
             sh["wq"] = ops.weight_bf16(a.query.weight)
             wk, wv = ops.weight_bf16(a.key.weight), ops.weight_bf16(a.value.weight)
@@ -408,6 +442,9 @@ class SegformerLayer(nn.Module):
             wt = torch.empty(9, hid, device=wkv.device, dtype=torch.float32)
             ops.call("sfk_dw_weight_to_tap", m.dwconv.dwconv.weight.data_ptr(), wt.data_ptr(), hid, ops.stream())
             sh["dw_wt"] = wt
+            sh["flat"] = all(getattr(p, "_sfk_w16", None) is not None for p in
+                             (a.query.weight, a.key.weight, a.value.weight, self.attention.output.dense.weight, m.dense1.weight,
+                              m.dense2.weight)) and sh["wkv"].data_ptr() == sh_ptr(a.key.weight) and sh["bkv"].data_ptr() == a.key.bias.data_ptr()
             self._sh, self._sh_key = sh, key
         return self._sh
 
@@ -462,12 +499,16 @@ class SegformerLayer(nn.Module):
             front_out = out[:, :0, :]
         return (out,), front_out
 
-    def _forward_split(self, spatial, front, height, width):
+    def drop_prob(self) -> float:
+        return self.drop_path.drop_prob if isinstance(self.drop_path, SegformerDropPath) else 0.0
+
+    def _forward_split(self, spatial, front, height, width, scales=None):
         B = spatial.shape[0]
-        dp = self.drop_path.drop_prob if isinstance(self.drop_path, SegformerDropPath) else 0.0
-        # the same DropPath module is applied twice with independent draws (MS:350,358)
-        s_attn = drop_path_scale(B, dp, self.training, spatial.device)
-        s_mlp = drop_path_scale(B, dp, self.training, spatial.device)
+        if scales is None and self.training and self.drop_prob() > 0.0:
+            # the same DropPath module is applied twice with independent draws (MS:350,358)
+            scales = drop_path_scales_batched(B, [self.drop_prob()], True, spatial.device)[0]
+        s_attn = scales[0] if scales is not None else None
+        s_mlp = scales[1] if scales is not None else None
         anchor = self._anchor.get(self._params(), spatial.device)
         return _LayerFn.apply(spatial.float(), None if front is None else front.float(), anchor, self, height, width, s_attn, s_mlp)
 
@@ -541,6 +582,9 @@ class SegformerEncoder(nn.Module):
         x_in, is_image = pixel_values.float().contiguous(), True
         Hin, Win = pixel_values.shape[2], pixel_values.shape[3]
         stages, block_cls = [], []
+        all_layers = [layer for blk in self.block for layer in blk]
+        dp_scales = drop_path_scales_batched(B, [l.drop_prob() for l in all_layers], self.training, pixel_values.device)
+        layer_no = 0
         for idx, (emb, blk, norm) in enumerate(zip(self.patch_embeddings, self.block, self.layer_norm)):
             hidden, H, W = emb._forward_tokens(x_in, is_image, Hin, Win)
             if self._ddp_bucketer is not None and hidden.requires_grad:
@@ -561,7 +605,8 @@ class SegformerEncoder(nn.Module):
                     rows = pt[i] if pt.dim() == 3 else pt
                     front_parts.append(rows.to(hidden.device).float().unsqueeze(0).expand(B, -1, -1))
                 front = torch.cat(front_parts, dim=1).contiguous() if front_parts else None
-                hidden, front_out = layer._forward_split(hidden, front, H, W)
+                hidden, front_out = layer._forward_split(hidden, front, H, W, dp_scales[layer_no])
+                layer_no += 1
                 if ct is not None:
                     running_cls = front_out[:, 0:1, :]  # MS:463-465
                     block_cls[-1] = running_cls
