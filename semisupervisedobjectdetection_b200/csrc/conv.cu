@@ -6,6 +6,7 @@
 // All kernels move 64/128-bit vectors with the channel dimension innermost (fully coalesced).
 #include "common.cuh"
 #include "sfk_internal.h"
+#include "colsum_slots.cuh"
 
 namespace sfk {
 
@@ -74,9 +75,11 @@ template <> struct VecIO<4> {
   }
 };
 
-// block-level reduction of per-thread channel partials: sh[cg_local*VEC + v] accumulates over the 8 warps
+// block-level reduction of per-thread channel partials (8 warps -> shared memory), then the slotted low-contention commit:
+// virtual column v = k * C + channel  (k-th output array)
 template <int VEC, int NV>
-__device__ __forceinline__ void dw_block_commit(float (&acc)[NV][VEC], float* sh, float* const* outs, int c0, int C, bool lane_ok) {
+__device__ __forceinline__ void dw_block_commit(float (&acc)[NV][VEC], float* sh, float* const* outs, int c0, int C, bool lane_ok,
+                                                int ns) {
   const int lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < NV * 32 * VEC; i += 256) sh[i] = 0.f;
   __syncthreads();
@@ -87,11 +90,17 @@ __device__ __forceinline__ void dw_block_commit(float (&acc)[NV][VEC], float* sh
       for (int v = 0; v < VEC; ++v) atomicAdd(&sh[(k * 32 + lane) * VEC + v], acc[k][v]);
   }
   __syncthreads();
-  const int cbase = c0 - lane * VEC;  // first channel of this block
-  for (int i = threadIdx.x; i < NV * 32 * VEC; i += 256) {
-    const int k = i / (32 * VEC), j = i % (32 * VEC);
-    if (cbase + j < C) atomicAdd(outs[k] + cbase + j, sh[i]);
-  }
+  const int cbase = c0 - lane * VEC;  // first channel of this block (same for every lane)
+  int ncol = C - cbase;
+  if (ncol > 32 * VEC) ncol = 32 * VEC;
+  // slots are laid out [ns][NV][ncol-wide window per blockIdx.x]: use V = gridDim.x * NV * 32 * VEC virtual columns
+  const int V = gridDim.x * NV * 32 * VEC;
+  const int v0 = blockIdx.x * NV * 32 * VEC;
+  colsum_commit(sh, v0, NV * 32 * VEC, V, ns, blockIdx.y, gridDim.y, blockIdx.x, [&](int v, float sum) {
+    const int local = v - v0;
+    const int k = local / (32 * VEC), j = local % (32 * VEC);
+    if (j < ncol) outs[k][cbase + j] += sum;
+  });
 }
 
 // mode 0: y = gelu(conv(x) + bias)     mode 1: y = conv_flipped(x)  (input gradient of the conv); colsum (+)= sum_pixels y
@@ -99,7 +108,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256, 2) dwconv3x3_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
                                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
                                                            float* __restrict__ colsum, int B, int H, int W, int C,
-                                                           int pos_per_block) {
+                                                           int pos_per_block, int ns) {
   pdl_sync();
   constexpr int VEC = 8;
   __shared__ float sh[32 * VEC];
@@ -178,7 +187,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_kernel(const __nv_bfloat16* 
   }
   if (MODE == 1 && colsum != nullptr) {
     float* outs[1] = {colsum};
-    dw_block_commit<VEC, 1>(csum, sh, outs, c0, C, lane_ok);
+    dw_block_commit<VEC, 1>(csum, sh, outs, c0, C, lane_ok, ns);
   }
 }
 
@@ -203,9 +212,10 @@ int dwconv3x3(const void* x, const float* wt, const float* bias, void* y, float*
   int ppb;
   dw_grid(C, 8, npos, grid, ppb);
   if (mode == 0)
-    launch_k(dwconv3x3_kernel<0>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, bias, (__nv_bfloat16*)y, nullptr, B, H, W, C, ppb);
+    launch_k(dwconv3x3_kernel<0>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, bias, (__nv_bfloat16*)y, nullptr, B, H, W, C, ppb, 1);
   else
-    launch_k(dwconv3x3_kernel<1>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, nullptr, (__nv_bfloat16*)y, colsum, B, H, W, C, ppb);
+    launch_k(dwconv3x3_kernel<1>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, nullptr, (__nv_bfloat16*)y, colsum, B, H, W, C, ppb,
+             colsum_num_slots((long long)grid.x * 32 * 8, grid.y));
   return check_launch("dwconv3x3_kernel");
 }
 
@@ -216,7 +226,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_bwd_kernel(const __nv_b
                                                                     const __nv_bfloat16* __restrict__ dg,
                                                                     __nv_bfloat16* __restrict__ dpre, float* __restrict__ dwt,
                                                                     float* __restrict__ dbias, int B, int H, int W, int C,
-                                                                    int pos_per_block) {
+                                                                    int pos_per_block, int ns) {
   pdl_sync();
   constexpr int VEC = 4;
   __shared__ float sh[10 * 32 * VEC];
@@ -297,7 +307,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_bwd_kernel(const __nv_b
 #pragma unroll
     for (int k = 0; k < 9; ++k) outs[k] = dwt + (long long)k * C;
     outs[9] = dbias;
-    dw_block_commit<VEC, 10>(acc, sh, outs, c0, C, lane_ok);
+    dw_block_commit<VEC, 10>(acc, sh, outs, c0, C, lane_ok, ns);
   }
 }
 
@@ -311,7 +321,8 @@ int dwconv3x3_gelu_bwd(const void* x, const float* wt, const float* bias, const 
   int ppb;
   dw_grid(C, 4, npos, grid, ppb);
   launch_k(dwconv3x3_gelu_bwd_kernel, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, bias, (const __nv_bfloat16*)dg,
-                                                      (__nv_bfloat16*)dpre, dwt, dbias, B, H, W, C, ppb);
+                                                      (__nv_bfloat16*)dpre, dwt, dbias, B, H, W, C, ppb,
+           colsum_num_slots((long long)grid.x * 10 * 32 * 4, grid.y));
   return check_launch("dwconv3x3_gelu_bwd_kernel");
 }
 

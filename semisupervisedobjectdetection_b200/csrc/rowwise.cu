@@ -5,6 +5,7 @@
 // autograd gradients of those; bias gradients of every nn.Linear/Conv2d on the path.
 #include "common.cuh"
 #include "sfk_internal.h"
+#include "colsum_slots.cuh"
 
 namespace sfk {
 
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDy* __restrict__ dy,
                                                      const float* __restrict__ gamma, const float* __restrict__ dres,
                                                      RowMap dres_map, TDx* __restrict__ dx, RowMap dx_map,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows,
-                                                     int C, int rows_per_block) {
+                                                     int C, int rows_per_block, int ns) {
   pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = C >> 2;
@@ -192,13 +193,18 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDy* __restrict__ dy,
     }
   }
   __syncthreads();
+  float* tot = red + 8 * 2 * C;  // [2*C] block totals
   for (int c = threadIdx.x; c < 2 * C; c += 256) {
     float t = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) t += red[w * 2 * C + c];
-    if (c < C) atomicAdd(dgamma + c, t);
-    else atomicAdd(dbeta + (c - C), t);
+    tot[c] = t;
   }
+  __syncthreads();
+  colsum_commit(tot, 0, 2 * C, 2 * C, ns, blockIdx.x, gridDim.x, 0, [&](int c, float sum) {
+    if (c < C) dgamma[c] += sum;
+    else dbeta[c - C] += sum;
+  });
 }
 
 int layernorm_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, RowMap x_map, const float* mean,
@@ -214,12 +220,13 @@ int layernorm_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, RowMap
     rows_per_block = (rows_per_block + 7) / 8 * 8;
     grid = (rows + rows_per_block - 1) / rows_per_block;
   }
-  const size_t smem = (size_t)8 * 2 * C * sizeof(float);
+  const size_t smem = (size_t)9 * 2 * C * sizeof(float);
+  const int ns = colsum_num_slots(2 * C, grid);
 #define LAUNCH_N(TD, TX, TO, NCH)                                                                                       \
   if (smem > 48 * 1024) cudaFuncSetAttribute(ln_bwd_kernel<TD, TX, TO, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   launch_k(ln_bwd_kernel<TD, TX, TO, NCH>, dim3((unsigned)grid), dim3(256), smem, stream, (const TD*)dy, (const TX*)x, x_map, mean, rstd, gamma, \
                                                                         dres, dres_map, (TO*)dx, dx_map, dgamma, dbeta, rows, \
-                                                                        C, rows_per_block)
+                                                                        C, rows_per_block, ns)
 #define LAUNCH(TD, TX, TO)                               \
   do {                                                   \
     if (C <= 128) { LAUNCH_N(TD, TX, TO, 1); }           \
@@ -254,9 +261,10 @@ template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) scale_cast_kernel(const TIn* __restrict__ x, RowMap in_map, TOut* __restrict__ y,
                                                          RowMap out_map, const float* __restrict__ scale, int rows_per_scale,
                                                          long long rows, int C4, int cwb, int rows_per_block,
-                                                         float* __restrict__ colsum0, float* __restrict__ colsum1, int split) {
+                                                         float* __restrict__ colsum0, float* __restrict__ colsum1, int split,
+                                                         int ns) {
   pdl_sync();
-  __shared__ float sh[256 * 4];
+  __shared__ __align__(16) float sh[256 * 4];
   const int lanes_r = 256 / cwb;                 // row lanes per block
   const int rl = threadIdx.x / cwb;              // this thread's row lane
   const int c4 = blockIdx.x * cwb + (threadIdx.x % cwb);
@@ -280,16 +288,23 @@ __global__ void __launch_bounds__(256) scale_cast_kernel(const TIn* __restrict__
   if (colsum0 == nullptr) return;
   *reinterpret_cast<float4*>(&sh[threadIdx.x * 4]) = acc;
   __syncthreads();
-  if (threadIdx.x < cwb && c4 < C4) {
+  __shared__ __align__(16) float colsh[256 * 4];
+  if (threadIdx.x < cwb) {
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = 0; r < lanes_r; ++r) {
       const float4 u = *reinterpret_cast<const float4*>(&sh[(r * cwb + threadIdx.x) * 4]);
       t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
     }
-    const int c = c4 * 4;
-    float* dst = c < split ? colsum0 + c : colsum1 + (c - split);
-    atomicAdd(dst, t.x); atomicAdd(dst + 1, t.y); atomicAdd(dst + 2, t.z); atomicAdd(dst + 3, t.w);
+    *reinterpret_cast<float4*>(&colsh[threadIdx.x * 4]) = t;
   }
+  __syncthreads();
+  const int v0 = blockIdx.x * cwb * 4;
+  int nv = cwb * 4;
+  if (v0 + nv > C4 * 4) nv = C4 * 4 - v0;
+  colsum_commit(colsh, v0, nv, C4 * 4, ns, blockIdx.y, gridDim.y, blockIdx.x, [&](int c, float sum) {
+    float* dst = c < split ? colsum0 + c : colsum1 + (c - split);
+    *dst += sum;
+  });
 }
 
 int scale_cast_sum(const void* x, int x_bf16, RowMap in_map, void* y, int y_bf16, RowMap out_map, const float* scale,
@@ -306,10 +321,12 @@ int scale_cast_sum(const void* x, int x_bf16, RowMap in_map, void* y, int y_bf16
   gy = (rows + rpb - 1) / rpb;
   if (rows_per_scale <= 0) rows_per_scale = 1;
   if (colsum0 != nullptr && colsum1 == nullptr) { colsum1 = colsum0; split = C; }
+  SFK_REQUIRE(colsum0 == nullptr || (gx <= COLSUM_MAX_GX && C <= COLSUM_SLOT_FLOATS), "scale_cast: C=%d too wide for fused sums", C);
+  const int ns = colsum_num_slots(C, gy);
   dim3 grid(gx, (unsigned)gy);
 #define LAUNCH(TI, TO)                                                                                                       \
   launch_k(scale_cast_kernel<TI, TO>, dim3(grid), dim3(256), 0, stream, (const TI*)x, in_map, (TO*)y, out_map, scale, rows_per_scale, rows, C4, \
-                                                      cwb, (int)rpb, colsum0, colsum1, split)
+                                                      cwb, (int)rpb, colsum0, colsum1, split, ns)
   if (x_bf16 && y_bf16) LAUNCH(__nv_bfloat16, __nv_bfloat16);
   else if (x_bf16) LAUNCH(__nv_bfloat16, float);
   else if (y_bf16) LAUNCH(float, __nv_bfloat16);
