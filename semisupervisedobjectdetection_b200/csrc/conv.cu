@@ -78,8 +78,8 @@ template <> struct VecIO<4> {
 // block-level reduction of per-thread channel partials (8 warps -> shared memory), then the slotted low-contention commit:
 // virtual column v = k * C + channel  (k-th output array)
 template <int VEC, int NV>
-__device__ __forceinline__ void dw_block_commit(float (&acc)[NV][VEC], float* sh, float* const* outs, int c0, int C, bool lane_ok,
-                                                int ns) {
+__device__ __forceinline__ void dw_block_commit(float (&acc)[NV][VEC], float* sh, float* out_base, long long out_stride,
+                                                float* out_last, int c0, int C, bool lane_ok, int ns) {
   const int lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < NV * 32 * VEC; i += 256) sh[i] = 0.f;
   __syncthreads();
@@ -99,52 +99,69 @@ __device__ __forceinline__ void dw_block_commit(float (&acc)[NV][VEC], float* sh
   colsum_commit(sh, v0, NV * 32 * VEC, V, ns, blockIdx.y, gridDim.y, blockIdx.x, [&](int v, float sum) {
     const int local = v - v0;
     const int k = local / (32 * VEC), j = local % (32 * VEC);
-    if (j < ncol) outs[k][cbase + j] += sum;
+    if (j < ncol) {
+      float* dst = (k == NV - 1) ? out_last : out_base + (long long)k * out_stride;
+      dst[cbase + j] += sum;
+    }
   });
 }
 
 // mode 0: y = gelu(conv(x) + bias)     mode 1: y = conv_flipped(x)  (input gradient of the conv); colsum (+)= sum_pixels y
+// The 9 x VEC filter taps of a lane live in shared memory ([tap][lane][VEC], conflict-free 128-bit reads) instead of 72
+// registers: the kernel is global-latency bound (ncu: long_scoreboard), so register count -> resident warps is what matters.
 template <int MODE>
 __global__ void __launch_bounds__(256, 2) dwconv3x3_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
                                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
                                                            float* __restrict__ colsum, int B, int H, int W, int C,
                                                            int pos_per_block, int ns) {
   pdl_sync();
-  constexpr int VEC = 8;
+  constexpr int VEC = 4;
+  __shared__ __align__(16) float sw[9 * 32 * VEC];
   __shared__ float sh[32 * VEC];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c0 = (blockIdx.x * 32 + lane) * VEC;
+  const int cblk = blockIdx.x * 32 * VEC;
+  const int c0 = cblk + lane * VEC;
   const bool lane_ok = c0 < C;
+  for (int i = threadIdx.x; i < 9 * 32 * VEC; i += 256) {
+    const int k = i / (32 * VEC), j = i % (32 * VEC);
+    const int kk = MODE == 1 ? 8 - k : k;
+    sw[i] = (cblk + j < C) ? wt[(long long)kk * C + cblk + j] : 0.f;
+  }
+  __syncthreads();
   const int nseg = (W + DW_SEG - 1) / DW_SEG;
   const long long npos = (long long)B * H * nseg;
   const long long p0 = (long long)blockIdx.y * pos_per_block;
   long long p1 = p0 + pos_per_block;
   if (p1 > npos) p1 = npos;
-  float w[9][VEC];
   float bs[VEC];
   float csum[1][VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) { bs[v] = 0.f; csum[0][v] = 0.f; }
   if (lane_ok) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      const int kk = MODE == 1 ? 8 - k : k;
-      const float4 a = __ldg(reinterpret_cast<const float4*>(wt + (long long)kk * C + c0));
-      const float4 bq = __ldg(reinterpret_cast<const float4*>(wt + (long long)kk * C + c0 + 4));
-      w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
-      w[k][4] = bq.x; w[k][5] = bq.y; w[k][6] = bq.z; w[k][7] = bq.w;
-    }
     if (MODE == 0) {
       const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c0));
-      const float4 bq = __ldg(reinterpret_cast<const float4*>(bias + c0 + 4));
-      bs[0] = a.x; bs[1] = a.y; bs[2] = a.z; bs[3] = a.w; bs[4] = bq.x; bs[5] = bq.y; bs[6] = bq.z; bs[7] = bq.w;
+      bs[0] = a.x; bs[1] = a.y; bs[2] = a.z; bs[3] = a.w;
     }
+    const float* swl = sw + lane * VEC;
     for (long long pos = p0 + warp; pos < p1; pos += 8) {
       const int seg = (int)(pos % nseg);
       const long long t = pos / nseg;
       const int yy = (int)(t % H);
       const int b = (int)(t / H);
       const int x0 = seg * DW_SEG;
+      // issue the whole 3 x (SEG+2) window first (18 independent 16-byte loads in flight), then do the math
+      typename VecIO<VEC>::packed win[3][DW_SEG + 2];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int sy = yy + r - 1;
+        const bool vy = sy >= 0 && sy < H;
+#pragma unroll
+        for (int j = 0; j < DW_SEG + 2; ++j) {
+          const int sx = x0 + j - 1;
+          win[r][j] = (vy && sx >= 0 && sx < W) ? VecIO<VEC>::ldp(x + ((long long)(b * H + sy) * W + sx) * C + c0)
+                                                : VecIO<VEC>::zero();
+        }
+      }
       float acc[DW_SEG][VEC];
 #pragma unroll
       for (int o = 0; o < DW_SEG; ++o)
@@ -152,22 +169,16 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_kernel(const __nv_bfloat16* 
         for (int v = 0; v < VEC; ++v) acc[o][v] = bs[v];
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
-        const int sy = yy + r - 1;
-        if (sy < 0 || sy >= H) continue;
-        const __nv_bfloat16* rowp = x + ((long long)(b * H + sy) * W) * C + c0;
 #pragma unroll
-        for (int j = 0; j < DW_SEG + 2; ++j) {
-          const int sx = x0 + j - 1;
-          if (sx < 0 || sx >= W) continue;
-          float f[VEC];
-          VecIO<VEC>::ld(rowp + (long long)sx * C, f);
+        for (int tt = 0; tt < 3; ++tt) {
+          const float4 w0 = *reinterpret_cast<const float4*>(swl + (r * 3 + tt) * 32 * VEC);
+          const float wv[VEC] = {w0.x, w0.y, w0.z, w0.w};
 #pragma unroll
-          for (int tt = 0; tt < 3; ++tt) {
-            const int o = j - tt;  // output position that sees column j through tap tt
-            if (o >= 0 && o < DW_SEG) {
+          for (int o = 0; o < DW_SEG; ++o) {
+            float f[VEC];
+            VecIO<VEC>::unpack(win[r][o + tt], f);
 #pragma unroll
-              for (int v = 0; v < VEC; ++v) acc[o][v] = fmaf(w[r * 3 + tt][v], f[v], acc[o][v]);
-            }
+            for (int v = 0; v < VEC; ++v) acc[o][v] = fmaf(wv[v], f[v], acc[o][v]);
           }
         }
       }
@@ -186,8 +197,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_kernel(const __nv_bfloat16* 
     }
   }
   if (MODE == 1 && colsum != nullptr) {
-    float* outs[1] = {colsum};
-    dw_block_commit<VEC, 1>(csum, sh, outs, c0, C, lane_ok, ns);
+    dw_block_commit<VEC, 1>(csum, sh, nullptr, 0, colsum, c0, C, lane_ok, ns);
   }
 }
 
@@ -210,17 +220,17 @@ int dwconv3x3(const void* x, const float* wt, const float* bias, void* y, float*
   if (npos == 0) return 0;
   dim3 grid;
   int ppb;
-  dw_grid(C, 8, npos, grid, ppb);
+  dw_grid(C, 4, npos, grid, ppb);
   if (mode == 0)
     launch_k(dwconv3x3_kernel<0>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, bias, (__nv_bfloat16*)y, nullptr, B, H, W, C, ppb, 1);
   else
     launch_k(dwconv3x3_kernel<1>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, nullptr, (__nv_bfloat16*)y, colsum, B, H, W, C, ppb,
-             colsum_num_slots((long long)grid.x * 32 * 8, grid.y));
+             colsum_num_slots((long long)grid.x * 32 * 4, grid.y));
   return check_launch("dwconv3x3_kernel");
 }
 
 // Backward stage 1: recompute pre = conv(x)+bias, dpre = dg * gelu'(pre); accumulate dW[9][C] and db[C].
-// Window kept packed (bf16) to stay under 128 registers -> 2 blocks (16 warps) per SM.
+// Window kept packed (bf16), filter taps in shared memory, unpack-on-use: no spills at 128 registers (2 blocks / SM).
 __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
                                                                     const float* __restrict__ bias,
                                                                     const __nv_bfloat16* __restrict__ dg,
@@ -229,30 +239,32 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_bwd_kernel(const __nv_b
                                                                     int pos_per_block, int ns) {
   pdl_sync();
   constexpr int VEC = 4;
-  __shared__ float sh[10 * 32 * VEC];
+  __shared__ __align__(16) float sh[10 * 32 * VEC];   // filter taps during the main loop, block reduction afterwards
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c0 = (blockIdx.x * 32 + lane) * VEC;
+  const int cblk = blockIdx.x * 32 * VEC;
+  const int c0 = cblk + lane * VEC;
   const bool lane_ok = c0 < C;
+  for (int i = threadIdx.x; i < 9 * 32 * VEC; i += 256) {
+    const int k = i / (32 * VEC), j = i % (32 * VEC);
+    sh[i] = (cblk + j < C) ? wt[(long long)k * C + cblk + j] : 0.f;
+  }
+  __syncthreads();
   const int nseg = (W + DW_SEG - 1) / DW_SEG;
   const long long npos = (long long)B * H * nseg;
   const long long p0 = (long long)blockIdx.y * pos_per_block;
   long long p1 = p0 + pos_per_block;
   if (p1 > npos) p1 = npos;
-  float w[9][VEC], acc[10][VEC], bs[VEC];  // acc[0..8] = dW taps, acc[9] = dbias
+  float acc[10][VEC], bs[VEC];  // acc[0..8] = dW taps, acc[9] = dbias
 #pragma unroll
   for (int k = 0; k < 10; ++k)
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[k][v] = 0.f;
   if (lane_ok) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(wt + (long long)k * C + c0));
-      w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
-    }
     {
       const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c0));
       bs[0] = a.x; bs[1] = a.y; bs[2] = a.z; bs[3] = a.w;
     }
+    const float* swl = sh + lane * VEC;
     for (long long pos = p0 + warp; pos < p1; pos += 8) {
       const int seg = (int)(pos % nseg);
       const long long t = pos / nseg;
@@ -260,6 +272,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_bwd_kernel(const __nv_b
       const int b = (int)(t / H);
       const int x0 = seg * DW_SEG;
       VecIO<VEC>::packed win[3][DW_SEG + 2];
+      VecIO<VEC>::packed gin[DW_SEG];
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         const int sy = yy + r - 1;
@@ -271,43 +284,44 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_bwd_kernel(const __nv_b
                                                 : VecIO<VEC>::zero();
         }
       }
+      const long long off0 = ((long long)(b * H + yy) * W + x0) * C + c0;
+#pragma unroll
+      for (int o = 0; o < DW_SEG; ++o) gin[o] = (x0 + o < W) ? VecIO<VEC>::ldp(dg + off0 + (long long)o * C) : VecIO<VEC>::zero();
 #pragma unroll
       for (int o = 0; o < DW_SEG; ++o) {
         if (x0 + o >= W) break;
-        float f[9][VEC];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int tt = 0; tt < 3; ++tt) VecIO<VEC>::unpack(win[r][o + tt], f[r * 3 + tt]);
         float pre[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) pre[v] = bs[v];
 #pragma unroll
-        for (int k = 0; k < 9; ++k)
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) pre[v] = fmaf(w[k][v], f[k][v], pre[v]);
-        const long long off = ((long long)(b * H + yy) * W + x0 + o) * C + c0;
+        for (int k = 0; k < 9; ++k) {
+          const float4 w4 = *reinterpret_cast<const float4*>(swl + k * 32 * VEC);
+          float f[VEC];
+          VecIO<VEC>::unpack(win[k / 3][o + k % 3], f);
+          pre[0] = fmaf(w4.x, f[0], pre[0]); pre[1] = fmaf(w4.y, f[1], pre[1]);
+          pre[2] = fmaf(w4.z, f[2], pre[2]); pre[3] = fmaf(w4.w, f[3], pre[3]);
+        }
         float g[VEC], d[VEC];
-        VecIO<VEC>::ld(dg + off, g);
+        VecIO<VEC>::unpack(gin[o], g);
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
           d[v] = g[v] * gelu_grad_fast(pre[v]);
           acc[9][v] += d[v];
         }
-        VecIO<VEC>::st(dpre + off, d);
+        VecIO<VEC>::st(dpre + off0 + (long long)o * C, d);
 #pragma unroll
-        for (int k = 0; k < 9; ++k)
+        for (int k = 0; k < 9; ++k) {
+          float f[VEC];
+          VecIO<VEC>::unpack(win[k / 3][o + k % 3], f);
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[k][v] = fmaf(d[v], f[k][v], acc[k][v]);
+          for (int v = 0; v < VEC; ++v) acc[k][v] = fmaf(d[v], f[v], acc[k][v]);
+        }
       }
     }
   }
   if (dwt != nullptr) {
-    float* outs[10];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) outs[k] = dwt + (long long)k * C;
-    outs[9] = dbias;
-    dw_block_commit<VEC, 10>(acc, sh, outs, c0, C, lane_ok, ns);
+    __syncthreads();  // everyone is done with the filter taps in sh
+    dw_block_commit<VEC, 10>(acc, sh, dwt, (long long)C, dbias, c0, C, lane_ok, ns);
   }
 }
 

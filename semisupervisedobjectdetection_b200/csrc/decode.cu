@@ -6,6 +6,7 @@
 //     and the two-pass backward (per-channel reductions, then dx).
 #include "common.cuh"
 #include "sfk_internal.h"
+#include "colsum_slots.cuh"
 
 namespace sfk {
 
@@ -268,40 +269,70 @@ __device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned 
 
 static constexpr int CLS_MAX_LABELS = 8;
 
-// One warp per row of x [M, C]: y = relu(bn(x)) * dropmask ; logits[b, l, pix] = sum_c y[c] * Wc[l, c] + bc[l]
+// y = relu(bn(x)) * dropmask ; logits[b, l, pix] = sum_c y[c] * Wc[l, c] + bc[l].
+// Per-channel affine (a = rstd*gamma, b = beta - mean*a) and the classifier rows are staged once per block in shared
+// memory; every warp then streams rows with 16-byte loads (8 channels per lane per step).
 template <int DUMMY>
 __global__ void __launch_bounds__(256) bn_relu_cls_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
                                                               const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, const float* __restrict__ wc,
                                                               const float* __restrict__ bc, float* __restrict__ logits,
                                                               long long M, int C, int NL, int pix_per_sample, float drop_p,
-                                                              unsigned long long seed) {
+                                                              unsigned long long seed, int rows_per_block) {
   pdl_sync();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + warp;
-  if (row >= M) return;
-  float acc[CLS_MAX_LABELS];
-#pragma unroll
-  for (int l = 0; l < CLS_MAX_LABELS; ++l) acc[l] = 0.f;
-  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  for (int c = lane * 2; c < C; c += 64) {
-    const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + row * C + c));
-    float y0 = fmaxf((v.x - mean[c]) * rstd[c] * gamma[c] + beta[c], 0.f);
-    float y1 = fmaxf((v.y - mean[c + 1]) * rstd[c + 1] * gamma[c + 1] + beta[c + 1], 0.f);
-    if (drop_p > 0.f) {
-      y0 = hash_uniform(seed, (unsigned long long)row * C + c) >= drop_p ? y0 * keep_scale : 0.f;
-      y1 = hash_uniform(seed, (unsigned long long)row * C + c + 1) >= drop_p ? y1 * keep_scale : 0.f;
-    }
-#pragma unroll
-    for (int l = 0; l < CLS_MAX_LABELS; ++l)
-      if (l < NL) acc[l] = fmaf(y0, wc[l * C + c], fmaf(y1, wc[l * C + c + 1], acc[l]));
+  extern __shared__ __align__(16) float shf[];  // a[C], b[C], wc[NL][C]
+  float* sa = shf;
+  float* sb = shf + C;
+  float* sw = shf + 2 * C;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const float a = rstd[c] * gamma[c];
+    sa[c] = a;
+    sb[c] = beta[c] - mean[c] * a;
   }
-  const long long b = row / pix_per_sample, pix = row % pix_per_sample;
+  for (int i = threadIdx.x; i < NL * C; i += 256) sw[i] = wc[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const int nchunk = C >> 3;
+  const long long row0 = (long long)blockIdx.x * rows_per_block;
+  for (int i = warp; i < rows_per_block; i += 8) {
+    const long long row = row0 + i;
+    if (row >= M) break;
+    float acc[CLS_MAX_LABELS];
 #pragma unroll
-  for (int l = 0; l < CLS_MAX_LABELS; ++l) {
-    if (l < NL) {
-      const float s = warp_sum(acc[l]);
-      if (lane == 0) logits[(b * NL + l) * pix_per_sample + pix] = s + bc[l];
+    for (int l = 0; l < CLS_MAX_LABELS; ++l) acc[l] = 0.f;
+    for (int ch = lane; ch < nchunk; ch += 32) {
+      const int c = ch * 8;
+      const uint4 u = *reinterpret_cast<const uint4*>(x + row * C + c);
+      const uint32_t* up = reinterpret_cast<const uint32_t*>(&u);
+      float y[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 v = unpack_bf16x2(up[k]);
+        y[2 * k] = fmaxf(fmaf(v.x, sa[c + 2 * k], sb[c + 2 * k]), 0.f);
+        y[2 * k + 1] = fmaxf(fmaf(v.y, sa[c + 2 * k + 1], sb[c + 2 * k + 1]), 0.f);
+      }
+      if (drop_p > 0.f) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          y[k] = hash_uniform(seed, (unsigned long long)row * C + c + k) >= drop_p ? y[k] * keep_scale : 0.f;
+      }
+#pragma unroll
+      for (int l = 0; l < CLS_MAX_LABELS; ++l) {
+        if (l < NL) {
+          const float* wl = sw + l * C + c;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[l] = fmaf(y[k], wl[k], acc[l]);
+        }
+      }
+    }
+    const long long b = row / pix_per_sample, pix = row % pix_per_sample;
+#pragma unroll
+    for (int l = 0; l < CLS_MAX_LABELS; ++l) {
+      if (l < NL) {
+        const float sres = warp_sum(acc[l]);
+        if (lane == 0) logits[(b * NL + l) * pix_per_sample + pix] = sres + bc[l];
+      }
     }
   }
 }
@@ -310,87 +341,199 @@ int bn_relu_cls_fwd(const void* x, const float* mean, const float* rstd, const f
                     const float* bc, float* logits, long long M, int C, int NL, int pix_per_sample, float drop_p,
                     unsigned long long seed, cudaStream_t stream) {
   SFK_REQUIRE(NL >= 1 && NL <= CLS_MAX_LABELS, "bn_relu_cls: num_labels=%d unsupported (1..%d)", NL, CLS_MAX_LABELS);
-  SFK_REQUIRE(C % 2 == 0, "bn_relu_cls: C must be even");
+  SFK_REQUIRE(C % 8 == 0, "bn_relu_cls: C must be a multiple of 8");
   if (M == 0) return 0;
-  launch_k(bn_relu_cls_fwd_kernel<0>, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, stream, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, wc, bc,
-                                                                         logits, M, C, NL, pix_per_sample, drop_p, seed);
+  const size_t smem = (size_t)(2 + NL) * C * sizeof(float);
+  SFK_REQUIRE(smem <= 48 * 1024, "bn_relu_cls: C*(2+NL) too large for shared memory");
+  int rpb = 64;
+  long long grid = (M + rpb - 1) / rpb;
+  const long long max_grid = (long long)num_sms() * 8;
+  if (grid > max_grid) {
+    rpb = (int)((M + max_grid - 1) / max_grid);
+    rpb = (rpb + 7) / 8 * 8;
+    grid = (M + rpb - 1) / rpb;
+  }
+  launch_k(bn_relu_cls_fwd_kernel<0>, dim3((unsigned)grid), dim3(256), smem, stream, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, wc,
+           bc, logits, M, C, NL, pix_per_sample, drop_p, seed, rpb);
   return check_launch("bn_relu_cls_fwd_kernel");
 }
 
-// Backward pass A (one warp per row, block-level column reduction):
-//   dyb[c] = (sum_l dlogit[l] * Wc[l,c]) * dropmask * [bn(x) > 0]      (gradient at the BN output)
-//   sums[0][c] += dyb[c] ; sums[1][c] += dyb[c] * xhat[c]               (-> dbeta, dgamma, BN dx terms)
-//   dwc[l][c] += dlogit[l] * y[c] ; dbc[l] += dlogit[l]
-// Backward pass B recomputes dyb and writes dx = gamma*rstd*(dyb - sums0/M - xhat*sums1/M)  (train) or gamma*rstd*dyb (eval)
-template <int PASS>
-__global__ void __launch_bounds__(256) bn_relu_cls_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
-                                                              const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, const float* __restrict__ wc,
-                                                              const float* __restrict__ dlogits, float* __restrict__ sums,
-                                                              float* __restrict__ dwc, float* __restrict__ dbc,
-                                                              __nv_bfloat16* __restrict__ dx, long long M, int C, int NL,
-                                                              int pix_per_sample, float drop_p, unsigned long long seed,
-                                                              int train_stats, int rows_per_block) {
+// Backward of BN(+batch statistics) -> ReLU -> Dropout -> classifier, two streaming passes over x [M, C] (bf16):
+//   pass A: dyb[c] = (sum_l dlogit[l] * Wc[l,c]) * dropmask * [bn(x) > 0]     (gradient at the BN output)
+//           sums[0][c] += dyb ; sums[1][c] += dyb * xhat ; dwc[l][c] += dlogit[l] * y[c] ; dbc[l] += dlogit[l]
+//           (per-lane register partials over all rows of the block -> shared-memory block reduce -> slotted commit)
+//   pass B: dx = gamma*rstd*(dyb - sums0/M - xhat*sums1/M)  (batch stats)   or   gamma*rstd*dyb  (running stats)
+// Each lane owns the same 8-channel chunks for every row, so per-channel constants live in shared memory / registers.
+static constexpr int CLS_CHUNKS = 4;  // 8-channel chunks per lane -> C <= 1024
+
+template <int LG>  // labels whose dWc partials are kept in registers by this launch
+__global__ void __launch_bounds__(256) bn_relu_cls_bwd_a_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, const float* __restrict__ wc,
+                                                                const float* __restrict__ dlogits, float* __restrict__ sums,
+                                                                float* __restrict__ dwc, float* __restrict__ dbc, long long M, int C,
+                                                                int NL, int l0, int pix_per_sample, float drop_p,
+                                                                unsigned long long seed, int rows_per_block, int do_stats, int ns) {
   pdl_sync();
-  extern __shared__ float sh[];  // PASS 0: [2 + NL][C] block accumulators
+  extern __shared__ __align__(16) float shf[];  // mean[C], rstd[C], a[C], b[C], wc[NL][C]; later reused for the block reduce
+  float* smean = shf;
+  float* srstd = shf + C;
+  float* sa = shf + 2 * C;
+  float* sb = shf + 3 * C;
+  float* sw = shf + 4 * C;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const float r = rstd[c], a = r * gamma[c];
+    smean[c] = mean[c]; srstd[c] = r; sa[c] = a; sb[c] = beta[c] - mean[c] * a;
+  }
+  for (int i = threadIdx.x; i < NL * C; i += 256) sw[i] = wc[i];
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  if (PASS == 0) {
-    for (int i = threadIdx.x; i < (2 + NL) * C; i += 256) sh[i] = 0.f;
-    __syncthreads();
-  }
-  const float invM = 1.f / (float)M;
-  const long long row0 = (long long)blockIdx.x * rows_per_block;
-  float dbc_acc[CLS_MAX_LABELS];
+  const int nchunk = C >> 3;
+  float a0[CLS_CHUNKS][8], a1[CLS_CHUNKS][8], aw[LG][CLS_CHUNKS][8], adb[LG];
 #pragma unroll
-  for (int l = 0; l < CLS_MAX_LABELS; ++l) dbc_acc[l] = 0.f;
+  for (int k = 0; k < CLS_CHUNKS; ++k)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a0[k][j] = 0.f; a1[k][j] = 0.f;
+#pragma unroll
+      for (int l = 0; l < LG; ++l) aw[l][k][j] = 0.f;
+    }
+#pragma unroll
+  for (int l = 0; l < LG; ++l) adb[l] = 0.f;
+  const long long row0 = (long long)blockIdx.x * rows_per_block;
   for (int i = warp; i < rows_per_block; i += 8) {
     const long long row = row0 + i;
     if (row >= M) break;
     const long long b = row / pix_per_sample, pix = row % pix_per_sample;
     float dl[CLS_MAX_LABELS];
 #pragma unroll
-    for (int l = 0; l < CLS_MAX_LABELS; ++l) {
-      dl[l] = l < NL ? dlogits[(b * NL + l) * pix_per_sample + pix] : 0.f;
-      dbc_acc[l] += dl[l];
-    }
-    for (int c = lane * 2; c < C; c += 64) {
-      const float2 v = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + row * C + c));
-      float xh[2] = {(v.x - mean[c]) * rstd[c], (v.y - mean[c + 1]) * rstd[c + 1]};
-      float o[2];
+    for (int l = 0; l < CLS_MAX_LABELS; ++l) dl[l] = l < NL ? dlogits[(b * NL + l) * pix_per_sample + pix] : 0.f;
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const float bn = xh[k] * gamma[c + k] + beta[c + k];
+    for (int l = 0; l < LG; ++l)
+      if (l0 + l < NL) adb[l] += dl[l0 + l];
+#pragma unroll
+    for (int k = 0; k < CLS_CHUNKS; ++k) {
+      const int ch = lane + 32 * k;
+      if (ch >= nchunk) break;
+      const int c = ch * 8;
+      const uint4 u = *reinterpret_cast<const uint4*>(x + row * C + c);
+      const uint32_t* up = reinterpret_cast<const uint32_t*>(&u);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 v2 = unpack_bf16x2(up[j >> 1]);
+        const float xv = (j & 1) ? v2.y : v2.x;
+        const float bn = fmaf(xv, sa[c + j], sb[c + j]);
         float m = bn > 0.f ? 1.f : 0.f;
-        if (drop_p > 0.f) m *= hash_uniform(seed, (unsigned long long)row * C + c + k) >= drop_p ? keep_scale : 0.f;
+        if (drop_p > 0.f) m *= hash_uniform(seed, (unsigned long long)row * C + c + j) >= drop_p ? keep_scale : 0.f;
         float dy = 0.f;
 #pragma unroll
         for (int l = 0; l < CLS_MAX_LABELS; ++l)
-          if (l < NL) dy = fmaf(dl[l], wc[l * C + c + k], dy);
+          if (l < NL) dy = fmaf(dl[l], sw[l * C + c + j], dy);
         const float dyb = dy * m;
-        if (PASS == 0) {
-          atomicAdd(&sh[c + k], dyb);
-          atomicAdd(&sh[C + c + k], dyb * xh[k]);
-          const float yv = fmaxf(bn, 0.f) * (drop_p > 0.f ? (m > 0.f ? keep_scale : 0.f) : 1.f);
+        const float xh = (xv - smean[c + j]) * srstd[c + j];
+        a0[k][j] += dyb;
+        a1[k][j] = fmaf(dyb, xh, a1[k][j]);
+        const float yv = bn * m;  // relu(bn) * dropout multiplier (m already carries both)
 #pragma unroll
-          for (int l = 0; l < CLS_MAX_LABELS; ++l)
-            if (l < NL) atomicAdd(&sh[(2 + l) * C + c + k], dl[l] * yv);
-        } else {
-          float g = gamma[c + k] * rstd[c + k];
-          o[k] = train_stats ? g * (dyb - sums[c + k] * invM - xh[k] * sums[C + c + k] * invM) : g * dyb;
-        }
+        for (int l = 0; l < LG; ++l)
+          if (l0 + l < NL) aw[l][k][j] = fmaf(dl[l0 + l], yv, aw[l][k][j]);
       }
-      if (PASS == 1) *reinterpret_cast<uint32_t*>(dx + row * C + c) = pack_bf16x2(o[0], o[1]);
     }
   }
-  if (PASS == 0) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += 256) atomicAdd(sums + i, sh[i]);
-    for (int i = threadIdx.x; i < NL * C; i += 256) atomicAdd(dwc + i, sh[2 * C + i]);
-    if (lane == 0) {
+  // block reduce: virtual columns v = arr * C + c, arr in {0: sums0, 1: sums1, 2..2+LG: dwc rows}
+  __syncthreads();
+  const int V = (2 + LG) * C;
+  float* red = shf;  // needs V floats <= (4 + NL) * C
+  for (int i = threadIdx.x; i < V; i += 256) red[i] = 0.f;
+  __syncthreads();
 #pragma unroll
-      for (int l = 0; l < CLS_MAX_LABELS; ++l)
-        if (l < NL) atomicAdd(dbc + l, dbc_acc[l]);
+  for (int k = 0; k < CLS_CHUNKS; ++k) {
+    const int ch = lane + 32 * k;
+    if (ch >= nchunk) break;
+    const int c = ch * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&red[c + j], a0[k][j]);
+      atomicAdd(&red[C + c + j], a1[k][j]);
+#pragma unroll
+      for (int l = 0; l < LG; ++l) atomicAdd(&red[(2 + l) * C + c + j], aw[l][k][j]);
+    }
+  }
+  __syncthreads();
+  colsum_commit(red, 0, V, V, ns, blockIdx.x, gridDim.x, 0, [&](int v, float sum) {
+    const int arr = v / C, c = v % C;
+    if (arr == 0) { if (do_stats) sums[c] += sum; }
+    else if (arr == 1) { if (do_stats) sums[C + c] += sum; }
+    else if (l0 + arr - 2 < NL) dwc[(l0 + arr - 2) * C + c] += sum;
+  });
+  if (lane == 0) {
+#pragma unroll
+    for (int l = 0; l < LG; ++l)
+      if (l0 + l < NL) atomicAdd(dbc + l0 + l, adb[l]);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_relu_cls_bwd_b_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, const float* __restrict__ wc,
+                                                                const float* __restrict__ dlogits, const float* __restrict__ sums,
+                                                                __nv_bfloat16* __restrict__ dx, long long M, int C, int NL,
+                                                                int pix_per_sample, float drop_p, unsigned long long seed,
+                                                                int train_stats, int rows_per_block) {
+  pdl_sync();
+  extern __shared__ __align__(16) float shf[];  // mean, rstd, a, b, g (=gamma*rstd), k0, k1, wc[NL][C]
+  float* smean = shf;
+  float* srstd = shf + C;
+  float* sa = shf + 2 * C;
+  float* sb = shf + 3 * C;
+  float* sk0 = shf + 4 * C;
+  float* sk1 = shf + 5 * C;
+  float* sw = shf + 6 * C;
+  const float invM = 1.f / (float)M;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const float r = rstd[c], a = r * gamma[c];
+    smean[c] = mean[c]; srstd[c] = r; sa[c] = a; sb[c] = beta[c] - mean[c] * a;
+    sk0[c] = train_stats ? sums[c] * invM : 0.f;
+    sk1[c] = train_stats ? sums[C + c] * invM : 0.f;
+  }
+  for (int i = threadIdx.x; i < NL * C; i += 256) sw[i] = wc[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const int nchunk = C >> 3;
+  const long long row0 = (long long)blockIdx.x * rows_per_block;
+  for (int i = warp; i < rows_per_block; i += 8) {
+    const long long row = row0 + i;
+    if (row >= M) break;
+    const long long b = row / pix_per_sample, pix = row % pix_per_sample;
+    float dl[CLS_MAX_LABELS];
+#pragma unroll
+    for (int l = 0; l < CLS_MAX_LABELS; ++l) dl[l] = l < NL ? dlogits[(b * NL + l) * pix_per_sample + pix] : 0.f;
+    for (int ch = lane; ch < nchunk; ch += 32) {
+      const int c = ch * 8;
+      const uint4 u = *reinterpret_cast<const uint4*>(x + row * C + c);
+      const uint32_t* up = reinterpret_cast<const uint32_t*>(&u);
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 v2 = unpack_bf16x2(up[j >> 1]);
+        const float xv = (j & 1) ? v2.y : v2.x;
+        const float bn = fmaf(xv, sa[c + j], sb[c + j]);
+        float m = bn > 0.f ? 1.f : 0.f;
+        if (drop_p > 0.f) m *= hash_uniform(seed, (unsigned long long)row * C + c + j) >= drop_p ? keep_scale : 0.f;
+        float dy = 0.f;
+#pragma unroll
+        for (int l = 0; l < CLS_MAX_LABELS; ++l)
+          if (l < NL) dy = fmaf(dl[l], sw[l * C + c + j], dy);
+        const float dyb = dy * m;
+        const float xh = (xv - smean[c + j]) * srstd[c + j];
+        o[j] = sa[c + j] * (dyb - sk0[c + j] - xh * sk1[c + j]);
+      }
+      uint4 w;
+      w.x = pack_bf16x2(o[0], o[1]); w.y = pack_bf16x2(o[2], o[3]);
+      w.z = pack_bf16x2(o[4], o[5]); w.w = pack_bf16x2(o[6], o[7]);
+      *reinterpret_cast<uint4*>(dx + row * C + c) = w;
     }
   }
 }
@@ -400,28 +543,41 @@ int bn_relu_cls_bwd(const void* x, const float* mean, const float* rstd, const f
                     const float* dlogits, float* sums, float* dwc, float* dbc, void* dx, long long M, int C, int NL,
                     int pix_per_sample, float drop_p, unsigned long long seed, int train_stats, cudaStream_t stream) {
   SFK_REQUIRE(NL >= 1 && NL <= CLS_MAX_LABELS, "bn_relu_cls_bwd: num_labels=%d unsupported", NL);
+  SFK_REQUIRE(C % 8 == 0 && C <= 256 * CLS_CHUNKS, "bn_relu_cls_bwd: C=%d unsupported (multiple of 8, <= %d)", C, 256 * CLS_CHUNKS);
   if (M == 0) return 0;
   cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)2 * C * sizeof(float), stream);
   SFK_REQUIRE(e == cudaSuccess, "bn_relu_cls_bwd: memset failed: %s", cudaGetErrorString(e));
-  int rpb = 64;
-  long long grid = (M + rpb - 1) / rpb;
-  const long long max_grid = (long long)num_sms() * 4;
-  if (grid > max_grid) {
-    rpb = (int)((M + max_grid - 1) / max_grid);
-    rpb = (rpb + 7) / 8 * 8;
-    grid = (M + rpb - 1) / rpb;
+  const long long max_grid = (long long)num_sms() * 2;   // few, long-lived blocks: register partials amortise the commit
+  int rpb = (int)((M + max_grid - 1) / max_grid);
+  rpb = (rpb + 7) / 8 * 8;
+  if (rpb < 8) rpb = 8;
+  const long long grid = (M + rpb - 1) / rpb;
+  const size_t smem_a = (size_t)(4 + NL) * C * sizeof(float);
+  const size_t smem_b = (size_t)(6 + NL) * C * sizeof(float);
+  SFK_REQUIRE(smem_b <= 48 * 1024, "bn_relu_cls_bwd: C*(6+NL) too large for shared memory");
+  for (int l0 = 0; l0 < NL; l0 += 4) {
+    const int lg = (NL - l0) >= 2 || l0 > 0 ? 4 : 1;
+    const int ns = colsum_num_slots((long long)(2 + lg) * C, grid);
+    if (lg == 1)
+      launch_k(bn_relu_cls_bwd_a_kernel<1>, dim3((unsigned)grid), dim3(256), smem_a, stream, (const __nv_bfloat16*)x, mean, rstd, gamma,
+               beta, wc, dlogits, sums, dwc, dbc, M, C, NL, l0, pix_per_sample, drop_p, seed, rpb, l0 == 0 ? 1 : 0, ns);
+    else
+      launch_k(bn_relu_cls_bwd_a_kernel<4>, dim3((unsigned)grid), dim3(256), smem_a, stream, (const __nv_bfloat16*)x, mean, rstd, gamma,
+               beta, wc, dlogits, sums, dwc, dbc, M, C, NL, l0, pix_per_sample, drop_p, seed, rpb, l0 == 0 ? 1 : 0, ns);
+    int rc = check_launch("bn_relu_cls_bwd_a_kernel");
+    if (rc) return rc;
   }
-  const size_t smem = (size_t)(2 + NL) * C * sizeof(float);
-  SFK_REQUIRE(smem <= 48 * 1024, "bn_relu_cls_bwd: C*(2+NL) too large for shared memory");
-  launch_k(bn_relu_cls_bwd_kernel<0>, dim3((unsigned)grid), dim3(256), smem, stream, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, wc, dlogits,
-                                                                   sums, dwc, dbc, nullptr, M, C, NL, pix_per_sample, drop_p,
-                                                                   seed, train_stats, rpb);
-  int rc = check_launch("bn_relu_cls_bwd_kernel<0>");
-  if (rc) return rc;
-  launch_k(bn_relu_cls_bwd_kernel<1>, dim3((unsigned)grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, wc, dlogits, sums,
-                                                                nullptr, nullptr, (__nv_bfloat16*)dx, M, C, NL, pix_per_sample,
-                                                                drop_p, seed, train_stats, rpb);
-  return check_launch("bn_relu_cls_bwd_kernel<1>");
+  int rpb_b = 64;
+  long long grid_b = (M + rpb_b - 1) / rpb_b;
+  const long long max_b = (long long)num_sms() * 8;
+  if (grid_b > max_b) {
+    rpb_b = (int)((M + max_b - 1) / max_b);
+    rpb_b = (rpb_b + 7) / 8 * 8;
+    grid_b = (M + rpb_b - 1) / rpb_b;
+  }
+  launch_k(bn_relu_cls_bwd_b_kernel, dim3((unsigned)grid_b), dim3(256), smem_b, stream, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, wc,
+           dlogits, (const float*)sums, (__nv_bfloat16*)dx, M, C, NL, pix_per_sample, drop_p, seed, train_stats, rpb_b);
+  return check_launch("bn_relu_cls_bwd_b_kernel");
 }
 
 }  // namespace sfk
