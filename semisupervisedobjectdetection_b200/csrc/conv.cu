@@ -42,6 +42,14 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
   return fmaf(x * 0.39894228040143267794f, e, 0.5f * (1.0f + er));
 }
 
+// 128-bit shared-memory read the compiler may not hoist out of the position loop (loop-invariant filter taps would
+// otherwise be promoted back into ~80 registers, which is exactly what keeping them in shared memory is meant to avoid)
+__device__ __forceinline__ float4 lds128_nohoist(const float* p) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+
 template <int VEC> struct VecIO;
 template <> struct VecIO<8> {
   typedef uint4 packed;
@@ -107,101 +115,101 @@ __device__ __forceinline__ void dw_block_commit(float (&acc)[NV][VEC], float* sh
 }
 
 // mode 0: y = gelu(conv(x) + bias)     mode 1: y = conv_flipped(x)  (input gradient of the conv); colsum (+)= sum_pixels y
-// The 9 x VEC filter taps of a lane live in shared memory ([tap][lane][VEC], conflict-free 128-bit reads) instead of 72
-// registers: the kernel is global-latency bound (ncu: long_scoreboard), so register count -> resident warps is what matters.
+// ncu (profiles/): the first versions were (a) latency bound — loads consumed one by one — then (b) issue bound — 64-bit
+// index division and per-(tap,output) re-unpacking.  This version: 8 channels x 2 pixels per thread, the 3x4 window is
+// loaded up front (12 independent 16-byte loads), every window vector is unpacked once and feeds all taps that see it,
+// filter taps / bias come from shared memory ([tap][lane][8], conflict-free 128-bit reads), 32-bit index arithmetic.
+static constexpr int DWF_SEG = 2;
+static constexpr int DWB_SEG = 2;
+
 template <int MODE>
 __global__ void __launch_bounds__(256, 2) dwconv3x3_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
                                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
                                                            float* __restrict__ colsum, int B, int H, int W, int C,
                                                            int pos_per_block, int ns) {
   pdl_sync();
-  constexpr int VEC = 4;
-  __shared__ __align__(16) float sw[9 * 32 * VEC];
+  constexpr int VEC = 8;
+  __shared__ __align__(16) float sw[10 * 32 * VEC];   // 9 taps + bias
   __shared__ float sh[32 * VEC];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cblk = blockIdx.x * 32 * VEC;
   const int c0 = cblk + lane * VEC;
   const bool lane_ok = c0 < C;
-  for (int i = threadIdx.x; i < 9 * 32 * VEC; i += 256) {
+  for (int i = threadIdx.x; i < 10 * 32 * VEC; i += 256) {
     const int k = i / (32 * VEC), j = i % (32 * VEC);
-    const int kk = MODE == 1 ? 8 - k : k;
-    sw[i] = (cblk + j < C) ? wt[(long long)kk * C + cblk + j] : 0.f;
+    float v = 0.f;
+    if (cblk + j < C) {
+      if (k < 9) v = wt[(MODE == 1 ? 8 - k : k) * C + cblk + j];
+      else if (MODE == 0) v = bias[cblk + j];
+    }
+    sw[i] = v;
   }
   __syncthreads();
-  const int nseg = (W + DW_SEG - 1) / DW_SEG;
-  const long long npos = (long long)B * H * nseg;
-  const long long p0 = (long long)blockIdx.y * pos_per_block;
-  long long p1 = p0 + pos_per_block;
+  const unsigned nseg = (unsigned)(W + DWF_SEG - 1) / DWF_SEG;
+  const unsigned npos = (unsigned)B * H * nseg;
+  const unsigned p0 = blockIdx.y * (unsigned)pos_per_block;
+  unsigned p1 = p0 + pos_per_block;
   if (p1 > npos) p1 = npos;
-  float bs[VEC];
   float csum[1][VEC];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) { bs[v] = 0.f; csum[0][v] = 0.f; }
+  for (int v = 0; v < VEC; ++v) csum[0][v] = 0.f;
   if (lane_ok) {
-    if (MODE == 0) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c0));
-      bs[0] = a.x; bs[1] = a.y; bs[2] = a.z; bs[3] = a.w;
-    }
     const float* swl = sw + lane * VEC;
-    for (long long pos = p0 + warp; pos < p1; pos += 8) {
-      const int seg = (int)(pos % nseg);
-      const long long t = pos / nseg;
-      const int yy = (int)(t % H);
-      const int b = (int)(t / H);
-      const int x0 = seg * DW_SEG;
-      // issue the whole 3 x (SEG+2) window first (18 independent 16-byte loads in flight), then do the math
-      typename VecIO<VEC>::packed win[3][DW_SEG + 2];
+    for (unsigned pos = p0 + warp; pos < p1; pos += 8) {
+      const unsigned seg = pos % nseg, t = pos / nseg;
+      const int yy = (int)(t % (unsigned)H), b = (int)(t / (unsigned)H);
+      const int x0 = (int)seg * DWF_SEG;
+      uint4 win[3][DWF_SEG + 2];
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         const int sy = yy + r - 1;
         const bool vy = sy >= 0 && sy < H;
+        const unsigned rowoff = ((unsigned)(b * H + sy) * W) * C + c0;
 #pragma unroll
-        for (int j = 0; j < DW_SEG + 2; ++j) {
+        for (int j = 0; j < DWF_SEG + 2; ++j) {
           const int sx = x0 + j - 1;
-          win[r][j] = (vy && sx >= 0 && sx < W) ? VecIO<VEC>::ldp(x + ((long long)(b * H + sy) * W + sx) * C + c0)
-                                                : VecIO<VEC>::zero();
+          win[r][j] = (vy && sx >= 0 && sx < W) ? *reinterpret_cast<const uint4*>(x + (size_t)(rowoff + (unsigned)sx * C))
+                                                : make_uint4(0, 0, 0, 0);
         }
       }
-      float acc[DW_SEG][VEC];
+      const unsigned outoff = ((unsigned)(b * H + yy) * W + x0) * C + c0;
+      // one output pixel at a time keeps the live state at {window, 8 accumulators}: no spills at 2-3 blocks / SM
 #pragma unroll
-      for (int o = 0; o < DW_SEG; ++o)
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[o][v] = bs[v];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-#pragma unroll
-        for (int tt = 0; tt < 3; ++tt) {
-          const float4 w0 = *reinterpret_cast<const float4*>(swl + (r * 3 + tt) * 32 * VEC);
-          const float wv[VEC] = {w0.x, w0.y, w0.z, w0.w};
-#pragma unroll
-          for (int o = 0; o < DW_SEG; ++o) {
-            float f[VEC];
-            VecIO<VEC>::unpack(win[r][o + tt], f);
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) acc[o][v] = fmaf(wv[v], f[v], acc[o][v]);
-          }
-        }
-      }
-#pragma unroll
-      for (int o = 0; o < DW_SEG; ++o) {
+      for (int o = 0; o < DWF_SEG; ++o) {
         if (x0 + o >= W) break;
+        float acc[VEC];
+        {
+          const float4 b0 = lds128_nohoist(swl + 9 * 32 * VEC);
+          const float4 b1 = lds128_nohoist(swl + 9 * 32 * VEC + 4);
+          acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const float4 w0 = lds128_nohoist(swl + k * 32 * VEC);
+          const float4 w1 = lds128_nohoist(swl + k * 32 * VEC + 4);
+          float f[VEC];
+          VecIO<VEC>::unpack(win[k / 3][o + k % 3], f);
+          acc[0] = fmaf(w0.x, f[0], acc[0]); acc[1] = fmaf(w0.y, f[1], acc[1]);
+          acc[2] = fmaf(w0.z, f[2], acc[2]); acc[3] = fmaf(w0.w, f[3], acc[3]);
+          acc[4] = fmaf(w1.x, f[4], acc[4]); acc[5] = fmaf(w1.y, f[5], acc[5]);
+          acc[6] = fmaf(w1.z, f[6], acc[6]); acc[7] = fmaf(w1.w, f[7], acc[7]);
+        }
         if (MODE == 0) {
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[o][v] = gelu_fast(acc[o][v]);
+          for (int v = 0; v < VEC; ++v) acc[v] = gelu_fast(acc[v]);
         } else {
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) csum[0][v] += acc[o][v];
+          for (int v = 0; v < VEC; ++v) csum[0][v] += acc[v];
         }
-        VecIO<VEC>::st(y + ((long long)(b * H + yy) * W + x0 + o) * C + c0, acc[o]);
+        VecIO<VEC>::st(y + (size_t)(outoff + (unsigned)o * C), acc);
       }
     }
   }
-  if (MODE == 1 && colsum != nullptr) {
-    dw_block_commit<VEC, 1>(csum, sh, nullptr, 0, colsum, c0, C, lane_ok, ns);
-  }
+  if (MODE == 1 && colsum != nullptr) dw_block_commit<VEC, 1>(csum, sh, nullptr, 0, colsum, c0, C, lane_ok, ns);
 }
 
 static void dw_grid(int C, int vec, long long npos, dim3& grid, int& ppb) {
+  // npos = number of (b, y, segment) positions; one warp handles 32 channel groups of one position
   const int gx = (C / vec + 31) / 32;
   long long gy = ((long long)num_sms() * 8 + gx - 1) / gx;   // ~8 blocks per SM in flight across the grid
   if (gy < 1) gy = 1;
@@ -216,16 +224,17 @@ static void dw_grid(int C, int vec, long long npos, dim3& grid, int& ppb) {
 int dwconv3x3(const void* x, const float* wt, const float* bias, void* y, float* colsum, int B, int H, int W, int C, int mode,
               cudaStream_t stream) {
   SFK_REQUIRE(C % 8 == 0, "dwconv3x3: C=%d must be a multiple of 8", C);
-  const long long npos = (long long)B * H * ((W + DW_SEG - 1) / DW_SEG);
+  SFK_REQUIRE((long long)B * H * W * C < (1LL << 31), "dwconv3x3: tensor too large for 32-bit offsets");
+  const long long npos = (long long)B * H * ((W + DWF_SEG - 1) / DWF_SEG);
   if (npos == 0) return 0;
   dim3 grid;
   int ppb;
-  dw_grid(C, 4, npos, grid, ppb);
+  dw_grid(C, 8, npos, grid, ppb);
   if (mode == 0)
     launch_k(dwconv3x3_kernel<0>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, bias, (__nv_bfloat16*)y, nullptr, B, H, W, C, ppb, 1);
   else
     launch_k(dwconv3x3_kernel<1>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, nullptr, (__nv_bfloat16*)y, colsum, B, H, W, C, ppb,
-             colsum_num_slots((long long)grid.x * 32 * 4, grid.y));
+             colsum_num_slots((long long)grid.x * 32 * 8, grid.y));
   return check_launch("dwconv3x3_kernel");
 }
 
@@ -249,10 +258,10 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_bwd_kernel(const __nv_b
     sh[i] = (cblk + j < C) ? wt[(long long)k * C + cblk + j] : 0.f;
   }
   __syncthreads();
-  const int nseg = (W + DW_SEG - 1) / DW_SEG;
-  const long long npos = (long long)B * H * nseg;
-  const long long p0 = (long long)blockIdx.y * pos_per_block;
-  long long p1 = p0 + pos_per_block;
+  const unsigned nseg = (unsigned)(W + DWB_SEG - 1) / DWB_SEG;
+  const unsigned npos = (unsigned)B * H * nseg;
+  const unsigned p0 = blockIdx.y * (unsigned)pos_per_block;
+  unsigned p1 = p0 + pos_per_block;
   if (p1 > npos) p1 = npos;
   float acc[10][VEC], bs[VEC];  // acc[0..8] = dW taps, acc[9] = dbias
 #pragma unroll
@@ -265,37 +274,36 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_bwd_kernel(const __nv_b
       bs[0] = a.x; bs[1] = a.y; bs[2] = a.z; bs[3] = a.w;
     }
     const float* swl = sh + lane * VEC;
-    for (long long pos = p0 + warp; pos < p1; pos += 8) {
-      const int seg = (int)(pos % nseg);
-      const long long t = pos / nseg;
-      const int yy = (int)(t % H);
-      const int b = (int)(t / H);
-      const int x0 = seg * DW_SEG;
-      VecIO<VEC>::packed win[3][DW_SEG + 2];
-      VecIO<VEC>::packed gin[DW_SEG];
+    for (unsigned pos = p0 + warp; pos < p1; pos += 8) {
+      const unsigned seg = pos % nseg, t = pos / nseg;
+      const int yy = (int)(t % (unsigned)H), b = (int)(t / (unsigned)H);
+      const int x0 = (int)seg * DWB_SEG;
+      VecIO<VEC>::packed win[3][DWB_SEG + 2];
+      VecIO<VEC>::packed gin[DWB_SEG];
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         const int sy = yy + r - 1;
         const bool vy = sy >= 0 && sy < H;
+        const unsigned rowoff = ((unsigned)(b * H + sy) * W) * C + c0;
 #pragma unroll
-        for (int j = 0; j < DW_SEG + 2; ++j) {
+        for (int j = 0; j < DWB_SEG + 2; ++j) {
           const int sx = x0 + j - 1;
-          win[r][j] = (vy && sx >= 0 && sx < W) ? VecIO<VEC>::ldp(x + ((long long)(b * H + sy) * W + sx) * C + c0)
-                                                : VecIO<VEC>::zero();
+          win[r][j] = (vy && sx >= 0 && sx < W) ? VecIO<VEC>::ldp(x + (size_t)(rowoff + (unsigned)sx * C)) : VecIO<VEC>::zero();
         }
       }
-      const long long off0 = ((long long)(b * H + yy) * W + x0) * C + c0;
+      const unsigned off0 = ((unsigned)(b * H + yy) * W + x0) * C + c0;
 #pragma unroll
-      for (int o = 0; o < DW_SEG; ++o) gin[o] = (x0 + o < W) ? VecIO<VEC>::ldp(dg + off0 + (long long)o * C) : VecIO<VEC>::zero();
+      for (int o = 0; o < DWB_SEG; ++o)
+        gin[o] = (x0 + o < W) ? VecIO<VEC>::ldp(dg + (size_t)(off0 + (unsigned)o * C)) : VecIO<VEC>::zero();
 #pragma unroll
-      for (int o = 0; o < DW_SEG; ++o) {
+      for (int o = 0; o < DWB_SEG; ++o) {
         if (x0 + o >= W) break;
         float pre[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) pre[v] = bs[v];
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
-          const float4 w4 = *reinterpret_cast<const float4*>(swl + k * 32 * VEC);
+          const float4 w4 = lds128_nohoist(swl + k * 32 * VEC);
           float f[VEC];
           VecIO<VEC>::unpack(win[k / 3][o + k % 3], f);
           pre[0] = fmaf(w4.x, f[0], pre[0]); pre[1] = fmaf(w4.y, f[1], pre[1]);
@@ -308,7 +316,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_bwd_kernel(const __nv_b
           d[v] = g[v] * gelu_grad_fast(pre[v]);
           acc[9][v] += d[v];
         }
-        VecIO<VEC>::st(dpre + off0 + (long long)o * C, d);
+        VecIO<VEC>::st(dpre + (size_t)(off0 + (unsigned)o * C), d);
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
           float f[VEC];
@@ -329,7 +337,8 @@ int dwconv3x3_gelu_bwd(const void* x, const float* wt, const float* bias, const 
                        float* dbias, int B, int H, int W, int C, cudaStream_t stream) {
   SFK_REQUIRE(C % 8 == 0, "dwconv3x3_gelu_bwd: C=%d must be a multiple of 8", C);
   SFK_REQUIRE((dwt == nullptr) == (dbias == nullptr), "dwconv3x3_gelu_bwd: pass both or neither of dwt / dbias");
-  const long long npos = (long long)B * H * ((W + DW_SEG - 1) / DW_SEG);
+  SFK_REQUIRE((long long)B * H * W * C < (1LL << 31), "dwconv3x3_gelu_bwd: tensor too large for 32-bit offsets");
+  const long long npos = (long long)B * H * ((W + DWB_SEG - 1) / DWB_SEG);
   if (npos == 0) return 0;
   dim3 grid;
   int ppb;

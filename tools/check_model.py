@@ -96,6 +96,7 @@ def run_golden():
         tol = {k: 5e-2 for k in res}
         if train:
             tol["grad_worst"] = 2e-1
+            tol["gradnorm_worst"] = 1e-1
         bad = {k: v for k, v in res.items() if v > tol[k]}
         print(f"{'OK ' if not bad else 'BAD'} {name}: " + " ".join(f"{k}={v:.2e}" for k, v in res.items()), flush=True)
         print(f"      worst grad {worst_k} | worst norm {worst_nk}", flush=True)
