@@ -45,6 +45,9 @@ int sfk_profile_gemm_end(double* total_ms, double* total_flops, long long* launc
 /* After sfk_profile_gemm_end: one CSV line per profiled GEMM launch (M,N,K,flags,microseconds). */
 int sfk_profile_gemm_dump(const char* path);
 
+/* Tuning switches: "gemm_cluster2" (default 0; measured neutral) = launch GEMMs as 2-CTA clusters that multicast the shared B tiles. */
+int sfk_set_option(const char* name, int value);
+
 /* ---- dense contractions (tcgen05 + TMA + TMEM) ------------------------------------------------------------
  * D[M,N] = alpha * (A · B^T) (+ bias[N]) (* row_scale[row / rows_per_scale]) (+ residual[M,N] f32) (relu)
  *   a: bf16.  a_mn == 0: stored [M, lda], K contiguous.   a_mn == 1: stored [K, lda], M contiguous.

@@ -1,11 +1,20 @@
 // extern "C" entry points of libsfk.so (declared in include/sfk.h). Thin argument marshalling only.
+#include <string>
 #include "common.cuh"
 #include "sfk_internal.h"
 #include "../../include/sfk.h"
 
 using namespace sfk;
 
+namespace sfk { extern int g_gemm_cluster2; }
+
 extern "C" {
+
+int sfk_set_option(const char* name, int value) {
+  if (name != nullptr && std::string(name) == "gemm_cluster2") { sfk::g_gemm_cluster2 = value ? 1 : 0; return 0; }
+  sfk::set_error("sfk_set_option: unknown option");
+  return -1;
+}
 
 int sfk_gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, int M, int N, int K,
                   float alpha, const float* bias, const float* residual, long long ldr, const float* row_scale,

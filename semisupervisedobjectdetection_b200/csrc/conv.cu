@@ -119,11 +119,11 @@ __device__ __forceinline__ void dw_block_commit(float (&acc)[NV][VEC], float* sh
 // index division and per-(tap,output) re-unpacking.  This version: 8 channels x 2 pixels per thread, the 3x4 window is
 // loaded up front (12 independent 16-byte loads), every window vector is unpacked once and feeds all taps that see it,
 // filter taps / bias come from shared memory ([tap][lane][8], conflict-free 128-bit reads), 32-bit index arithmetic.
-static constexpr int DWF_SEG = 2;
+static constexpr int DWF_SEG = 4;
 static constexpr int DWB_SEG = 2;
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 2) dwconv3x3_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
+__global__ void __launch_bounds__(256, 1) dwconv3x3_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
                                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
                                                            float* __restrict__ colsum, int B, int H, int W, int C,
                                                            int pos_per_block, int ns) {
@@ -173,35 +173,52 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_kernel(const __nv_bfloat16* 
         }
       }
       const unsigned outoff = ((unsigned)(b * H + yy) * W + x0) * C + c0;
-      // one output pixel at a time keeps the live state at {window, 8 accumulators}: no spills at 2-3 blocks / SM
+      // minimum-instruction order: every window vector is unpacked once and feeds the (up to 3) outputs that see it
+      float acc[DWF_SEG][VEC];
+      {
+        const float4 b0 = lds128_nohoist(swl + 9 * 32 * VEC);
+        const float4 b1 = lds128_nohoist(swl + 9 * 32 * VEC + 4);
+#pragma unroll
+        for (int o = 0; o < DWF_SEG; ++o) {
+          acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w;
+          acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        float wr[3][VEC];
+#pragma unroll
+        for (int tt = 0; tt < 3; ++tt) {
+          const float4 w0 = lds128_nohoist(swl + (r * 3 + tt) * 32 * VEC);
+          const float4 w1 = lds128_nohoist(swl + (r * 3 + tt) * 32 * VEC + 4);
+          wr[tt][0] = w0.x; wr[tt][1] = w0.y; wr[tt][2] = w0.z; wr[tt][3] = w0.w;
+          wr[tt][4] = w1.x; wr[tt][5] = w1.y; wr[tt][6] = w1.z; wr[tt][7] = w1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < DWF_SEG + 2; ++j) {
+          float f[VEC];
+          VecIO<VEC>::unpack(win[r][j], f);
+#pragma unroll
+          for (int tt = 0; tt < 3; ++tt) {
+            const int o = j - tt;
+            if (o >= 0 && o < DWF_SEG) {
+#pragma unroll
+              for (int v = 0; v < VEC; ++v) acc[o][v] = fmaf(wr[tt][v], f[v], acc[o][v]);
+            }
+          }
+        }
+      }
 #pragma unroll
       for (int o = 0; o < DWF_SEG; ++o) {
         if (x0 + o >= W) break;
-        float acc[VEC];
-        {
-          const float4 b0 = lds128_nohoist(swl + 9 * 32 * VEC);
-          const float4 b1 = lds128_nohoist(swl + 9 * 32 * VEC + 4);
-          acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
-        }
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          const float4 w0 = lds128_nohoist(swl + k * 32 * VEC);
-          const float4 w1 = lds128_nohoist(swl + k * 32 * VEC + 4);
-          float f[VEC];
-          VecIO<VEC>::unpack(win[k / 3][o + k % 3], f);
-          acc[0] = fmaf(w0.x, f[0], acc[0]); acc[1] = fmaf(w0.y, f[1], acc[1]);
-          acc[2] = fmaf(w0.z, f[2], acc[2]); acc[3] = fmaf(w0.w, f[3], acc[3]);
-          acc[4] = fmaf(w1.x, f[4], acc[4]); acc[5] = fmaf(w1.y, f[5], acc[5]);
-          acc[6] = fmaf(w1.z, f[6], acc[6]); acc[7] = fmaf(w1.w, f[7], acc[7]);
-        }
         if (MODE == 0) {
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[v] = gelu_fast(acc[v]);
+          for (int v = 0; v < VEC; ++v) acc[o][v] = gelu_fast(acc[o][v]);
         } else {
 #pragma unroll
-          for (int v = 0; v < VEC; ++v) csum[0][v] += acc[v];
+          for (int v = 0; v < VEC; ++v) csum[0][v] += acc[o][v];
         }
-        VecIO<VEC>::st(y + (size_t)(outoff + (unsigned)o * C), acc);
+        VecIO<VEC>::st(y + (size_t)(outoff + (unsigned)o * C), acc[o]);
       }
     }
   }

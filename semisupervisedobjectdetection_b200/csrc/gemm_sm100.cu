@@ -27,6 +27,9 @@ static constexpr int TMEM_COLS = 512;  // 2 accumulator buffers x 256 fp32 colum
 static constexpr int GEMM_THREADS = 192;
 static constexpr int MAX_STAGES = 8;
 
+// runtime switch (sfk_set_option("gemm_cluster2", 0|1)); measured neutral on B200 for this workload (profiles/), default off
+int g_gemm_cluster2 = 0;
+
 struct GemmKernelParams {
   int M, N, K;
   int block_n;
@@ -50,6 +53,7 @@ struct GemmKernelParams {
   int out_bf16;
   int atomic_add;
   int relu;
+  int cluster2;  // launched as 2-CTA clusters: the pair works on two adjacent row tiles and shares (multicasts) the B tiles
 };
 
 __device__ __forceinline__ long long gemm_map_row(long long row, const RowMap& m) {
@@ -90,7 +94,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, p.cluster2 ? 2 : 1);  // a multicast stage is free once BOTH CTAs' MMAs have retired it
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
@@ -107,22 +111,29 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   pdl_wait();
   tc_fence_before();
   __syncthreads();
+  if (p.cluster2) cluster_sync_all();  // peer barriers are initialised before any multicast / remote arrive targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
-  const int tiles_mn = p.m_tiles * p.n_tiles;
+  // work units: (row tile | row-tile pair, column tile, k split); in cluster mode the two CTAs of a pair walk the same
+  // unit sequence in lockstep, CTA rank r owning row tile 2*pair + r
+  const uint32_t crank = p.cluster2 ? cluster_ctarank() : 0u;
+  const int m_groups = p.cluster2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int tiles_mn = m_groups * p.n_tiles;
   const int total_units = tiles_mn * p.splits;
+  const int unit0 = p.cluster2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = p.cluster2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+      for (int unit = unit0; unit < total_units; unit += unit_stride) {
         const int split = unit % p.splits;
         const int tile = unit / p.splits;
         const int n_blk = tile % p.n_tiles;
-        const int m_blk = tile / p.n_tiles;
+        const int m_blk = p.cluster2 ? 2 * (tile / p.n_tiles) + (int)crank : tile / p.n_tiles;
         const int kb0 = (int)(((long long)split * p.k_blocks) / p.splits);
         const int kb1 = (int)(((long long)(split + 1) * p.k_blocks) / p.splits);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -138,11 +149,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             tma_load_2d(sa, &tmap_a, full, m_blk * BLOCK_M, kb * BLOCK_K);
             tma_load_2d(sa + 8192, &tmap_a, full, m_blk * BLOCK_M + 64, kb * BLOCK_K);
           }
-          if (!p.b_mn) {
-            tma_load_2d(sb, &tmap_b, full, kb * BLOCK_K, n_blk * p.block_n);
+          if (!p.cluster2) {
+            if (!p.b_mn) {
+              tma_load_2d(sb, &tmap_b, full, kb * BLOCK_K, n_blk * p.block_n);
+            } else {
+              for (int j = 0; j < p.block_n / 64; ++j)
+                tma_load_2d(sb + j * 8192, &tmap_b, full, n_blk * p.block_n + j * 64, kb * BLOCK_K);
+            }
           } else {
-            for (int j = 0; j < p.block_n / 64; ++j)
-              tma_load_2d(sb + j * 8192, &tmap_b, full, n_blk * p.block_n + j * 64, kb * BLOCK_K);
+            // each CTA fetches half of the B tile and multicasts it into both CTAs' stage (same offsets, own barriers)
+            if (!p.b_mn) {
+              const int half = p.block_n / 2;   // tmap_b box is [64, block_n / 2] rows in cluster mode
+              tma_load_2d_mc(sb + crank * half * 128, &tmap_b, full, kb * BLOCK_K, n_blk * p.block_n + (int)crank * half, 3);
+            } else {
+              for (int j = (int)crank; j < p.block_n / 64; j += 2)
+                tma_load_2d_mc(sb + j * 8192, &tmap_b, full, n_blk * p.block_n + j * 64, kb * BLOCK_K, 3);
+            }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -155,7 +177,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase[2] = {0, 0};
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+    for (int unit = unit0; unit < total_units; unit += unit_stride) {
       const int split = unit % p.splits;
       const int kb0 = (int)(((long long)split * p.k_blocks) / p.splits);
       const int kb1 = (int)(((long long)(split + 1) * p.k_blocks) / p.splits);
@@ -177,7 +199,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                           : umma_smem_desc(sb + kk * 32, 16, 1024);
             umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
-          umma_commit(bar_empty + 8 * stage);                  // smem slot reusable once these MMAs retire
+          if (p.cluster2) umma_commit_mc(bar_empty + 8 * stage, 3);  // tell both producers of the pair
+          else umma_commit(bar_empty + 8 * stage);              // smem slot reusable once these MMAs retire
           if (kb == kb1 - 1) umma_commit(bar_tfull + 8 * acc);  // accumulator complete
         }
         __syncwarp();
@@ -191,10 +214,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     int acc = 0;
     uint32_t acc_phase[2] = {0, 0};
-    for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+    for (int unit = unit0; unit < total_units; unit += unit_stride) {
       const int tile = unit / p.splits;
       const int n_blk = tile % p.n_tiles;
-      const int m_blk = tile / p.n_tiles;
+      const int m_blk = p.cluster2 ? 2 * (tile / p.n_tiles) + (int)crank : tile / p.n_tiles;
       mbar_wait(bar_tfull + 8 * acc, acc_phase[acc]);
       tc_fence_after();
       const long long row = (long long)m_blk * BLOCK_M + q * 32 + lane;
@@ -292,6 +315,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   tc_fence_before();
   __syncthreads();
+  if (p.cluster2) cluster_sync_all();  // the peer may still multicast into our smem / arrive on our barriers until it is done
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -301,14 +325,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
-static int pick_block_n(int N, int b_mn, int M) {
-  // candidates must be multiples of 32 (epilogue chunk) and of 64 when B is MN-major (64-wide TMA boxes)
+// Tile-width heuristic.  These GEMMs are mostly bound by the L2 -> shared-memory fill rate of one SM (small K, weights
+// re-read by every row tile), so per k-block time ~ bytes loaded ~ (BLOCK_M + bn) and the whole problem costs
+//   waves(bn) * (BLOCK_M + bn) * k_blocks + per-tile overhead.
+// Split-K (wgrad) launches fill the machine through `splits`, so they simply take the widest tile that does not waste
+// more than ~20 % of its columns on padding: wide tiles double the flop/byte of the operand stream.
+static int pick_block_n(int N, int b_mn, int M, int atomic_add) {
   const int cands_k[] = {256, 224, 192, 160, 128, 96, 64, 32};
   const int cands_mn[] = {256, 192, 128, 64};
   const int* cands = b_mn ? cands_mn : cands_k;
   const int nc = b_mn ? 4 : 8;
   const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
   const int sms = num_sms();
+  if (atomic_add) {
+    for (int i = 0; i < nc; ++i) {
+      const int bn = cands[i];
+      const int n_tiles = (N + bn - 1) / bn;
+      if ((double)n_tiles * bn <= 1.2 * N || i == nc - 1) return bn;
+    }
+  }
   int best = cands[nc - 1];
   double best_cost = 1e30;
   for (int i = 0; i < nc; ++i) {
@@ -316,8 +351,7 @@ static int pick_block_n(int N, int b_mn, int M) {
     const int n_tiles = (N + bn - 1) / bn;
     const long long tiles = (long long)m_tiles * n_tiles;
     const long long waves = (tiles + sms - 1) / sms;
-    // cost ~ waves * (MMA time of a tile ~ bn) with a fixed per-tile overhead (~48 columns worth)
-    const double cost = (double)waves * (bn + 48);
+    const double cost = (double)waves * (BLOCK_M + bn + 24);
     if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
   }
   return best;
@@ -342,7 +376,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.a_mn = g.a_mn ? 1 : 0;
   p.b_mn = g.b_mn ? 1 : 0;
-  p.block_n = g.block_n > 0 ? g.block_n : pick_block_n(g.N, p.b_mn, g.M);
+  p.block_n = g.block_n > 0 ? g.block_n : pick_block_n(g.N, p.b_mn, g.M, g.atomic_add);
   SFK_REQUIRE(p.block_n % 32 == 0 && p.block_n >= 32 && p.block_n <= MAX_BLOCK_N, "gemm: bad block_n %d", p.block_n);
   SFK_REQUIRE(!p.b_mn || p.block_n % 64 == 0, "gemm: MN-major B needs block_n %% 64 == 0");
   p.k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
@@ -354,9 +388,9 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     if (g.atomic_add) {
       const long long tiles = (long long)p.m_tiles * p.n_tiles;
       const int sms = num_sms();
-      if (tiles < sms) splits = (int)((2LL * sms + tiles - 1) / tiles);
-      // keep at least 4 k-blocks per split so the pipeline has something to overlap
-      const int max_splits = p.k_blocks >= 4 ? p.k_blocks / 4 : 1;
+      if (tiles < 2 * sms) splits = (int)((2LL * sms + tiles - 1) / tiles);
+      // keep at least 8 k-blocks per split so the pipeline has something to overlap
+      const int max_splits = p.k_blocks >= 8 ? p.k_blocks / 8 : 1;
       if (splits > max_splits) splits = max_splits;
     }
   }
@@ -383,13 +417,16 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.out_bf16 = g.out_bf16;
   p.atomic_add = g.atomic_add;
   p.relu = g.relu;
+  // 2-CTA clusters sharing B through TMA multicast: halves the dominant L2 -> smem stream of these small-K GEMMs
+  p.cluster2 = (g_gemm_cluster2 && p.m_tiles >= 2 && (num_sms() % 2 == 0)) ? 1 : 0;
 
   CUtensorMap ta, tb;
   int rc;
   if (!p.a_mn) rc = make_tmap_2d_bf16(&ta, g.a, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda * 2, BLOCK_K, BLOCK_M);
   else         rc = make_tmap_2d_bf16(&ta, g.a, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda * 2, 64, BLOCK_K);
   if (rc) return rc;
-  if (!p.b_mn) rc = make_tmap_2d_bf16(&tb, g.b, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb * 2, BLOCK_K, p.block_n);
+  if (!p.b_mn) rc = make_tmap_2d_bf16(&tb, g.b, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb * 2, BLOCK_K,
+                                      p.cluster2 ? p.block_n / 2 : p.block_n);
   else         rc = make_tmap_2d_bf16(&tb, g.b, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb * 2, 64, BLOCK_K);
   if (rc) return rc;
 
@@ -400,11 +437,35 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     SFK_REQUIRE(e == cudaSuccess, "gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const long long units = (long long)p.m_tiles * p.n_tiles * p.splits;
-  int grid = (int)(units < num_sms() ? units : num_sms());
+  const long long units = (long long)(p.cluster2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles * p.splits;
+  int grid;
+  if (p.cluster2) {
+    const long long clusters = units < num_sms() / 2 ? units : num_sms() / 2;
+    grid = (int)(2 * clusters);
+  } else {
+    grid = (int)(units < num_sms() ? units : num_sms());
+  }
   prof_gemm_shape(g.M, g.N, g.K, (g.a_mn ? 1 : 0) | (g.b_mn ? 2 : 0) | (g.atomic_add ? 4 : 0) | (p.splits << 8) | ((long long)p.block_n << 20));
   prof_gemm_begin(2.0 * (double)g.M * (double)g.N * (double)g.K, stream);
-  launch_k(gemm_bf16_tcgen05_kernel, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, p);
+  if (p.cluster2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    (void)cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel, ta, tb, p);
+  } else {
+    launch_k(gemm_bf16_tcgen05_kernel, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, p);
+  }
   prof_gemm_end(stream);
   return check_launch("gemm_bf16_tcgen05_kernel");
 }

@@ -36,6 +36,9 @@ def report(name, got, ref):
 
 def main():
     group = sys.argv[1]
+    if os.environ.get("SFK_GEMM_CLUSTER2") is not None:
+        L.check(L.load().sfk_set_option(b"gemm_cluster2", int(os.environ["SFK_GEMM_CLUSTER2"])))
+        print("gemm_cluster2 =", os.environ["SFK_GEMM_CLUSTER2"], flush=True)
     torch.manual_seed(0)
     dev = "cuda"
     allok = True
@@ -80,7 +83,8 @@ def main():
         out = gemm(a, b, M, N, K, bias=bias, relu=True, out_bf16=True)
         allok &= report("epilogue bias+relu bf16", out, torch.relu(a.float() @ b.float().t() + bias))
     elif group == "perf":
-        shapes = [("fuse 262144x768x3072", 262144, 768, 3072), ("ffn1_s3 16384x1280x320", 16384, 1280, 320),
+        shapes = [("q_s3 16384x320x320", 16384, 320, 320), ("kv_s3 4096x640x320", 4096, 640, 320),
+                  ("fuse 262144x768x3072", 262144, 768, 3072), ("ffn1_s3 16384x1280x320", 16384, 1280, 320),
                   ("ffn2_s3 16384x320x1280", 16384, 320, 1280), ("ffn1_s1 262144x256x64", 262144, 256, 64),
                   ("q_s1 262144x64x64", 262144, 64, 64), ("ffn1_s4 4096x2048x512", 4096, 2048, 512),
                   ("square 8192", 8192, 8192, 8192)]
