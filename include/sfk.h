@@ -141,9 +141,12 @@ size_t sfk_layer_saved_bytes(const sfk_layer_dims* dims);
 size_t sfk_layer_scratch_bytes(const sfk_layer_dims* dims);
 int sfk_layer_fwd(const sfk_layer_dims* dims, const sfk_layer_params* params, const float* x, const float* front, float* out,
                   float* front_out, void* saved, size_t saved_bytes, void* scratch, size_t scratch_bytes, sfk_stream_t stream);
+/* wgrad_stream (optional, may be NULL): second stream for the weight-gradient GEMMs, which are off the critical path.
+ * The caller must alternate `parity` (0/1) AND the scratch arena between consecutive calls, keep `saved` alive until the
+ * side stream has drained, and make its main stream wait for wgrad_stream before consuming the parameter gradients. */
 int sfk_layer_bwd(const sfk_layer_dims* dims, const sfk_layer_params* params, const sfk_layer_grads* grads, const float* x,
                   const float* dout, const float* dfront_out, float* dx, float* dfront, void* saved, size_t saved_bytes,
-                  void* scratch, size_t scratch_bytes, sfk_stream_t stream);
+                  void* scratch, size_t scratch_bytes, sfk_stream_t stream, sfk_stream_t wgrad_stream, int parity);
 
 /* ---- decode head (MS:752-782) ------------------------------------------------------------------------------ */
 /* out[b,y,x,ch_off:ch_off+C] = bilinear(in[b,:,:,0:C]) (align_corners=False), bf16 channels-last; and its transpose */

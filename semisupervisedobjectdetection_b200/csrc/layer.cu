@@ -113,6 +113,46 @@ RowMap kv_spatial_map(const Dims& d) {  // compact reduced row (b*Nkv + t) -> ro
   return m;
 }
 
+// Weight-gradient GEMMs are off the critical path of backward (nothing downstream in the layer consumes them), so they
+// can run on a second stream and fill the bubbles of the latency-bound dgrad chain.  fork(): side stream waits for what
+// the main stream has produced so far.  The caller alternates between two scratch arenas (parity) on consecutive calls;
+// a call first makes the main stream wait for the side work that last used its arena.
+struct SideCtx {
+  cudaStream_t main = nullptr, side = nullptr;
+  cudaEvent_t fork_ev[8] = {nullptr};
+  cudaEvent_t done_ev[2] = {nullptr, nullptr};
+  bool done_valid[2] = {false, false};
+  int next_fork = 0;
+};
+static SideCtx g_side;
+
+static int side_begin(cudaStream_t main, cudaStream_t side, int parity) {
+  if (side == nullptr) return 0;
+  if (g_side.done_ev[0] == nullptr) {
+    for (auto& e : g_side.fork_ev) SFK_REQUIRE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess, "event create failed");
+    for (auto& e : g_side.done_ev) SFK_REQUIRE(cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess, "event create failed");
+  }
+  g_side.main = main;
+  g_side.side = side;
+  if (g_side.done_valid[parity])  // side work of the call that last used this scratch arena must be finished
+    SFK_REQUIRE(cudaStreamWaitEvent(main, g_side.done_ev[parity], 0) == cudaSuccess, "stream wait failed");
+  return 0;
+}
+// returns the stream wgrad work should be enqueued on (side stream after a fork, else the main stream)
+static cudaStream_t side_fork(cudaStream_t main, cudaStream_t side) {
+  if (side == nullptr) return main;
+  cudaEvent_t e = g_side.fork_ev[g_side.next_fork];
+  g_side.next_fork = (g_side.next_fork + 1) & 7;
+  if (cudaEventRecord(e, main) != cudaSuccess || cudaStreamWaitEvent(side, e, 0) != cudaSuccess) return main;
+  return side;
+}
+static int side_end(cudaStream_t side, int parity) {
+  if (side == nullptr) return 0;
+  SFK_REQUIRE(cudaEventRecord(g_side.done_ev[parity], side) == cudaSuccess, "event record failed");
+  g_side.done_valid[parity] = true;
+  return 0;
+}
+
 #define TRY(expr)            \
   do {                       \
     int _rc = (expr);        \
@@ -246,9 +286,10 @@ int layer_forward(const sfk_layer_dims& dd, const sfk_layer_params& p, const flo
 // ------------------------------------------------------------------------------------------------
 int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sfk_layer_grads& gr, const float* x,
                    const float* dout, const float* dfront_out, float* dx, float* dfront, void* saved_buf, size_t saved_bytes,
-                   void* scratch_buf, size_t scratch_bytes, cudaStream_t st) {
+                   void* scratch_buf, size_t scratch_bytes, cudaStream_t st, cudaStream_t side, int parity) {
   const Dims d = make_dims(dd);
   TRY(check_dims(d));
+  TRY(side_begin(st, side, parity & 1));
   Arena sa(saved_buf, saved_bytes);
   Saved s = carve_saved(sa, d);
   SFK_REQUIRE(sa.off <= saved_bytes, "layer_backward: saved arena too small");
@@ -279,7 +320,7 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
   // drop-path backward + bf16 cast, fused with the dense2 bias gradient (column sums of dmlp)
   TRY(scale_cast_sum(dout, 0, id, dmlp, 1, id, p.drop_scale_mlp, (int)d.N, rows_sp, (int)C, gr.db2, nullptr, 0, st));
   TRY(gemm_bf16(linear_dgrad(dmlp, C, p.w2, Hd, rows_sp, C, Hd, dg, Hd, 1), st));
-  if (gr.dw2) TRY(gemm_bf16(linear_wgrad(dmlp, C, s.g, Hd, rows_sp, C, Hd, gr.dw2, Hd), st));
+  if (gr.dw2) TRY(gemm_bf16(linear_wgrad(dmlp, C, s.g, Hd, rows_sp, C, Hd, gr.dw2, Hd), side_fork(st, side)));
   {
     const bool want = gr.ddw != nullptr;
     if (want) {
@@ -294,7 +335,7 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
   // input gradient of the depthwise conv; the dense1 bias gradient (column sums of dh1) is produced by the same pass
   TRY(dwconv3x3(dpre, p.dw_wt, nullptr, dh1, gr.db1, (int)d.B, (int)d.H, (int)d.W, (int)Hd, 1, st));
   TRY(gemm_bf16(linear_dgrad(dh1, Hd, p.w1, C, rows_sp, Hd, C, dxn2, C, 1), st));
-  if (gr.dw1) TRY(gemm_bf16(linear_wgrad(dh1, Hd, s.xn2, C, rows_sp, Hd, C, gr.dw1, C), st));
+  if (gr.dw1) TRY(gemm_bf16(linear_wgrad(dh1, Hd, s.xn2, C, rows_sp, Hd, C, gr.dw1, C), side_fork(st, side)));
   // LN2 backward + residual gradient -> dx1 (spatial rows); front rows of dx1 come from the returned cls/prompt rows
   TRY(layernorm_bwd(dxn2, 1, s.x1, 0, spatial_map(d), s.mean2, s.rstd2, p.ln2_g, dout, id, dx1, 0, spatial_map(d), gr.dln2_g,
                     gr.dln2_b, rows_sp, (int)C, st));
@@ -311,7 +352,7 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
   // ---- attention branch ----
   TRY(scale_cast_sum(dx1, 0, id, da, 1, id, p.drop_scale_attn, (int)d.T, rows_all, (int)C, gr.dbo, nullptr, 0, st));
   TRY(gemm_bf16(linear_dgrad(da, C, p.wo, C, rows_all, C, C, dctx, C, 1), st));
-  if (gr.dwo) TRY(gemm_bf16(linear_wgrad(da, C, s.ctx, C, rows_all, C, C, gr.dwo, C), st));
+  if (gr.dwo) TRY(gemm_bf16(linear_wgrad(da, C, s.ctx, C, rows_all, C, C, gr.dwo, C), side_fork(st, side)));
   {
     cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)rows_all * C * sizeof(float), st);
     SFK_REQUIRE(e == cudaSuccess, "layer_backward: memset failed");
@@ -335,8 +376,11 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
       TRY(scale_cast(dkv32, 0, id, dkv16, 1, id, nullptr, 1, rows_kv, (int)(2 * C), st));
   }
   // K | V projections
-  if (gr.dwk) TRY(gemm_bf16(linear_wgrad(dkv16, 2 * C, s.kvn, C, rows_kv, C, C, gr.dwk, C), st));
-  if (gr.dwv) TRY(gemm_bf16(linear_wgrad(dkv16 + C, 2 * C, s.kvn, C, rows_kv, C, C, gr.dwv, C), st));
+  if (gr.dwk || gr.dwv) {
+    cudaStream_t ws = side_fork(st, side);
+    if (gr.dwk) TRY(gemm_bf16(linear_wgrad(dkv16, 2 * C, s.kvn, C, rows_kv, C, C, gr.dwk, C), ws));
+    if (gr.dwv) TRY(gemm_bf16(linear_wgrad(dkv16 + C, 2 * C, s.kvn, C, rows_kv, C, C, gr.dwv, C), ws));
+  }
   if ((gr.dbk == nullptr) != (gr.dbv == nullptr)) {  // only one of the two biases trainable: separate column sums
     if (gr.dbk) TRY(colsum(dkv16, 1, 2 * C, gr.dbk, rows_kv, (int)C, st));
     if (gr.dbv) TRY(colsum(dkv16 + C, 1, 2 * C, gr.dbv, rows_kv, (int)C, st));
@@ -363,11 +407,12 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
     TRY(gemm_bf16(linear_dgrad(dsr_sp, C, p.wsr, Ksr, rows_red, C, Ksr, dA, Ksr, 1), st));
     TRY(col2im_nhwc(dA, dxn1, (int)d.B, (int)d.H, (int)d.W, (int)C, (int)d.sr, (int)d.sr, 0, d.T, d.P, 0, st));
     if (gr.dwsr) {
-      cudaError_t e = cudaMemsetAsync(dwsr, 0, (size_t)C * Ksr * sizeof(float), st);
+      cudaStream_t ws = side_fork(st, side);  // dsr_sp is final here; patch gather + wgrad + layout fix all run off-path
+      cudaError_t e = cudaMemsetAsync(dwsr, 0, (size_t)C * Ksr * sizeof(float), ws);
       SFK_REQUIRE(e == cudaSuccess, "layer_backward: memset failed");
-      TRY(im2col_nhwc(s.xn1, A, (int)d.B, (int)d.H, (int)d.W, (int)C, (int)d.sr, (int)d.sr, 0, d.T, d.P, st));
-      TRY(gemm_bf16(linear_wgrad(dsr_sp, C, A, Ksr, rows_red, C, Ksr, dwsr, Ksr), st));
-      TRY(conv_wgrad_ohwi_to_oihw(dwsr, gr.dwsr, (int)C, (int)C, (int)d.sr, (int)d.sr, Ksr, st));
+      TRY(im2col_nhwc(s.xn1, A, (int)d.B, (int)d.H, (int)d.W, (int)C, (int)d.sr, (int)d.sr, 0, d.T, d.P, ws));
+      TRY(gemm_bf16(linear_wgrad(dsr_sp, C, A, Ksr, rows_red, C, Ksr, dwsr, Ksr), ws));
+      TRY(conv_wgrad_ohwi_to_oihw(dwsr, gr.dwsr, (int)C, (int)C, (int)d.sr, (int)d.sr, Ksr, ws));
     }
     if (gr.dbsr) TRY(colsum(dsr_sp, 1, C, gr.dbsr, rows_red, (int)C, st));
   } else {
@@ -379,7 +424,7 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
     g.residual = dxn1; g.ldr = C;
     TRY(gemm_bf16(g, st));
   }
-  if (gr.dwq) TRY(gemm_bf16(linear_wgrad(dq16, C, s.xn1, C, rows_all, C, C, gr.dwq, C), st));
+  if (gr.dwq) TRY(gemm_bf16(linear_wgrad(dq16, C, s.xn1, C, rows_all, C, C, gr.dwq, C), side_fork(st, side)));
   // LN1 backward + residual gradient
   if (d.P == 0) {
     TRY(layernorm_bwd(dxn1t, 1, xcat, 0, id, s.mean1, s.rstd1, p.ln1_g, dx1, id, dx, 0, id, gr.dln1_g, gr.dln1_b, rows_all, (int)C,
@@ -392,6 +437,7 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
     TRY(scale_cast(dxcat, 0, spatial_map(d), dx, 0, id, nullptr, 1, rows_sp, (int)C, st));
     if (dfront != nullptr) TRY(scale_cast(dxcat, 0, front_map(d.P, d.N), dfront, 0, id, nullptr, 1, d.B * d.P, (int)C, st));
   }
+  TRY(side_end(side, parity & 1));
   return 0;
 }
 
@@ -410,9 +456,9 @@ int sfk_layer_fwd(const sfk_layer_dims* dims, const sfk_layer_params* params, co
 
 int sfk_layer_bwd(const sfk_layer_dims* dims, const sfk_layer_params* params, const sfk_layer_grads* grads, const float* x,
                   const float* dout, const float* dfront_out, float* dx, float* dfront, void* saved, size_t saved_bytes,
-                  void* scratch, size_t scratch_bytes, sfk_stream_t stream) {
+                  void* scratch, size_t scratch_bytes, sfk_stream_t stream, sfk_stream_t wgrad_stream, int parity) {
   return sfk::layer_backward(*dims, *params, *grads, x, dout, dfront_out, dx, dfront, saved, saved_bytes, scratch, scratch_bytes,
-                             static_cast<cudaStream_t>(stream));
+                             static_cast<cudaStream_t>(stream), static_cast<cudaStream_t>(wgrad_stream), parity);
 }
 
 }  // extern "C"

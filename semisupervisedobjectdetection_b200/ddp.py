@@ -46,6 +46,8 @@ class GradBucketer:
         # NCCL averages in the collective itself; gloo (CPU tests) has no AVG, so sums are scaled in finish()
         op = dist.ReduceOp.AVG if self._nccl else dist.ReduceOp.SUM
         if self._side is not None:
+            from . import ops
+            ops.join_wgrad()  # weight gradients of this bucket may still be in flight on the wgrad stream
             self._side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._side):
                 w = dist.all_reduce(view, op=op, group=self.group, async_op=True)

@@ -182,6 +182,8 @@ class _PatchEmbedFn(torch.autograd.Function):
         gb = ops.grad_buffer(mod.proj.bias)
         if gb is not None:
             ops.colsum_into(dy, gb, M, C)
+        if is_image:
+            ops.join_wgrad()  # the image patch-embed is the last node of backward: gradients are complete after this point
         dx = None
         if (not is_image) and ctx.needs_input_grad[0]:
             dA = ops.gemm(dy, ctx.sh["w"], M, Kp, C, lda=C, ldb=Kp, b_mn=1, out_bf16=True)
@@ -363,13 +365,18 @@ class _LayerFn(torch.autograd.Function):
             dfront_out = ops._chk(dfront_out, torch.float32, "front grad")
         lib = ops.lib()
         scratch_bytes = lib.sfk_layer_scratch_bytes(ctypes.byref(dims))
-        scratch = ops.scratch(scratch_bytes, x.device)
+        # weight-gradient GEMMs go to a side stream; consecutive calls alternate between two scratch arenas (parity)
+        ws = ops.wgrad_stream(x.device)
+        parity = ops.next_bwd_parity()
+        scratch = ops.scratch(scratch_bytes, x.device, f"bwd{parity}")
         grads, gkeep = layer._grad_struct()
         dx = torch.empty_like(x)
         dfront = torch.empty(B, ptl, C, device=x.device, dtype=torch.float32) if ptl else None
         ops.call("sfk_layer_bwd", ctypes.byref(dims), ctypes.byref(params), ctypes.byref(grads), x.data_ptr(), dout.data_ptr(),
                  ops._p(dfront_out), dx.data_ptr(), ops._p(dfront), ctx.saved.data_ptr(), ctx.saved.numel(), scratch.data_ptr(),
-                 scratch.numel(), ops.stream())
+                 scratch.numel(), ops.stream(), None if ws is None else ws.cuda_stream, parity)
+        if ws is not None:
+            ctx.saved.record_stream(ws)  # the saved activations are still being read by the side-stream wgrad GEMMs
         ctx.saved = None
         return dx, dfront, None, None, None, None, None, None
 

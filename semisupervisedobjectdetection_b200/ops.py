@@ -39,13 +39,47 @@ def call(fn_name: str, *args) -> None:
 
 
 def scratch(nbytes: int, device: torch.device, slot: str = "main") -> torch.Tensor:
-    """Reusable byte arena (grows on demand). Safe because all libsfk work of a process is ordered on one stream."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), slot)
+    """Reusable byte arena (grows on demand); work enqueued on one stream is ordered, so reuse within a stream is safe."""
+    # one arena per (device, slot, stream): work on different streams may run concurrently (teacher || student forward)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), slot, stream())
     buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(int(nbytes * 1.25) + 4096, dtype=torch.uint8, device=device)
+        ws = wgrad_stream(device) if slot.startswith("bwd") else None
+        if ws is not None:
+            buf.record_stream(ws)  # side-stream GEMMs read this arena: the allocator must not recycle it under them
         _scratch[key] = buf
     return buf
+
+
+# ---- second stream for weight-gradient GEMMs (off the critical path of backward, see csrc/layer.cu) ----
+WGRAD_OVERLAP = True
+_wgrad_streams: dict = {}
+_bwd_parity = 0
+
+
+def wgrad_stream(device=None):
+    """torch.cuda.Stream used for weight-gradient GEMMs on `device` (None when the overlap is disabled)."""
+    if not WGRAD_OVERLAP:
+        return None
+    idx = torch.cuda.current_device() if device is None or device.index is None else device.index
+    st = _wgrad_streams.get(idx)
+    if st is None:
+        st = torch.cuda.Stream(device=idx)
+        _wgrad_streams[idx] = st
+    return st
+
+
+def join_wgrad() -> None:
+    """Make the current stream wait for every weight-gradient GEMM enqueued so far (before gradients are consumed)."""
+    for st in _wgrad_streams.values():
+        torch.cuda.current_stream().wait_stream(st)
+
+
+def next_bwd_parity() -> int:
+    global _bwd_parity
+    _bwd_parity ^= 1
+    return _bwd_parity
 
 
 def stream() -> int:

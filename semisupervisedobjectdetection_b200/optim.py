@@ -87,6 +87,7 @@ class FusedClipAdam(torch.optim.Optimizer):
 
     # --- gradient bookkeeping ---
     def zero_grad(self, set_to_none: bool = False):
+        ops.join_wgrad()
         self.flat_g.zero_()
         for p, o in zip(self._params, self._offsets):
             if p.grad is None or p.grad.data_ptr() != self.flat_g.data_ptr() + 4 * o:
@@ -111,6 +112,7 @@ class FusedClipAdam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def step(self, closure=None):
+        ops.join_wgrad()  # weight-gradient GEMMs run on a side stream
         ranges = self.live_ranges()
         if not ranges:
             return None  # reference: every .grad is None -> Adam touches nothing

@@ -95,8 +95,18 @@ def labeled_iteration(teacher, student, img, ground_truth, supervise_weight: flo
     return loss, teacher_loss_gt, student_loss, self_sup
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = str(device)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 def ema_teacher_student_step(teacher, student, img_labeled, ground_truth, img_unlabeled, supervise_weight: float = 0.8,
-                             ema_decay: float = 0.99, grad_sync=None):
+                             ema_decay: float = 0.99, grad_sync=None, overlap_teacher: bool = True):
     """North-star variant: EMA teacher forward on labeled + unlabeled tiles -> confidence-thresholded pseudo labels ->
     student forward/backward on both -> fused clip+Adam -> rank-local EMA teacher update.
     `grad_sync`: optional callable run between backward and the optimiser step (data-parallel all-reduce)."""
@@ -106,14 +116,25 @@ def ema_teacher_student_step(teacher, student, img_labeled, ground_truth, img_un
     gt = ground_truth.to(device=dev, dtype=torch.float32)
     imgs = torch.cat([img_l, img_u], dim=0)
     nl = img_l.shape[0]
-    with torch.no_grad():
-        t_probs = teacher.predict(imgs)
+    if overlap_teacher:
+        # the (gradient-free) teacher forward and the student forward are independent until the losses: run the teacher on a
+        # side stream so the two chains of small kernels fill each other's bubbles
+        main, side = torch.cuda.current_stream(), _side_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side), torch.no_grad():
+            t_probs = teacher.predict(imgs)
+        s_probs = student.predict(imgs)
+        main.wait_stream(side)
+        t_probs.record_stream(main)
+    else:
+        with torch.no_grad():
+            t_probs = teacher.predict(imgs)
+        s_probs = student.predict(imgs)
     t_l = denoise_teacher_probs(t_probs[:nl], gt)
     pseudo_l, _ = pseudo_label_stats(t_l, allow_throw_sample=False)
     pseudo_u, stats_u = pseudo_label_stats(t_probs[nl:].contiguous(), allow_throw_sample=True)
     keep_u = (stats_u[:, 4] > 0.5)
     # static shapes: rejected unlabeled tiles stay in the batch with an all-zero target and zero weight
-    s_probs = student.predict(imgs)
     sup = loss_func(s_probs[:nl], gt.to(torch.int64))
     self_l = loss_func(s_probs[:nl], pseudo_l)
     w_u = keep_u.float().mean()
