@@ -242,6 +242,9 @@ def run_sfk(args):
         torch.cuda.synchronize()
 
     lib = L.load()
+    for opt in ("gemm_occ2", "gemm_cluster2"):
+        if os.environ.get("SFK_" + opt.upper()) is not None:
+            lib.sfk_set_option(opt.encode(), int(os.environ["SFK_" + opt.upper()]))
     imgs_per_step = (N_LABELED + N_UNLABELED) * world
     # ---- resident-input throughput ----
     for _ in range(args.warmup):

@@ -48,6 +48,11 @@ int sfk_profile_gemm_dump(const char* path);
 /* Tuning switches: "gemm_cluster2" (default 0; measured neutral) = launch GEMMs as 2-CTA clusters that multicast the shared B tiles. */
 int sfk_set_option(const char* name, int value);
 
+/* Debug aid: device buffer (>= 8 x uint64) receiving CTA 0's globaltimer (ns) at the phase boundaries of each following
+ * GEMM launch: 0 start, 1 setup done, 2 first TMA issued, 3 first operands landed, 4 last MMA issued, 5 accumulator ready,
+ * 6 first tile stored, 7 CTA done.  NULL switches it off. */
+int sfk_debug_gemm_trace(void* device_u64x8);
+
 /* ---- dense contractions (tcgen05 + TMA + TMEM) ------------------------------------------------------------
  * D[M,N] = alpha * (A · B^T) (+ bias[N]) (* row_scale[row / rows_per_scale]) (+ residual[M,N] f32) (relu)
  *   a: bf16.  a_mn == 0: stored [M, lda], K contiguous.   a_mn == 1: stored [K, lda], M contiguous.

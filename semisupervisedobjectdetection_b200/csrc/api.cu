@@ -6,14 +6,21 @@
 
 using namespace sfk;
 
-namespace sfk { extern int g_gemm_cluster2; }
+namespace sfk { extern int g_gemm_cluster2; extern int g_gemm_occ2; extern unsigned long long* g_gemm_trace; }
 
 extern "C" {
 
 int sfk_set_option(const char* name, int value) {
   if (name != nullptr && std::string(name) == "gemm_cluster2") { sfk::g_gemm_cluster2 = value ? 1 : 0; return 0; }
+  if (name != nullptr && std::string(name) == "gemm_occ2") { sfk::g_gemm_occ2 = value ? 1 : 0; return 0; }
   sfk::set_error("sfk_set_option: unknown option");
   return -1;
+}
+
+/* debug: device buffer of >= 8 u64 receiving CTA 0's globaltimer at phase boundaries of every following GEMM (NULL = off) */
+int sfk_debug_gemm_trace(void* device_u64x8) {
+  sfk::g_gemm_trace = static_cast<unsigned long long*>(device_u64x8);
+  return 0;
 }
 
 int sfk_gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, int M, int N, int K,

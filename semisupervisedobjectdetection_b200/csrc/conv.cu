@@ -375,33 +375,33 @@ __global__ void __launch_bounds__(256) im2col_nhwc_kernel(const __nv_bfloat16* _
                                                           int B, int H, int W, int C, int K, int S, int P, int Ho, int Wo,
                                                           long long tok_stride, long long tok_offset) {
   pdl_sync();
-  const int C8 = C >> 3;
-  const long long total = (long long)B * Ho * Wo * K * K * C8;
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= total) return;
-  const int c8 = (int)(idx % C8);
-  long long t = idx / C8;
-  const int tap = (int)(t % (K * K));
-  const long long m = t / (K * K);
-  const int ox = (int)(m % Wo);
-  const int oy = (int)((m / Wo) % Ho);
-  const long long b = m / ((long long)Wo * Ho);
-  const int ky = tap / K, kx = tap % K;
-  const int sy = oy * S + ky - P, sx = ox * S + kx - P;
-  uint4 v = make_uint4(0, 0, 0, 0);
-  if (sy >= 0 && sy < H && sx >= 0 && sx < W)
-    v = *reinterpret_cast<const uint4*>(x + (b * tok_stride + tok_offset + (long long)sy * W + sx) * C + c8 * 8);
-  *reinterpret_cast<uint4*>(A + idx * 8) = v;
+  // one block per output row (b, oy); threads walk (ox, tap, 8-channel chunk) with 32-bit arithmetic
+  const int C8 = C >> 3, KK = K * K;
+  const int oy = blockIdx.x % Ho;
+  const int b = blockIdx.x / Ho;
+  const int per_pix = KK * C8;
+  const int n = Wo * per_pix;
+  const __nv_bfloat16* xb = x + ((size_t)b * tok_stride + tok_offset) * C;
+  __nv_bfloat16* Ab = A + ((size_t)b * Ho + oy) * Wo * (size_t)per_pix * 8;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int ox = i / per_pix, r = i - ox * per_pix;
+    const int tap = r / C8, c8 = r - tap * C8;
+    const int ky = tap / K, kx = tap - ky * K;
+    const int sy = oy * S + ky - P, sx = ox * S + kx - P;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (sy >= 0 && sy < H && sx >= 0 && sx < W) v = *reinterpret_cast<const uint4*>(xb + ((size_t)sy * W + sx) * C + c8 * 8);
+    *reinterpret_cast<uint4*>(Ab + (size_t)i * 8) = v;
+  }
 }
 
 int im2col_nhwc(const void* x, void* A, int B, int H, int W, int C, int K, int S, int P, long long tok_stride,
                 long long tok_offset, cudaStream_t stream) {
   SFK_REQUIRE(C % 8 == 0, "im2col_nhwc: C=%d must be a multiple of 8", C);
   const int Ho = (H + 2 * P - K) / S + 1, Wo = (W + 2 * P - K) / S + 1;
-  const long long total = (long long)B * Ho * Wo * K * K * (C / 8);
-  if (total == 0) return 0;
-  launch_k(im2col_nhwc_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)A, B, H, W,
-                                                                          C, K, S, P, Ho, Wo, tok_stride, tok_offset);
+  if ((long long)B * Ho * Wo == 0) return 0;
+  SFK_REQUIRE((long long)Wo * K * K * (C / 8) < (1LL << 31), "im2col_nhwc: row too large");
+  launch_k(im2col_nhwc_kernel, dim3((unsigned)(B * Ho)), dim3(256), 0, stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)A, B, H, W, C, K, S,
+           P, Ho, Wo, tok_stride, tok_offset);
   return check_launch("im2col_nhwc_kernel");
 }
 
@@ -444,44 +444,43 @@ __global__ void __launch_bounds__(256) col2im_nhwc_kernel(const __nv_bfloat16* _
                                                           int H, int W, int C, int K, int S, int P, int Ho, int Wo,
                                                           long long tok_stride, long long tok_offset, int accumulate) {
   pdl_sync();
-  const int C4 = C >> 2;
-  const long long total = (long long)B * H * W * C4;
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= total) return;
-  const int c4 = (int)(idx % C4);
-  long long t = idx / C4;
-  const int sx = (int)(t % W);
-  const int sy = (int)((t / W) % H);
-  const long long b = t / ((long long)W * H);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int ky = (sy + P) % S; ky < K; ky += S) {
-    const int oy = (sy + P - ky) / S;
-    if (sy + P - ky < 0 || oy >= Ho) continue;
-    for (int kx = (sx + P) % S; kx < K; kx += S) {
-      const int ox = (sx + P - kx) / S;
-      if (sx + P - kx < 0 || ox >= Wo) continue;
-      const long long m = (b * Ho + oy) * Wo + ox;
-      const uint2 u = *reinterpret_cast<const uint2*>(dA + (m * K * K + ky * K + kx) * C + c4 * 4);
-      const float2 a = unpack_bf16x2(u.x), bq = unpack_bf16x2(u.y);
-      acc.x += a.x; acc.y += a.y; acc.z += bq.x; acc.w += bq.y;
+  // one block per input row (b, sy); threads walk (sx, 4-channel chunk) with 32-bit arithmetic
+  const int C4 = C >> 2, KK = K * K;
+  const int sy = blockIdx.x % H;
+  const int b = blockIdx.x / H;
+  const int n = W * C4;
+  float* drow = dx + ((size_t)b * tok_stride + tok_offset + (size_t)sy * W) * C;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int sx = i / C4, c4 = i - sx * C4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ky = (sy + P) % S; ky < K; ky += S) {
+      const int oy = (sy + P - ky) / S;
+      if (sy + P - ky < 0 || oy >= Ho) continue;
+      for (int kx = (sx + P) % S; kx < K; kx += S) {
+        const int ox = (sx + P - kx) / S;
+        if (sx + P - kx < 0 || ox >= Wo) continue;
+        const size_t m = ((size_t)b * Ho + oy) * Wo + ox;
+        const uint2 u = *reinterpret_cast<const uint2*>(dA + (m * KK + ky * K + kx) * C + c4 * 4);
+        const float2 a = unpack_bf16x2(u.x), bq = unpack_bf16x2(u.y);
+        acc.x += a.x; acc.y += a.y; acc.z += bq.x; acc.w += bq.y;
+      }
     }
+    float* dst = drow + (size_t)sx * C + c4 * 4;
+    if (accumulate) {
+      const float4 o = *reinterpret_cast<const float4*>(dst);
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    *reinterpret_cast<float4*>(dst) = acc;
   }
-  float* dst = dx + (b * tok_stride + tok_offset + (long long)sy * W + sx) * C + c4 * 4;
-  if (accumulate) {
-    const float4 o = *reinterpret_cast<const float4*>(dst);
-    acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
-  }
-  *reinterpret_cast<float4*>(dst) = acc;
 }
 
 int col2im_nhwc(const void* dA, float* dx, int B, int H, int W, int C, int K, int S, int P, long long tok_stride,
                 long long tok_offset, int accumulate, cudaStream_t stream) {
   SFK_REQUIRE(C % 4 == 0, "col2im_nhwc: C=%d must be a multiple of 4", C);
   const int Ho = (H + 2 * P - K) / S + 1, Wo = (W + 2 * P - K) / S + 1;
-  const long long total = (long long)B * H * W * (C / 4);
-  if (total == 0) return 0;
-  launch_k(col2im_nhwc_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, (const __nv_bfloat16*)dA, dx, B, H, W, C, K, S, P, Ho,
-                                                                          Wo, tok_stride, tok_offset, accumulate);
+  if ((long long)B * H * W == 0) return 0;
+  launch_k(col2im_nhwc_kernel, dim3((unsigned)(B * H)), dim3(256), 0, stream, (const __nv_bfloat16*)dA, dx, B, H, W, C, K, S, P, Ho, Wo,
+           tok_stride, tok_offset, accumulate);
   return check_launch("col2im_nhwc_kernel");
 }
 

@@ -21,47 +21,52 @@ __device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, 
 }
 
 // out[b, y, x, ch_off + c] = bilinear(in[b, :, :, c]);  in: bf16 [B,h,w,C], out: bf16 [B,H,W,ld_out]
+// One block per output row (b, y): the vertical taps are computed once per block, threads walk (x, 8-channel chunk) with
+// 32-bit index arithmetic (the first version spent most of its instructions on 64-bit div/mod per element).
 __global__ void __launch_bounds__(256) upsample_concat_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                               int B, int h, int w, int C, int H, int W, long long ld_out,
                                                               int ch_off) {
   pdl_sync();
   const int C8 = C >> 3;
-  const long long total = (long long)B * H * W * C8;
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= total) return;
-  const int c8 = (int)(idx % C8);
-  long long t = idx / C8;
-  const int x = (int)(t % W);
-  t /= W;
-  const int y = (int)(t % H);
-  const long long b = t / H;
-  __nv_bfloat16* op = out + ((b * H + y) * W + x) * ld_out + ch_off + c8 * 8;
-  if (h == H && w == W) {
-    *reinterpret_cast<uint4*>(op) = *reinterpret_cast<const uint4*>(in + ((b * h + y) * w + x) * C + c8 * 8);
-    return;
-  }
-  int y0, y1, x0, x1;
-  float ly, lx;
-  bilinear_src(y, (float)h / (float)H, h, y0, y1, ly);
-  bilinear_src(x, (float)w / (float)W, w, x0, x1, lx);
-  const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
-  const __nv_bfloat16* base = in + b * h * w * C + c8 * 8;
-  const uint4 a = *reinterpret_cast<const uint4*>(base + ((long long)y0 * w + x0) * C);
-  const uint4 bq = *reinterpret_cast<const uint4*>(base + ((long long)y0 * w + x1) * C);
-  const uint4 c = *reinterpret_cast<const uint4*>(base + ((long long)y1 * w + x0) * C);
-  const uint4 d = *reinterpret_cast<const uint4*>(base + ((long long)y1 * w + x1) * C);
-  const uint32_t* ap = reinterpret_cast<const uint32_t*>(&a);
-  const uint32_t* bp = reinterpret_cast<const uint32_t*>(&bq);
-  const uint32_t* cp = reinterpret_cast<const uint32_t*>(&c);
-  const uint32_t* dp = reinterpret_cast<const uint32_t*>(&d);
-  uint4 o;
-  uint32_t* o32 = reinterpret_cast<uint32_t*>(&o);
+  const int y = blockIdx.x % H;
+  const int b = blockIdx.x / H;
+  const bool ident = (h == H && w == W);
+  int y0 = y, y1 = y;
+  float ly = 0.f;
+  if (!ident) bilinear_src(y, (float)h / (float)H, h, y0, y1, ly);
+  const float sx = (float)w / (float)W;
+  const __nv_bfloat16* row0 = in + ((size_t)b * h + y0) * w * C;
+  const __nv_bfloat16* row1 = in + ((size_t)b * h + y1) * w * C;
+  __nv_bfloat16* orow = out + ((size_t)b * H + y) * W * ld_out + ch_off;
+  const int n = W * C8;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int x = i / C8, c8 = i - x * C8;
+    __nv_bfloat16* op = orow + (size_t)x * ld_out + c8 * 8;
+    if (ident) {
+      *reinterpret_cast<uint4*>(op) = *reinterpret_cast<const uint4*>(row0 + (size_t)x * C + c8 * 8);
+      continue;
+    }
+    int x0, x1;
+    float lx;
+    bilinear_src(x, sx, w, x0, x1, lx);
+    const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+    const uint4 a = *reinterpret_cast<const uint4*>(row0 + (size_t)x0 * C + c8 * 8);
+    const uint4 bq = *reinterpret_cast<const uint4*>(row0 + (size_t)x1 * C + c8 * 8);
+    const uint4 c = *reinterpret_cast<const uint4*>(row1 + (size_t)x0 * C + c8 * 8);
+    const uint4 d = *reinterpret_cast<const uint4*>(row1 + (size_t)x1 * C + c8 * 8);
+    const uint32_t* ap = reinterpret_cast<const uint32_t*>(&a);
+    const uint32_t* bp = reinterpret_cast<const uint32_t*>(&bq);
+    const uint32_t* cp = reinterpret_cast<const uint32_t*>(&c);
+    const uint32_t* dp = reinterpret_cast<const uint32_t*>(&d);
+    uint4 o;
+    uint32_t* o32 = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 fa = unpack_bf16x2(ap[i]), fb = unpack_bf16x2(bp[i]), fc = unpack_bf16x2(cp[i]), fd = unpack_bf16x2(dp[i]);
-    o32[i] = pack_bf16x2(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x, w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
+    for (int k = 0; k < 4; ++k) {
+      const float2 fa = unpack_bf16x2(ap[k]), fb = unpack_bf16x2(bp[k]), fc = unpack_bf16x2(cp[k]), fd = unpack_bf16x2(dp[k]);
+      o32[k] = pack_bf16x2(w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x, w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y);
+    }
+    *reinterpret_cast<uint4*>(op) = o;
   }
-  *reinterpret_cast<uint4*>(op) = o;
 }
 
 int upsample_concat(const void* in, void* out, int B, int h, int w, int C, int H, int W, long long ld_out, int ch_off,
@@ -69,52 +74,61 @@ int upsample_concat(const void* in, void* out, int B, int h, int w, int C, int H
   SFK_REQUIRE(C % 8 == 0 && ld_out % 8 == 0 && ch_off % 8 == 0, "upsample_concat: channel counts must be multiples of 8");
   const long long total = (long long)B * H * W * (C / 8);
   if (total == 0) return 0;
-  launch_k(upsample_concat_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, h, w,
-                                                                              C, H, W, ld_out, ch_off);
+  launch_k(upsample_concat_kernel, dim3((unsigned)(B * H)), dim3(256), 0, stream, (const __nv_bfloat16*)in, (__nv_bfloat16*)out, B, h, w, C,
+           H, W, ld_out, ch_off);
   return check_launch("upsample_concat_kernel");
 }
 
 // Transposed bilinear: din[b, yi, xi, c] = sum over hi-res (y, x) of weight(y,x -> yi,xi) * dout[b, y, x, ch_off + c].
-// Gather formulation: every low-res pixel scans the hi-res window that can reference it (no atomics, deterministic).
+// Gather formulation (no atomics, deterministic). One block per low-res row (b, yi): the contributing hi-res rows and their
+// vertical weights are found once per block (shared memory), threads walk (xi, 8-channel chunk) with 32-bit arithmetic.
 __global__ void __launch_bounds__(256) upsample_concat_bwd_kernel(const __nv_bfloat16* __restrict__ dout,
                                                                   __nv_bfloat16* __restrict__ din, int B, int h, int w, int C,
                                                                   int H, int W, long long ld_out, int ch_off) {
   pdl_sync();
+  __shared__ int s_rows[64];
+  __shared__ float s_wy[64];
+  __shared__ int s_nrows;
   const int C8 = C >> 3;
-  const long long total = (long long)B * h * w * C8;
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= total) return;
-  const int c8 = (int)(idx % C8);
-  long long t = idx / C8;
-  const int xi = (int)(t % w);
-  t /= w;
-  const int yi = (int)(t % h);
-  const long long b = t / h;
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  if (h == H && w == W) {
-    *reinterpret_cast<uint4*>(din + idx * 8) =
-        *reinterpret_cast<const uint4*>(dout + ((b * H + yi) * W + xi) * ld_out + ch_off + c8 * 8);
-    return;
+  const int yi = blockIdx.x % h;
+  const int b = blockIdx.x / h;
+  const bool ident = (h == H && w == W);
+  if (threadIdx.x == 0) {
+    int n = 0;
+    if (!ident) {
+      const float sy = (float)h / (float)H, fy = (float)H / (float)h;
+      int ylo = (int)floorf((yi - 1 + 0.5f) * fy - 0.5f) - 1, yhi = (int)ceilf((yi + 1 + 0.5f) * fy - 0.5f) + 1;
+      if (ylo < 0) ylo = 0;
+      if (yhi > H - 1) yhi = H - 1;
+      for (int y = ylo; y <= yhi && n < 64; ++y) {
+        int y0, y1;
+        float ly;
+        bilinear_src(y, sy, h, y0, y1, ly);
+        float wy = 0.f;
+        if (y0 == yi) wy += 1.f - ly;
+        if (y1 == yi) wy += ly;
+        if (wy != 0.f) { s_rows[n] = y; s_wy[n] = wy; ++n; }
+      }
+    }
+    s_nrows = n;
   }
-  const float sy = (float)h / (float)H, sx = (float)w / (float)W;
-  // hi-res rows whose source rows {y0, y1} can include yi: src in (yi-1, yi+1)
-  const float fy = (float)H / (float)h, fx = (float)W / (float)w;
-  int ylo = (int)floorf((yi - 1 + 0.5f) * fy - 0.5f) - 1, yhi = (int)ceilf((yi + 1 + 0.5f) * fy - 0.5f) + 1;
-  int xlo = (int)floorf((xi - 1 + 0.5f) * fx - 0.5f) - 1, xhi = (int)ceilf((xi + 1 + 0.5f) * fx - 0.5f) + 1;
-  if (ylo < 0) ylo = 0;
-  if (xlo < 0) xlo = 0;
-  if (yhi > H - 1) yhi = H - 1;
-  if (xhi > W - 1) xhi = W - 1;
-  for (int y = ylo; y <= yhi; ++y) {
-    int y0, y1;
-    float ly;
-    bilinear_src(y, sy, h, y0, y1, ly);
-    float wy = 0.f;
-    if (y0 == yi) wy += 1.f - ly;
-    if (y1 == yi) wy += ly;
-    if (wy == 0.f) continue;
+  __syncthreads();
+  const int nrows = s_nrows;
+  const float sx = (float)w / (float)W, fx = (float)W / (float)w;
+  const int n = w * C8;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int xi = i / C8, c8 = i - xi * C8;
+    __nv_bfloat16* dst = din + (((size_t)b * h + yi) * w + xi) * C + c8 * 8;
+    if (ident) {
+      *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(dout + (((size_t)b * H + yi) * W + xi) * ld_out + ch_off + c8 * 8);
+      continue;
+    }
+    int xlo = (int)floorf((xi - 1 + 0.5f) * fx - 0.5f) - 1, xhi = (int)ceilf((xi + 1 + 0.5f) * fx - 0.5f) + 1;
+    if (xlo < 0) xlo = 0;
+    if (xhi > W - 1) xhi = W - 1;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
     for (int x = xlo; x <= xhi; ++x) {
       int x0, x1;
       float lx;
@@ -123,21 +137,24 @@ __global__ void __launch_bounds__(256) upsample_concat_bwd_kernel(const __nv_bfl
       if (x0 == xi) wx += 1.f - lx;
       if (x1 == xi) wx += lx;
       if (wx == 0.f) continue;
-      const float wt = wy * wx;
-      const uint4 v = *reinterpret_cast<const uint4*>(dout + ((b * H + y) * W + x) * ld_out + ch_off + c8 * 8);
-      const uint32_t* vp = reinterpret_cast<const uint32_t*>(&v);
+      const __nv_bfloat16* col = dout + ((size_t)b * H * W + x) * ld_out + ch_off + c8 * 8;
+      for (int r = 0; r < nrows; ++r) {
+        const float wt = wx * s_wy[r];
+        const uint4 v = *reinterpret_cast<const uint4*>(col + (size_t)s_rows[r] * W * ld_out);
+        const uint32_t* vp = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = unpack_bf16x2(vp[i]);
-        acc[2 * i] = fmaf(wt, f.x, acc[2 * i]);
-        acc[2 * i + 1] = fmaf(wt, f.y, acc[2 * i + 1]);
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = unpack_bf16x2(vp[k]);
+          acc[2 * k] = fmaf(wt, f.x, acc[2 * k]);
+          acc[2 * k + 1] = fmaf(wt, f.y, acc[2 * k + 1]);
+        }
       }
     }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(dst) = o;
   }
-  uint4 o;
-  o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
-  o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
-  *reinterpret_cast<uint4*>(din + idx * 8) = o;
 }
 
 int upsample_concat_bwd(const void* dout, void* din, int B, int h, int w, int C, int H, int W, long long ld_out, int ch_off,
@@ -145,8 +162,9 @@ int upsample_concat_bwd(const void* dout, void* din, int B, int h, int w, int C,
   SFK_REQUIRE(C % 8 == 0 && ld_out % 8 == 0 && ch_off % 8 == 0, "upsample_concat_bwd: channel counts must be multiples of 8");
   const long long total = (long long)B * h * w * (C / 8);
   if (total == 0) return 0;
-  launch_k(upsample_concat_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, (const __nv_bfloat16*)dout, (__nv_bfloat16*)din,
-                                                                                  B, h, w, C, H, W, ld_out, ch_off);
+  SFK_REQUIRE(H <= 16 * h + 32 || h == H, "upsample_concat_bwd: scale factor too large");
+  launch_k(upsample_concat_bwd_kernel, dim3((unsigned)(B * h)), dim3(256), 0, stream, (const __nv_bfloat16*)dout, (__nv_bfloat16*)din, B, h, w,
+           C, H, W, ld_out, ch_off);
   return check_launch("upsample_concat_bwd_kernel");
 }
 

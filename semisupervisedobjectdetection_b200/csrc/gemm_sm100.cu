@@ -29,6 +29,22 @@ static constexpr int MAX_STAGES = 8;
 
 // runtime switch (sfk_set_option("gemm_cluster2", 0|1)); measured neutral on B200 for this workload (profiles/), default off
 int g_gemm_cluster2 = 0;
+// small-K GEMMs: 2 resident CTAs per SM (<= 110 KB smem, 256 TMEM columns each) so one CTA's epilogue / pipeline fill
+// overlaps the other's main loop
+int g_gemm_occ2 = 1;
+
+// optional in-kernel timeline (debug): CTA 0 stores globaltimer (ns) at phase boundaries into this device buffer
+unsigned long long* g_gemm_trace = nullptr;
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define GEMM_TRACE(slot)                                                     \
+  do {                                                                       \
+    if (p.trace != nullptr && blockIdx.x == 0) p.trace[slot] = gtime();      \
+  } while (0)
 
 struct GemmKernelParams {
   int M, N, K;
@@ -53,6 +69,8 @@ struct GemmKernelParams {
   int out_bf16;
   int atomic_add;
   int relu;
+  unsigned long long* trace;
+  int tmem_cols;   // 512 (1 CTA / SM) or 256 (2 CTAs / SM); accumulator buffer a lives at column a * tmem_cols / 2
   int cluster2;  // launched as 2-CTA clusters: the pair works on two adjacent row tiles and shares (multicasts) the B tiles
 };
 
@@ -67,10 +85,11 @@ __device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, fl
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmKernelParams p) {
   pdl_launch_dependents();  // let the next kernel of the stream get scheduled; it waits for our completion itself
+  if (threadIdx.x == 0) GEMM_TRACE(0);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-B alignment is required by SWIZZLE_128B atoms; dynamic smem base is only 16-B aligned by contract.
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -103,7 +122,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tmem_relinquish();
   }
   // barrier init / TMEM allocation / descriptor prefetch above overlap the previous kernel's tail (PDL);
@@ -114,6 +133,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (p.cluster2) cluster_sync_all();  // peer barriers are initialised before any multicast / remote arrive targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  if (threadIdx.x == 0) GEMM_TRACE(1);
 
   // work units: (row tile | row-tile pair, column tile, k split); in cluster mode the two CTAs of a pair walk the same
   // unit sequence in lockstep, CTA rank r owning row tile 2*pair + r
@@ -142,6 +162,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const uint32_t sb = sa + a_bytes;
           const uint32_t full = bar_full + 8 * stage;
           mbar_arrive_expect_tx(full, p.stage_bytes);
+          if (unit == unit0 && kb == kb0) GEMM_TRACE(2);
           if (!p.a_mn) {
             tma_load_2d(sa, &tmap_a, full, kb * BLOCK_K, m_blk * BLOCK_M);
           } else {
@@ -184,10 +205,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       // wait for the epilogue to have drained this accumulator buffer
       mbar_wait(bar_tempty + 8 * acc, acc_phase[acc] ^ 1);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * MAX_BLOCK_N;
+      const uint32_t tmem_d = tmem_base + acc * (p.tmem_cols >> 1);
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(bar_full + 8 * stage, phase);
         tc_fence_after();
+        if (lane == 0 && unit == unit0 && kb == kb0) GEMM_TRACE(3);
         if (lane == 0) {
           const uint32_t sa = smem_base + stage * p.stage_bytes;
           const uint32_t sb = sa + a_bytes;
@@ -202,6 +224,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (p.cluster2) umma_commit_mc(bar_empty + 8 * stage, 3);  // tell both producers of the pair
           else umma_commit(bar_empty + 8 * stage);              // smem slot reusable once these MMAs retire
           if (kb == kb1 - 1) umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+          if (kb == kb1 - 1 && unit == unit0) GEMM_TRACE(4);
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -220,6 +243,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int m_blk = p.cluster2 ? 2 * (tile / p.n_tiles) + (int)crank : tile / p.n_tiles;
       mbar_wait(bar_tfull + 8 * acc, acc_phase[acc]);
       tc_fence_after();
+      if (threadIdx.x == 64 && unit == unit0) GEMM_TRACE(5);
       const long long row = (long long)m_blk * BLOCK_M + q * 32 + lane;
       const bool row_ok = row < p.M;
       float rscale = p.alpha;
@@ -229,7 +253,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       for (int c = 0; c < p.block_n; c += 32) {
         uint32_t r[32];
         __syncwarp();
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * MAX_BLOCK_N + c, r);
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (p.tmem_cols >> 1) + c, r);
         tmem_ld_wait();
         const int col0 = n0 + c;
         if (!row_ok || col0 >= p.N) continue;
@@ -308,6 +332,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (threadIdx.x == 64 && unit == unit0) GEMM_TRACE(6);
       acc_phase[acc] ^= 1;
       acc ^= 1;
     }
@@ -315,10 +340,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) GEMM_TRACE(7);
   if (p.cluster2) cluster_sync_all();  // the peer may still multicast into our smem / arrive on our barriers until it is done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -376,10 +402,26 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.a_mn = g.a_mn ? 1 : 0;
   p.b_mn = g.b_mn ? 1 : 0;
+  p.k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
+  // latency-bound regime (few k-blocks per tile): prefer two co-resident CTAs per SM over wide tiles
+  const bool occ2 = g_gemm_occ2 && g.block_n <= 0 && !g.atomic_add && p.k_blocks <= 8 && g.N >= 64;
   p.block_n = g.block_n > 0 ? g.block_n : pick_block_n(g.N, p.b_mn, g.M, g.atomic_add);
+  if (occ2 && p.block_n > 128) {
+    // widest tile <= 128 columns with the least padding
+    const int c_k[] = {128, 96, 64}, c_mn[] = {128, 64};
+    const int* c = p.b_mn ? c_mn : c_k;
+    const int nc2 = p.b_mn ? 2 : 3;
+    int best = c[0];
+    long long best_cols = 1LL << 60;
+    for (int i = 0; i < nc2; ++i) {
+      const long long cols = (long long)((g.N + c[i] - 1) / c[i]) * c[i];
+      if (cols < best_cols) { best_cols = cols; best = c[i]; }
+    }
+    p.block_n = best;
+  }
+  p.tmem_cols = (occ2 && p.block_n <= 128) ? 256 : TMEM_COLS;
   SFK_REQUIRE(p.block_n % 32 == 0 && p.block_n >= 32 && p.block_n <= MAX_BLOCK_N, "gemm: bad block_n %d", p.block_n);
   SFK_REQUIRE(!p.b_mn || p.block_n % 64 == 0, "gemm: MN-major B needs block_n %% 64 == 0");
-  p.k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
   p.m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
   p.n_tiles = (g.N + p.block_n - 1) / p.block_n;
   int splits = g.splits;
@@ -399,9 +441,10 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   SFK_REQUIRE(splits == 1 || g.atomic_add, "gemm: split-K requires atomic accumulation");
   p.splits = splits;
   p.stage_bytes = BLOCK_M * BLOCK_K * 2 + p.block_n * BLOCK_K * 2;
-  const int smem_budget = 227 * 1024 - 2048;
+  const int smem_budget = (p.tmem_cols == 256 ? 110 * 1024 : 227 * 1024) - 2048;
   int stages = smem_budget / (int)p.stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages > p.k_blocks + 1 && p.tmem_cols == 256) stages = p.k_blocks + 1;
   SFK_REQUIRE(stages >= 2, "gemm: not enough shared memory for 2 stages");
   p.stages = stages;
   p.alpha = g.alpha;
@@ -417,6 +460,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.out_bf16 = g.out_bf16;
   p.atomic_add = g.atomic_add;
   p.relu = g.relu;
+  p.trace = g_gemm_trace;
   // 2-CTA clusters sharing B through TMA multicast: halves the dominant L2 -> smem stream of these small-K GEMMs
   p.cluster2 = (g_gemm_cluster2 && p.m_tiles >= 2 && (num_sms() % 2 == 0)) ? 1 : 0;
 
@@ -443,7 +487,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     const long long clusters = units < num_sms() / 2 ? units : num_sms() / 2;
     grid = (int)(2 * clusters);
   } else {
-    grid = (int)(units < num_sms() ? units : num_sms());
+    const long long slots = (long long)num_sms() * (p.tmem_cols == 256 ? 2 : 1);
+    grid = (int)(units < slots ? units : slots);
   }
   prof_gemm_shape(g.M, g.N, g.K, (g.a_mn ? 1 : 0) | (g.b_mn ? 2 : 0) | (g.atomic_add ? 4 : 0) | (p.splits << 8) | ((long long)p.block_n << 20));
   prof_gemm_begin(2.0 * (double)g.M * (double)g.N * (double)g.K, stream);

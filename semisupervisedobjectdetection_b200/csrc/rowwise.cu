@@ -141,16 +141,25 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDy* __restrict__ dy,
     if (row >= rows) break;
     const TDy* dyr = dy + row * C;
     const TX* xr = x + map_row(row, x_map) * C;
+    const float* rr = dres ? dres + map_row(row, dres_map) * C : nullptr;
     const float mu = mean[row], rs = rstd[row];
-    float4 dyv[LN_MAX_CHUNKS], xh[LN_MAX_CHUNKS];
+    float4 dyv[LN_MAX_CHUNKS], xh[LN_MAX_CHUNKS], rv[LN_MAX_CHUNKS];
     float s1 = 0.f, s2 = 0.f;
+    // all loads of the row (dy, x and the residual gradient) are issued before the reductions: one memory latency per row
 #pragma unroll
     for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
       const int ci = lane + 32 * k;
       if (ci < nchunk) {
         dyv[k] = Ld4<TDy>::ld(dyr + ci * 4);
-        const float4 xv = Ld4<TX>::ld(xr + ci * 4);
-        xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        xh[k] = Ld4<TX>::ld(xr + ci * 4);
+        rv[k] = rr ? *reinterpret_cast<const float4*>(rr + ci * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
+      const int ci = lane + 32 * k;
+      if (ci < nchunk) {
+        xh[k] = make_float4((xh[k].x - mu) * rs, (xh[k].y - mu) * rs, (xh[k].z - mu) * rs, (xh[k].w - mu) * rs);
         const float a = dyv[k].x * g[k].x, b = dyv[k].y * g[k].y, c = dyv[k].z * g[k].z, d = dyv[k].w * g[k].w;
         s1 += a + b + c + d;
         s2 += a * xh[k].x + b * xh[k].y + c * xh[k].z + d * xh[k].w;
@@ -162,20 +171,15 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDy* __restrict__ dy,
     s1 = warp_sum(s1) / (float)C;
     s2 = warp_sum(s2) / (float)C;
     TDx* dxr = dx + map_row(row, dx_map) * C;
-    const float* rr = dres ? dres + map_row(row, dres_map) * C : nullptr;
 #pragma unroll
     for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
       const int ci = lane + 32 * k;
       if (ci < nchunk) {
         float4 o;
-        o.x = rs * (dyv[k].x * g[k].x - s1 - xh[k].x * s2);
-        o.y = rs * (dyv[k].y * g[k].y - s1 - xh[k].y * s2);
-        o.z = rs * (dyv[k].z * g[k].z - s1 - xh[k].z * s2);
-        o.w = rs * (dyv[k].w * g[k].w - s1 - xh[k].w * s2);
-        if (rr) {
-          const float4 r4 = *reinterpret_cast<const float4*>(rr + ci * 4);
-          o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-        }
+        o.x = rs * (dyv[k].x * g[k].x - s1 - xh[k].x * s2) + rv[k].x;
+        o.y = rs * (dyv[k].y * g[k].y - s1 - xh[k].y * s2) + rv[k].y;
+        o.z = rs * (dyv[k].z * g[k].z - s1 - xh[k].z * s2) + rv[k].z;
+        o.w = rs * (dyv[k].w * g[k].w - s1 - xh[k].w * s2) + rv[k].w;
         Ld4<TDx>::st(dxr + ci * 4, o);
       }
     }
@@ -231,6 +235,7 @@ int layernorm_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, RowMap
   do {                                                   \
     if (C <= 128) { LAUNCH_N(TD, TX, TO, 1); }           \
     else if (C <= 256) { LAUNCH_N(TD, TX, TO, 2); }      \
+    else if (C <= 384) { LAUNCH_N(TD, TX, TO, 3); }      \
     else if (C <= 512) { LAUNCH_N(TD, TX, TO, 4); }      \
     else { LAUNCH_N(TD, TX, TO, 8); }                    \
   } while (0)
