@@ -280,7 +280,24 @@ __global__ void __launch_bounds__(256) scale_cast_kernel(const TIn* __restrict__
     long long r1 = r0 + rows_per_block;
     if (r1 > rows) r1 = rows;
     const long long ldc = (long long)C4 * 4;
-    for (long long row = r0 + rl; row < r1; row += lanes_r) {
+    // 4 rows per iteration: four independent 16-byte loads in flight per thread
+    long long row = r0 + rl;
+    for (; row + 3LL * lanes_r < r1; row += 4LL * lanes_r) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = Ld4<TIn>::ld(x + map_row(row + (long long)u * lanes_r, in_map) * ldc + c4 * 4);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long ru = row + (long long)u * lanes_r;
+        if (scale) {
+          const float sc = scale[ru / rows_per_scale];
+          v[u].x *= sc; v[u].y *= sc; v[u].z *= sc; v[u].w *= sc;
+        }
+        Ld4<TOut>::st(y + map_row(ru, out_map) * ldc + c4 * 4, v[u]);
+        acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+      }
+    }
+    for (; row < r1; row += lanes_r) {
       float4 v = Ld4<TIn>::ld(x + map_row(row, in_map) * ldc + c4 * 4);
       if (scale) {
         const float sc = scale[row / rows_per_scale];
@@ -320,9 +337,10 @@ int scale_cast_sum(const void* x, int x_bf16, RowMap in_map, void* y, int y_bf16
   const int cwb = C4 < 256 ? C4 : 256;
   const int gx = (C4 + cwb - 1) / cwb;
   const int lanes_r = 256 / cwb;
-  long long gy = ((long long)num_sms() * 8 + gx - 1) / gx;
+  // with fused column sums every block pays a fence + slot commit: use few, long-lived blocks (2 per SM)
+  long long gy = ((long long)num_sms() * (colsum0 != nullptr ? 2 : 8) + gx - 1) / gx;
   long long rpb = (rows + gy - 1) / gy;
-  if (rpb < lanes_r) rpb = lanes_r;
+  if (rpb < 4LL * lanes_r) rpb = 4LL * lanes_r;
   gy = (rows + rpb - 1) / rpb;
   if (rows_per_scale <= 0) rows_per_scale = 1;
   if (colsum0 != nullptr && colsum1 == nullptr) { colsum1 = colsum0; split = C; }
