@@ -12,76 +12,17 @@ namespace sfk {
 
 // ------------------------------------------------------------------------------------------------
 // depthwise 3x3, stride 1, pad 1.  x: bf16 [B,H,W,C].  wt: fp32 [9][C] (tap-major copy of weight[C,1,3,3]).
-// Mapping: a warp = 32 consecutive channel groups (VEC channels each) of ONE (b, y, 4-pixel segment) position, so every
-// load/store instruction of a warp is one contiguous 256/512-byte run; the 8 warps of a block walk different positions.
-// Each thread produces SEG consecutive outputs along W, loading its 3 x (SEG+2) window once (4.5 loads per output).
-// Per-thread channel sums (bias gradients) are reduced across the block in shared memory -> one atomic per channel/block.
+// Per-thread channel sums (bias / filter gradients) are reduced across the block in shared memory and committed through
+// the slotted low-contention column-sum path (colsum_slots.cuh).
 // ------------------------------------------------------------------------------------------------
-static constexpr int DW_SEG = 4;
 
-// erf with |err| <= 1.5e-7 (Abramowitz-Stegun 7.1.26) from one rcp and one ex2; `e` = exp(-x*x) is passed in so the
-// GELU derivative can reuse it for the Gaussian pdf.
-__device__ __forceinline__ float erf_from_exp(float ax, float e) {
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  return 1.0f - p * t * e;
-}
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = x * 0.70710678118654752440f;
-  const float e = __expf(-z * z);
-  const float er = copysignf(erf_from_exp(fabsf(z), e), x);
-  return 0.5f * x * (1.0f + er);
-}
-__device__ __forceinline__ float gelu_grad_fast(float x) {
-  const float z = x * 0.70710678118654752440f;
-  const float e = __expf(-z * z);  // == exp(-x^2/2)
-  const float er = copysignf(erf_from_exp(fabsf(z), e), x);
-  return fmaf(x * 0.39894228040143267794f, e, 0.5f * (1.0f + er));
-}
-
-// 128-bit shared-memory read the compiler may not hoist out of the position loop (loop-invariant filter taps would
-// otherwise be promoted back into ~80 registers, which is exactly what keeping them in shared memory is meant to avoid)
+// 128-bit shared-memory read the compiler may not hoist out of the row loop (loop-invariant filter taps would otherwise
+// be promoted back into registers, which is exactly what keeping them in shared memory is meant to avoid)
 __device__ __forceinline__ float4 lds128_nohoist(const float* p) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
   return v;
 }
-
-template <int VEC> struct VecIO;
-template <> struct VecIO<8> {
-  typedef uint4 packed;
-  static __device__ __forceinline__ packed ldp(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
-  static __device__ __forceinline__ packed zero() { return make_uint4(0, 0, 0, 0); }
-  static __device__ __forceinline__ void unpack(const packed& u, float* f) {
-    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
-    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
-  }
-  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* f) { unpack(ldp(p), f); }
-  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* f) {
-    uint4 u;
-    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
-    u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
-    *reinterpret_cast<uint4*>(p) = u;
-  }
-};
-template <> struct VecIO<4> {
-  typedef uint2 packed;
-  static __device__ __forceinline__ packed ldp(const __nv_bfloat16* p) { return *reinterpret_cast<const uint2*>(p); }
-  static __device__ __forceinline__ packed zero() { return make_uint2(0, 0); }
-  static __device__ __forceinline__ void unpack(const packed& u, float* f) {
-    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
-  }
-  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float* f) { unpack(ldp(p), f); }
-  static __device__ __forceinline__ void st(__nv_bfloat16* p, const float* f) {
-    uint2 u;
-    u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
-    *reinterpret_cast<uint2*>(p) = u;
-  }
-};
 
 // block-level reduction of per-thread channel partials (8 warps -> shared memory), then the slotted low-contention commit:
 // virtual column v = k * C + channel  (k-th output array)
@@ -114,157 +55,294 @@ __device__ __forceinline__ void dw_block_commit(float (&acc)[NV][VEC], float* sh
   });
 }
 
-// mode 0: y = gelu(conv(x) + bias)     mode 1: y = conv_flipped(x)  (input gradient of the conv); colsum (+)= sum_pixels y
-// ncu (profiles/): the first versions were (a) latency bound — loads consumed one by one — then (b) issue bound — 64-bit
-// index division and per-(tap,output) re-unpacking.  This version: 8 channels x 2 pixels per thread, the 3x4 window is
-// loaded up front (12 independent 16-byte loads), every window vector is unpacked once and feeds all taps that see it,
-// filter taps / bias come from shared memory ([tap][lane][8], conflict-free 128-bit reads), 32-bit index arithmetic.
-static constexpr int DWF_SEG = 4;
-static constexpr int DWB_SEG = 2;
+// ------------------------------------------------------------------------------------------------
+// Rolling-window depthwise 3x3 (replaces the per-position kernels above on the hot path).
+// ncu on the per-position kernels: issue bound (~49 instructions per output element), not HBM bound.  This version cuts the
+// instruction count ~2.5x:
+//   * a thread owns 4 channels x 4 pixels (along W) and WALKS DOWN the image: every input row is loaded and unpacked once
+//     and scattered into the three output rows it touches (accumulators rotate statically, loop unrolled by 3), so the
+//     bf16->fp32 unpack cost is (SEG+2)/SEG = 1.5 per output instead of 4.5;
+//   * all fp32 math is packed (fma.rn.f32x2 -> FFMA2, two lanes per issue slot): taps, bias, GELU polynomial;
+//   * the 9 taps of the thread's 4 channels live in registers (18 packed pairs), no shared-memory reads in the loop;
+//   * the next input row is prefetched (6 independent 8-byte loads) while the current one is consumed.
+// A warp = 32 channel quads of one (image, row chunk, 4-pixel segment): every load/store instruction covers 256 contiguous bytes.
+// ------------------------------------------------------------------------------------------------
+typedef unsigned long long p2;  // two packed fp32 (lo, hi)
+__device__ __forceinline__ p2 p2_make(float lo, float hi) {
+  p2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ p2 p2_make_u(uint32_t lo, uint32_t hi) {
+  p2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void p2_split(p2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void p2_split_u(p2 v, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ p2 p2_splat(float a) { return p2_make(a, a); }
+__device__ __forceinline__ p2 p2_fma(p2 a, p2 b, p2 c) {
+  p2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ p2 p2_mul(p2 a, p2 b) {
+  p2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ p2 p2_add(p2 a, p2 b) {
+  p2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// bf16x2 word -> packed fp32 pair (exact): lo = u << 16, hi = u & 0xffff0000
+__device__ __forceinline__ p2 p2_from_bf16x2(uint32_t u) { return p2_make_u(u << 16, u & 0xffff0000u); }
+__device__ __forceinline__ uint32_t p2_to_bf16x2(p2 v) {
+  float lo, hi;
+  p2_split(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// q(x) = P(t) * t * exp(-x^2/2), t = 1/(1 + p|x|/sqrt2): erf(|x|/sqrt2) = 1 - q  (Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7).
+// Returns q, |x| and e = exp(-x^2/2) for a packed pair.
+__device__ __forceinline__ p2 erfc_pair(p2 x, p2& ax, p2& e) {
+  uint32_t xl, xh;
+  p2_split_u(x, xl, xh);
+  ax = p2_make_u(xl & 0x7fffffffu, xh & 0x7fffffffu);
+  const p2 m = p2_mul(p2_mul(x, x), p2_splat(-0.72134752044448170368f));  // -x^2/2 * log2(e)
+  float ml, mh, dl, dh;
+  p2_split(m, ml, mh);
+  e = p2_make(ex2_approx(ml), ex2_approx(mh));
+  const p2 d = p2_fma(ax, p2_splat(0.3275911f * 0.70710678118654752440f), p2_splat(1.0f));
+  p2_split(d, dl, dh);
+  const p2 t = p2_make(rcp_approx(dl), rcp_approx(dh));
+  p2 p = p2_fma(p2_splat(1.061405429f), t, p2_splat(-1.453152027f));
+  p = p2_fma(p, t, p2_splat(1.421413741f));
+  p = p2_fma(p, t, p2_splat(-0.284496736f));
+  p = p2_fma(p, t, p2_splat(0.254829592f));
+  return p2_mul(p2_mul(p, t), e);
+}
+// gelu(x) = 0.5 x (1 + erf(x/sqrt2)) = relu(x) - 0.5 |x| q(x)
+__device__ __forceinline__ p2 gelu_pair(p2 x) {
+  p2 ax, e;
+  const p2 q = erfc_pair(x, ax, e);
+  const p2 w = p2_mul(ax, q);
+  const p2 s = p2_add(x, ax);  // 2 relu(x)
+  return p2_fma(w, p2_splat(-0.5f), p2_mul(s, p2_splat(0.5f)));
+}
+// gelu'(x) = Phi(x) + x phi(x),  Phi(x) = 0.5 + copysign(0.5 (1 - q), x),  phi(x) = e / sqrt(2 pi)
+__device__ __forceinline__ p2 gelu_grad_pair(p2 x) {
+  p2 ax, e;
+  const p2 q = erfc_pair(x, ax, e);
+  const p2 u = p2_fma(q, p2_splat(-0.5f), p2_splat(0.5f));  // 0.5 (1 - q) >= 0
+  uint32_t ul, uh, xl, xh;
+  p2_split_u(u, ul, uh);
+  p2_split_u(x, xl, xh);
+  const p2 us = p2_make_u(ul | (xl & 0x80000000u), uh | (xh & 0x80000000u));
+  const p2 phi_x = p2_mul(p2_mul(x, p2_splat(0.39894228040143267794f)), e);
+  return p2_add(p2_add(us, p2_splat(0.5f)), phi_x);
+}
 
+static constexpr int DWR_SEG = 4;  // output pixels per thread along W
+static constexpr int DWR_VEC = 4;  // channels per thread
+
+// loads one (SEG+2)-pixel input row for this thread's 4 channels; `rp` points at pixel (x0-1) of that row (never dereferenced
+// where the row / column is outside the image: zeros there)
+__device__ __forceinline__ void dwr_load_row(uint2 (&row)[DWR_SEG + 2], const __nv_bfloat16* rp, bool vy, unsigned colmask, int C) {
+#pragma unroll
+  for (int j = 0; j < DWR_SEG + 2; ++j)
+    row[j] = (vy && ((colmask >> j) & 1u)) ? __ldg(reinterpret_cast<const uint2*>(rp + (unsigned)(j * C))) : make_uint2(0, 0);
+}
+
+// scatter one unpacked input row into the three output rows it feeds: a_old gets filter row 2, a_mid row 1, a_new row 0
+#define DWR_SCATTER(a_old, a_mid, a_new, cur)                                                                \
+  {                                                                                                       \
+    _Pragma("unroll") for (int j = 0; j < DWR_SEG + 2; ++j) {                                             \
+      const p2 f0 = p2_from_bf16x2(cur[j].x), f1 = p2_from_bf16x2(cur[j].y);                              \
+      _Pragma("unroll") for (int tt = 0; tt < 3; ++tt) {                                                  \
+        const int o = j - tt;                                                                             \
+        if (o >= 0 && o < DWR_SEG) {                                                                      \
+          a_old[o][0] = p2_fma(wk[6 + tt][0], f0, a_old[o][0]);                                           \
+          a_old[o][1] = p2_fma(wk[6 + tt][1], f1, a_old[o][1]);                                           \
+          a_mid[o][0] = p2_fma(wk[3 + tt][0], f0, a_mid[o][0]);                                           \
+          a_mid[o][1] = p2_fma(wk[3 + tt][1], f1, a_mid[o][1]);                                           \
+          a_new[o][0] = p2_fma(wk[tt][0], f0, a_new[o][0]);                                               \
+          a_new[o][1] = p2_fma(wk[tt][1], f1, a_new[o][1]);                                               \
+        }                                                                                                 \
+      }                                                                                                   \
+    }                                                                                                     \
+  }
+
+// mode 0: y = gelu(conv(x) + bias)     mode 1: y = conv_flipped(x)  (input gradient of the conv); colsum (+)= sum_pixels y
 template <int MODE>
-__global__ void __launch_bounds__(256, 1) dwconv3x3_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
-                                                           const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
-                                                           float* __restrict__ colsum, int B, int H, int W, int C,
-                                                           int pos_per_block, int ns) {
+__global__ void __launch_bounds__(256, 2) dwconv3x3_roll_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
+                                                                const float* __restrict__ bias, __nv_bfloat16* __restrict__ y,
+                                                                float* __restrict__ colsum, int B, int H, int W, int C, int ns) {
   pdl_sync();
-  constexpr int VEC = 8;
-  __shared__ __align__(16) float sw[10 * 32 * VEC];   // 9 taps + bias
+  constexpr int SEG = DWR_SEG, VEC = DWR_VEC;
   __shared__ float sh[32 * VEC];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cblk = blockIdx.x * 32 * VEC;
-  const int c0 = cblk + lane * VEC;
+  const int c0 = (blockIdx.x * 32 + lane) * VEC;
   const bool lane_ok = c0 < C;
-  for (int i = threadIdx.x; i < 10 * 32 * VEC; i += 256) {
-    const int k = i / (32 * VEC), j = i % (32 * VEC);
-    float v = 0.f;
-    if (cblk + j < C) {
-      if (k < 9) v = wt[(MODE == 1 ? 8 - k : k) * C + cblk + j];
-      else if (MODE == 0) v = bias[cblk + j];
-    }
-    sw[i] = v;
-  }
-  __syncthreads();
-  const unsigned nseg = (unsigned)(W + DWF_SEG - 1) / DWF_SEG;
-  const unsigned npos = (unsigned)B * H * nseg;
-  const unsigned p0 = blockIdx.y * (unsigned)pos_per_block;
-  unsigned p1 = p0 + pos_per_block;
-  if (p1 > npos) p1 = npos;
   float csum[1][VEC];
 #pragma unroll
   for (int v = 0; v < VEC; ++v) csum[0][v] = 0.f;
   if (lane_ok) {
-    const float* swl = sw + lane * VEC;
-    for (unsigned pos = p0 + warp; pos < p1; pos += 8) {
-      const unsigned seg = pos % nseg, t = pos / nseg;
-      const int yy = (int)(t % (unsigned)H), b = (int)(t / (unsigned)H);
-      const int x0 = (int)seg * DWF_SEG;
-      uint4 win[3][DWF_SEG + 2];
+    p2 wk[9][2], bs[2];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const int sy = yy + r - 1;
-        const bool vy = sy >= 0 && sy < H;
-        const unsigned rowoff = ((unsigned)(b * H + sy) * W) * C + c0;
+    for (int k = 0; k < 9; ++k) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wt + (size_t)(MODE == 1 ? 8 - k : k) * C + c0));
+      wk[k][0] = p2_make(w4.x, w4.y);
+      wk[k][1] = p2_make(w4.z, w4.w);
+    }
+    if (MODE == 0) {
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0));
+      bs[0] = p2_make(b4.x, b4.y);
+      bs[1] = p2_make(b4.z, b4.w);
+    } else {
+      bs[0] = bs[1] = p2_splat(0.f);
+    }
+    p2 cs0 = p2_splat(0.f), cs1 = p2_splat(0.f);
+    // work split: the (image, 4-pixel segment) columns of this channel block form one long list of rows; every warp of
+    // the grid takes an equal contiguous range of it (at most two partial columns), so the GPU is filled evenly in ONE
+    // wave whatever B, H, W are
+    const unsigned nseg = (unsigned)(W + SEG - 1) / SEG;
+    const unsigned long long total = (unsigned long long)B * nseg * H;
+    const unsigned gwarp = blockIdx.y * 8 + warp, nwarp = gridDim.y * 8;
+    unsigned pos = (unsigned)(gwarp * total / nwarp);
+    const unsigned pos_end = (unsigned)((gwarp + 1) * total / nwarp);
+    while (pos < pos_end) {
+      const unsigned col = pos / (unsigned)H;
+      const int y0 = (int)(pos - col * (unsigned)H);
+      int y1 = y0 + (int)(pos_end - pos);
+      if (y1 > H) y1 = H;
+      pos += (unsigned)(y1 - y0);
+      const int b = (int)(col / nseg);
+      const int x0 = (int)(col % nseg) * SEG;
+      p2 a0[SEG][2], a1[SEG][2], a2[SEG][2];
 #pragma unroll
-        for (int j = 0; j < DWF_SEG + 2; ++j) {
-          const int sx = x0 + j - 1;
-          win[r][j] = (vy && sx >= 0 && sx < W) ? *reinterpret_cast<const uint4*>(x + (size_t)(rowoff + (unsigned)sx * C))
-                                                : make_uint4(0, 0, 0, 0);
-        }
+      for (int o = 0; o < SEG; ++o) {
+        a0[o][0] = a0[o][1] = a1[o][0] = a1[o][1] = p2_splat(0.f);
       }
-      const unsigned outoff = ((unsigned)(b * H + yy) * W + x0) * C + c0;
-      // minimum-instruction order: every window vector is unpacked once and feeds the (up to 3) outputs that see it
-      float acc[DWF_SEG][VEC];
-      {
-        const float4 b0 = lds128_nohoist(swl + 9 * 32 * VEC);
-        const float4 b1 = lds128_nohoist(swl + 9 * 32 * VEC + 4);
+      uint2 rb0[SEG + 2], rb1[SEG + 2], rb2[SEG + 2];  // row buffers: step k consumes rb(k%3) and prefetches rb((k+1)%3)
+      unsigned colmask = 0;
 #pragma unroll
-        for (int o = 0; o < DWF_SEG; ++o) {
-          acc[o][0] = b0.x; acc[o][1] = b0.y; acc[o][2] = b0.z; acc[o][3] = b0.w;
-          acc[o][4] = b1.x; acc[o][5] = b1.y; acc[o][6] = b1.z; acc[o][7] = b1.w;
-        }
+      for (int j = 0; j < SEG + 2; ++j) colmask |= (x0 + j - 1 >= 0 && x0 + j - 1 < W) ? (1u << j) : 0u;
+      const ptrdiff_t rstride = (ptrdiff_t)W * C;
+      // rp: pixel (x0-1) of the NEXT input row to load;  yp: pixel x0 of the next output row to store
+      const __nv_bfloat16* rp = x + ((ptrdiff_t)(b * H + y0 - 1) * W + (x0 - 1)) * C + c0;
+      __nv_bfloat16* yp = y + ((ptrdiff_t)(b * H + y0) * W + x0) * C + c0;
+      dwr_load_row(rb0, rp, y0 - 1 >= 0, colmask, C);
+      rp += rstride;
+      // one step: input row ry is in `cur`; completes output row ry-1 (a_old)
+#define DWR_STEP(a_old, a_mid, a_new, cur, nxt, ry)                                                       \
+  {                                                                                                       \
+    dwr_load_row(nxt, rp, (ry) < y1 && (ry) + 1 < H, colmask, C);                                         \
+    rp += rstride;                                                                                        \
+    _Pragma("unroll") for (int o = 0; o < SEG; ++o) { a_new[o][0] = bs[0]; a_new[o][1] = bs[1]; }         \
+    DWR_SCATTER(a_old, a_mid, a_new, cur)                                                                 \
+    if ((ry) - 1 >= y0 && (ry) - 1 < y1) {                                                                \
+      _Pragma("unroll") for (int o = 0; o < SEG; ++o) {                                                   \
+        if ((colmask >> (o + 1)) & 1u) {                                                                  \
+          p2 r0 = a_old[o][0], r1 = a_old[o][1];                                                          \
+          if (MODE == 0) { r0 = gelu_pair(r0); r1 = gelu_pair(r1); }                                      \
+          else { cs0 = p2_add(cs0, r0); cs1 = p2_add(cs1, r1); }                                          \
+          *reinterpret_cast<uint2*>(yp + (unsigned)(o * C)) = make_uint2(p2_to_bf16x2(r0), p2_to_bf16x2(r1)); \
+        }                                                                                                 \
+      }                                                                                                   \
+      yp += rstride;                                                                                      \
+    }                                                                                                     \
+  }
+      // steps are padded to a multiple of 3 (no control-flow merge inside the rotation): the extra steps load nothing
+      // (zeros) and store nothing
+      for (int ry = y0 - 1; ry <= y1; ry += 3) {
+        DWR_STEP(a0, a1, a2, rb0, rb1, ry)
+        DWR_STEP(a1, a2, a0, rb1, rb2, ry + 1)
+        DWR_STEP(a2, a0, a1, rb2, rb0, ry + 2)
       }
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        float wr[3][VEC];
-#pragma unroll
-        for (int tt = 0; tt < 3; ++tt) {
-          const float4 w0 = lds128_nohoist(swl + (r * 3 + tt) * 32 * VEC);
-          const float4 w1 = lds128_nohoist(swl + (r * 3 + tt) * 32 * VEC + 4);
-          wr[tt][0] = w0.x; wr[tt][1] = w0.y; wr[tt][2] = w0.z; wr[tt][3] = w0.w;
-          wr[tt][4] = w1.x; wr[tt][5] = w1.y; wr[tt][6] = w1.z; wr[tt][7] = w1.w;
-        }
-#pragma unroll
-        for (int j = 0; j < DWF_SEG + 2; ++j) {
-          float f[VEC];
-          VecIO<VEC>::unpack(win[r][j], f);
-#pragma unroll
-          for (int tt = 0; tt < 3; ++tt) {
-            const int o = j - tt;
-            if (o >= 0 && o < DWF_SEG) {
-#pragma unroll
-              for (int v = 0; v < VEC; ++v) acc[o][v] = fmaf(wr[tt][v], f[v], acc[o][v]);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int o = 0; o < DWF_SEG; ++o) {
-        if (x0 + o >= W) break;
-        if (MODE == 0) {
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[o][v] = gelu_fast(acc[o][v]);
-        } else {
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) csum[0][v] += acc[o][v];
-        }
-        VecIO<VEC>::st(y + (size_t)(outoff + (unsigned)o * C), acc[o]);
-      }
+#undef DWR_STEP
+    }
+    if (MODE == 1) {
+      p2_split(cs0, csum[0][0], csum[0][1]);
+      p2_split(cs1, csum[0][2], csum[0][3]);
     }
   }
   if (MODE == 1 && colsum != nullptr) dw_block_commit<VEC, 1>(csum, sh, nullptr, 0, colsum, c0, C, lane_ok, ns);
 }
 
-static void dw_grid(int C, int vec, long long npos, dim3& grid, int& ppb) {
-  // npos = number of (b, y, segment) positions; one warp handles 32 channel groups of one position
+// grid = (channel blocks, row-range blocks): exactly one wave (<= resident_per_sm blocks per SM), each warp >= ~6 rows
+static dim3 dwr_grid(int B, int H, int W, int C, int vec, int resident_per_sm) {
   const int gx = (C / vec + 31) / 32;
-  long long gy = ((long long)num_sms() * 8 + gx - 1) / gx;   // ~8 blocks per SM in flight across the grid
+  const long long total = (long long)B * ((W + DWR_SEG - 1) / DWR_SEG) * H;
+  long long gy = (long long)num_sms() * resident_per_sm / gx;
+  const long long gy_rows = (total + 6 * 8 - 1) / (6 * 8);
+  if (gy > gy_rows) gy = gy_rows;
   if (gy < 1) gy = 1;
-  long long per = (npos + gy - 1) / gy;
-  if (per < 8) per = 8;
-  per = (per + 7) / 8 * 8;
-  gy = (npos + per - 1) / per;
-  ppb = (int)per;
-  grid = dim3(gx, (unsigned)gy);
+  return dim3(gx, (unsigned)gy);
 }
 
 int dwconv3x3(const void* x, const float* wt, const float* bias, void* y, float* colsum, int B, int H, int W, int C, int mode,
               cudaStream_t stream) {
   SFK_REQUIRE(C % 8 == 0, "dwconv3x3: C=%d must be a multiple of 8", C);
   SFK_REQUIRE((long long)B * H * W * C < (1LL << 31), "dwconv3x3: tensor too large for 32-bit offsets");
-  const long long npos = (long long)B * H * ((W + DWF_SEG - 1) / DWF_SEG);
-  if (npos == 0) return 0;
-  dim3 grid;
-  int ppb;
-  dw_grid(C, 8, npos, grid, ppb);
+  if ((long long)B * H * W == 0) return 0;
+  const dim3 grid = dwr_grid(B, H, W, C, DWR_VEC, 2);
   if (mode == 0)
-    launch_k(dwconv3x3_kernel<0>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, bias, (__nv_bfloat16*)y, nullptr, B, H, W, C, ppb, 1);
+    launch_k(dwconv3x3_roll_kernel<0>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, bias, (__nv_bfloat16*)y, nullptr, B, H, W,
+             C, 1);
   else
-    launch_k(dwconv3x3_kernel<1>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, nullptr, (__nv_bfloat16*)y, colsum, B, H, W, C, ppb,
-             colsum_num_slots((long long)grid.x * 32 * 8, grid.y));
-  return check_launch("dwconv3x3_kernel");
+    launch_k(dwconv3x3_roll_kernel<1>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, nullptr, (__nv_bfloat16*)y, colsum, B, H, W,
+             C, colsum_num_slots((long long)grid.x * 32 * DWR_VEC, grid.y));
+  return check_launch("dwconv3x3_roll_kernel");
 }
 
-// Backward stage 1: recompute pre = conv(x)+bias, dpre = dg * gelu'(pre); accumulate dW[9][C] and db[C].
-// Window kept packed (bf16), filter taps in shared memory, unpack-on-use: no spills at 128 registers (2 blocks / SM).
-__global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_bwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt,
-                                                                    const float* __restrict__ bias,
-                                                                    const __nv_bfloat16* __restrict__ dg,
-                                                                    __nv_bfloat16* __restrict__ dpre, float* __restrict__ dwt,
-                                                                    float* __restrict__ dbias, int B, int H, int W, int C,
-                                                                    int pos_per_block, int ns) {
+// Rolling-window backward stage 1 (same walk as dwconv3x3_roll_kernel): recompute pre = conv(x)+bias row by row, when
+// an output row completes: dpre = dg * gelu'(pre) (stored bf16), db += dpre, dW[ky][kx] += dpre * x(window).
+// Filter taps come from shared memory ([tap][lane][VEC], conflict-free vector reads) to leave registers for the packed
+// gradient accumulators; three packed input rows stay live for the dW products of the row that just completed.
+// VEC = channels per thread: 2 keeps the kernel at <= 128 registers (2 blocks = 16 warps per SM; the latency of the
+// row / dg prefetches is then hidden), 4 halves the load instructions but needs ~250 registers (8 warps per SM).
+template <int VEC> struct DwrVec;
+template <> struct DwrVec<4> {
+  typedef uint2 T;
+  static __device__ __forceinline__ T zero() { return make_uint2(0, 0); }
+  static __device__ __forceinline__ uint32_t word(const T& v, int q) { return q == 0 ? v.x : v.y; }
+  static __device__ __forceinline__ T make(const p2* r) { return make_uint2(p2_to_bf16x2(r[0]), p2_to_bf16x2(r[1])); }
+  static __device__ __forceinline__ void lds(const float* p, p2* w) {
+    const float4 v = lds128_nohoist(p);
+    w[0] = p2_make(v.x, v.y);
+    w[1] = p2_make(v.z, v.w);
+  }
+};
+template <> struct DwrVec<2> {
+  typedef uint32_t T;
+  static __device__ __forceinline__ T zero() { return 0u; }
+  static __device__ __forceinline__ uint32_t word(const T& v, int) { return v; }
+  static __device__ __forceinline__ T make(const p2* r) { return p2_to_bf16x2(r[0]); }
+  static __device__ __forceinline__ void lds(const float* p, p2* w) {
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(w[0]) : "r"(smem_u32(p)));
+  }
+};
+
+template <int VEC>
+__global__ void __launch_bounds__(256, VEC == 2 ? 2 : 1)
+dwconv3x3_gelu_bwd_roll_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ bias,
+                               const __nv_bfloat16* __restrict__ dg, __nv_bfloat16* __restrict__ dpre, float* __restrict__ dwt,
+                               float* __restrict__ dbias, int B, int H, int W, int C, int ns) {
   pdl_sync();
-  constexpr int VEC = 4;
+  constexpr int SEG = DWR_SEG, NP = VEC / 2;
+  typedef DwrVec<VEC> V;
+  typedef typename V::T RowT;
   __shared__ __align__(16) float sh[10 * 32 * VEC];   // filter taps during the main loop, block reduction afterwards
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cblk = blockIdx.x * 32 * VEC;
@@ -275,74 +353,128 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_bwd_kernel(const __nv_b
     sh[i] = (cblk + j < C) ? wt[(long long)k * C + cblk + j] : 0.f;
   }
   __syncthreads();
-  const unsigned nseg = (unsigned)(W + DWB_SEG - 1) / DWB_SEG;
-  const unsigned npos = (unsigned)B * H * nseg;
-  const unsigned p0 = blockIdx.y * (unsigned)pos_per_block;
-  unsigned p1 = p0 + pos_per_block;
-  if (p1 > npos) p1 = npos;
-  float acc[10][VEC], bs[VEC];  // acc[0..8] = dW taps, acc[9] = dbias
+  float acc[10][VEC];  // acc[0..8] = dW taps, acc[9] = dbias (unpacked at the end for the block commit)
 #pragma unroll
   for (int k = 0; k < 10; ++k)
 #pragma unroll
     for (int v = 0; v < VEC; ++v) acc[k][v] = 0.f;
   if (lane_ok) {
-    {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(bias + c0));
-      bs[0] = a.x; bs[1] = a.y; bs[2] = a.z; bs[3] = a.w;
-    }
+    p2 gw[10][NP];
+#pragma unroll
+    for (int k = 0; k < 10; ++k)
+#pragma unroll
+      for (int q = 0; q < NP; ++q) gw[k][q] = p2_splat(0.f);
+    p2 bs[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) bs[q] = p2_make(__ldg(bias + c0 + 2 * q), __ldg(bias + c0 + 2 * q + 1));
     const float* swl = sh + lane * VEC;
-    for (unsigned pos = p0 + warp; pos < p1; pos += 8) {
-      const unsigned seg = pos % nseg, t = pos / nseg;
-      const int yy = (int)(t % (unsigned)H), b = (int)(t / (unsigned)H);
-      const int x0 = (int)seg * DWB_SEG;
-      VecIO<VEC>::packed win[3][DWB_SEG + 2];
-      VecIO<VEC>::packed gin[DWB_SEG];
+    const unsigned nseg = (unsigned)(W + SEG - 1) / SEG;
+    const unsigned long long total = (unsigned long long)B * nseg * H;
+    const unsigned gwarp = blockIdx.y * 8 + warp, nwarp = gridDim.y * 8;
+    unsigned pos = (unsigned)(gwarp * total / nwarp);
+    const unsigned pos_end = (unsigned)((gwarp + 1) * total / nwarp);
+    while (pos < pos_end) {
+      const unsigned col = pos / (unsigned)H;
+      const int y0 = (int)(pos - col * (unsigned)H);
+      int y1 = y0 + (int)(pos_end - pos);
+      if (y1 > H) y1 = H;
+      pos += (unsigned)(y1 - y0);
+      const int b = (int)(col / nseg);
+      const int x0 = (int)(col % nseg) * SEG;
+      p2 a0[SEG][NP], a1[SEG][NP], a2[SEG][NP];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const int sy = yy + r - 1;
-        const bool vy = sy >= 0 && sy < H;
-        const unsigned rowoff = ((unsigned)(b * H + sy) * W) * C + c0;
+      for (int o = 0; o < SEG; ++o)
 #pragma unroll
-        for (int j = 0; j < DWB_SEG + 2; ++j) {
-          const int sx = x0 + j - 1;
-          win[r][j] = (vy && sx >= 0 && sx < W) ? VecIO<VEC>::ldp(x + (size_t)(rowoff + (unsigned)sx * C)) : VecIO<VEC>::zero();
-        }
+        for (int q = 0; q < NP; ++q) a0[o][q] = a1[o][q] = p2_splat(0.f);
+      RowT rb0[SEG + 2], rb1[SEG + 2], rb2[SEG + 2], nxt[SEG + 2], g[SEG], gn[SEG];
+#pragma unroll
+      for (int j = 0; j < SEG + 2; ++j) rb1[j] = rb2[j] = V::zero();
+#pragma unroll
+      for (int o = 0; o < SEG; ++o) g[o] = V::zero();
+      unsigned colmask = 0;
+#pragma unroll
+      for (int j = 0; j < SEG + 2; ++j) colmask |= (x0 + j - 1 >= 0 && x0 + j - 1 < W) ? (1u << j) : 0u;
+      const ptrdiff_t rstride = (ptrdiff_t)W * C;
+      const __nv_bfloat16* rp = x + ((ptrdiff_t)(b * H + y0 - 1) * W + (x0 - 1)) * C + c0;   // next input row to load
+      const __nv_bfloat16* gp = dg + ((ptrdiff_t)(b * H + y0 - 1) * W + x0) * C + c0;         // dg row of the next step's input row - 1
+      __nv_bfloat16* op = dpre + ((ptrdiff_t)(b * H + y0) * W + x0) * C + c0;                  // next dpre row to store
+#pragma unroll
+      for (int j = 0; j < SEG + 2; ++j)
+        rb0[j] = (y0 - 1 >= 0 && ((colmask >> j) & 1u)) ? __ldg(reinterpret_cast<const RowT*>(rp + (unsigned)(j * C))) : V::zero();
+      rp += rstride;
+      // one step: input row ry is in r_cur (r_p1 = row ry-1, r_p2 = row ry-2) and g = dg row ry-1; completes output row
+      // ry-1 (a_old).  Prefetched for the next step: input row ry+1 (nxt) and dg row ry (gn).
+#define DWB_DW_ROW(row, kbase)                                                                            \
+  {                                                                                                       \
+    _Pragma("unroll") for (int j = 0; j < SEG + 2; ++j) {                                                 \
+      _Pragma("unroll") for (int q = 0; q < NP; ++q) {                                                    \
+        const p2 fq = p2_from_bf16x2(V::word(row[j], q));                                                 \
+        _Pragma("unroll") for (int tt = 0; tt < 3; ++tt) {                                                \
+          const int o = j - tt;                                                                           \
+          if (o >= 0 && o < SEG) gw[(kbase) + tt][q] = p2_fma(d[o][q], fq, gw[(kbase) + tt][q]);          \
+        }                                                                                                 \
+      }                                                                                                   \
+    }                                                                                                     \
+  }
+#define DWB_STEP(a_old, a_mid, a_new, r_p2, r_p1, r_cur, ry)                                              \
+  {                                                                                                       \
+    const bool emit = (ry) - 1 >= y0 && (ry) - 1 < y1;                                                    \
+    const bool more = (ry) < y1 && (ry) + 1 < H;                                                          \
+    const bool gmore = (ry) >= y0 && (ry) < y1;                                                           \
+    _Pragma("unroll") for (int j = 0; j < SEG + 2; ++j)                                                   \
+      nxt[j] = (more && ((colmask >> j) & 1u)) ? __ldg(reinterpret_cast<const RowT*>(rp + (unsigned)(j * C))) : V::zero(); \
+    _Pragma("unroll") for (int o = 0; o < SEG; ++o)                                                       \
+      gn[o] = (gmore && ((colmask >> (o + 1)) & 1u)) ? __ldg(reinterpret_cast<const RowT*>(gp + (unsigned)(o * C))) : V::zero(); \
+    rp += rstride;                                                                                        \
+    gp += rstride;                                                                                        \
+    _Pragma("unroll") for (int o = 0; o < SEG; ++o)                                                       \
+      _Pragma("unroll") for (int q = 0; q < NP; ++q) a_new[o][q] = bs[q];                                 \
+    {                                                                                                     \
+      p2 f[SEG + 2][NP];                                                                                  \
+      _Pragma("unroll") for (int j = 0; j < SEG + 2; ++j)                                                 \
+        _Pragma("unroll") for (int q = 0; q < NP; ++q) f[j][q] = p2_from_bf16x2(V::word(r_cur[j], q));    \
+      _Pragma("unroll") for (int tt = 0; tt < 3; ++tt) {                                                  \
+        p2 wo[NP], wm[NP], wn[NP];                                                                        \
+        V::lds(swl + (6 + tt) * 32 * VEC, wo);                                                            \
+        V::lds(swl + (3 + tt) * 32 * VEC, wm);                                                            \
+        V::lds(swl + tt * 32 * VEC, wn);                                                                  \
+        _Pragma("unroll") for (int o = 0; o < SEG; ++o)                                                   \
+          _Pragma("unroll") for (int q = 0; q < NP; ++q) {                                                \
+            a_old[o][q] = p2_fma(wo[q], f[o + tt][q], a_old[o][q]);                                       \
+            a_mid[o][q] = p2_fma(wm[q], f[o + tt][q], a_mid[o][q]);                                       \
+            a_new[o][q] = p2_fma(wn[q], f[o + tt][q], a_new[o][q]);                                       \
+          }                                                                                               \
+      }                                                                                                   \
+    }                                                                                                     \
+    if (emit) {                                                                                           \
+      p2 d[SEG][NP];                                                                                      \
+      _Pragma("unroll") for (int o = 0; o < SEG; ++o) {                                                   \
+        _Pragma("unroll") for (int q = 0; q < NP; ++q) {                                                  \
+          d[o][q] = p2_mul(p2_from_bf16x2(V::word(g[o], q)), gelu_grad_pair(a_old[o][q]));                \
+          gw[9][q] = p2_add(gw[9][q], d[o][q]);                                                           \
+        }                                                                                                 \
+        if ((colmask >> (o + 1)) & 1u) *reinterpret_cast<RowT*>(op + (unsigned)(o * C)) = V::make(d[o]);  \
+      }                                                                                                   \
+      DWB_DW_ROW(r_p2, 0)                                                                                 \
+      DWB_DW_ROW(r_p1, 3)                                                                                 \
+      DWB_DW_ROW(r_cur, 6)                                                                                \
+      op += rstride;                                                                                      \
+    }                                                                                                     \
+    _Pragma("unroll") for (int j = 0; j < SEG + 2; ++j) r_p2[j] = nxt[j];                                 \
+    _Pragma("unroll") for (int o = 0; o < SEG; ++o) g[o] = gn[o];                                         \
+  }
+      for (int ry = y0 - 1; ry <= y1; ry += 3) {
+        DWB_STEP(a0, a1, a2, rb1, rb2, rb0, ry)
+        DWB_STEP(a1, a2, a0, rb2, rb0, rb1, ry + 1)
+        DWB_STEP(a2, a0, a1, rb0, rb1, rb2, ry + 2)
       }
-      const unsigned off0 = ((unsigned)(b * H + yy) * W + x0) * C + c0;
-#pragma unroll
-      for (int o = 0; o < DWB_SEG; ++o)
-        gin[o] = (x0 + o < W) ? VecIO<VEC>::ldp(dg + (size_t)(off0 + (unsigned)o * C)) : VecIO<VEC>::zero();
-#pragma unroll
-      for (int o = 0; o < DWB_SEG; ++o) {
-        if (x0 + o >= W) break;
-        float pre[VEC];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) pre[v] = bs[v];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          const float4 w4 = lds128_nohoist(swl + k * 32 * VEC);
-          float f[VEC];
-          VecIO<VEC>::unpack(win[k / 3][o + k % 3], f);
-          pre[0] = fmaf(w4.x, f[0], pre[0]); pre[1] = fmaf(w4.y, f[1], pre[1]);
-          pre[2] = fmaf(w4.z, f[2], pre[2]); pre[3] = fmaf(w4.w, f[3], pre[3]);
-        }
-        float g[VEC], d[VEC];
-        VecIO<VEC>::unpack(gin[o], g);
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-          d[v] = g[v] * gelu_grad_fast(pre[v]);
-          acc[9][v] += d[v];
-        }
-        VecIO<VEC>::st(dpre + (size_t)(off0 + (unsigned)o * C), d);
-#pragma unroll
-        for (int k = 0; k < 9; ++k) {
-          float f[VEC];
-          VecIO<VEC>::unpack(win[k / 3][o + k % 3], f);
-#pragma unroll
-          for (int v = 0; v < VEC; ++v) acc[k][v] = fmaf(d[v], f[v], acc[k][v]);
-        }
-      }
+#undef DWB_STEP
+#undef DWB_DW_ROW
     }
+#pragma unroll
+    for (int k = 0; k < 10; ++k)
+#pragma unroll
+      for (int q = 0; q < NP; ++q) p2_split(gw[k][q], acc[k][2 * q], acc[k][2 * q + 1]);
   }
   if (dwt != nullptr) {
     __syncthreads();  // everyone is done with the filter taps in sh
@@ -350,20 +482,27 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_gelu_bwd_kernel(const __nv_b
   }
 }
 
+static int g_dw_bwd_vec = 4;  // measured on B200 (tools/check_ops.py dw_perf): 4 is 5-25% faster than 2 on the MiT-b5 shapes
+void set_dw_bwd_vec(int v) { g_dw_bwd_vec = (v == 2) ? 2 : 4; }
+
 int dwconv3x3_gelu_bwd(const void* x, const float* wt, const float* bias, const void* dg, void* dpre, float* dwt,
                        float* dbias, int B, int H, int W, int C, cudaStream_t stream) {
   SFK_REQUIRE(C % 8 == 0, "dwconv3x3_gelu_bwd: C=%d must be a multiple of 8", C);
   SFK_REQUIRE((dwt == nullptr) == (dbias == nullptr), "dwconv3x3_gelu_bwd: pass both or neither of dwt / dbias");
   SFK_REQUIRE((long long)B * H * W * C < (1LL << 31), "dwconv3x3_gelu_bwd: tensor too large for 32-bit offsets");
-  const long long npos = (long long)B * H * ((W + DWB_SEG - 1) / DWB_SEG);
-  if (npos == 0) return 0;
-  dim3 grid;
-  int ppb;
-  dw_grid(C, 4, npos, grid, ppb);
-  launch_k(dwconv3x3_gelu_bwd_kernel, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, bias, (const __nv_bfloat16*)dg,
-                                                      (__nv_bfloat16*)dpre, dwt, dbias, B, H, W, C, ppb,
-           colsum_num_slots((long long)grid.x * 10 * 32 * 4, grid.y));
-  return check_launch("dwconv3x3_gelu_bwd_kernel");
+  if ((long long)B * H * W == 0) return 0;
+  if (g_dw_bwd_vec == 4) {
+    const dim3 grid = dwr_grid(B, H, W, C, 4, 1);
+    launch_k(dwconv3x3_gelu_bwd_roll_kernel<4>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, bias,
+             (const __nv_bfloat16*)dg, (__nv_bfloat16*)dpre, dwt, dbias, B, H, W, C,
+             colsum_num_slots((long long)grid.x * 10 * 32 * 4, grid.y));
+  } else {
+    const dim3 grid = dwr_grid(B, H, W, C, 2, 2);
+    launch_k(dwconv3x3_gelu_bwd_roll_kernel<2>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, bias,
+             (const __nv_bfloat16*)dg, (__nv_bfloat16*)dpre, dwt, dbias, B, H, W, C,
+             colsum_num_slots((long long)grid.x * 10 * 32 * 2, grid.y));
+  }
+  return check_launch("dwconv3x3_gelu_bwd_roll_kernel");
 }
 
 // ------------------------------------------------------------------------------------------------

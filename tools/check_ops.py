@@ -1,5 +1,5 @@
 """GPU bring-up check of the non-GEMM ops against plain PyTorch fp32. Usage: python tools/check_ops.py <group>
-groups: ln | dwconv | im2col | attn_fwd | attn_bwd | decode | loss | optim | attn_perf"""
+groups: ln | dwconv | dw_perf | im2col | attn_fwd | attn_bwd | decode | loss | optim | attn_perf"""
 import math
 import os
 import sys
@@ -51,6 +51,9 @@ def main():
     L.ensure_device()
     group = sys.argv[1]
     torch.manual_seed(0)
+    if os.environ.get("SFK_DW_BWD_VEC"):
+        L.check(L.load().sfk_set_option(b"dw_bwd_vec", int(os.environ["SFK_DW_BWD_VEC"])))
+        print("dw_bwd_vec =", os.environ["SFK_DW_BWD_VEC"], flush=True)
     allok = True
     if group == "ln":
         for rows, C in [(1000, 64), (4096, 320), (513, 512), (77, 32), (300, 160), (64, 1024)]:
@@ -82,7 +85,8 @@ def main():
             allok &= report(f"ln_bwd dgamma", dg, gr.grad, 1e-4)
             allok &= report(f"ln_bwd dbeta", db, br.grad, 1e-4)
     elif group == "dwconv":
-        for B, H, W, C in [(2, 16, 16, 128), (1, 7, 5, 64), (2, 32, 32, 256), (3, 2, 2, 1024), (2, 9, 13, 640)]:
+        for B, H, W, C in [(2, 16, 16, 128), (1, 7, 5, 64), (2, 32, 32, 256), (3, 2, 2, 1024), (2, 9, 13, 640), (1, 1, 1, 8),
+                           (1, 1, 9, 72), (1, 37, 3, 136), (16, 32, 32, 1280)]:
             x = torch.randn(B, H, W, C, device=dev).bfloat16()
             w = torch.randn(C, 1, 3, 3, device=dev) * 0.3
             bias = torch.randn(C, device=dev) * 0.1
@@ -110,6 +114,45 @@ def main():
             allok &= report("dwconv bwd dx", dx, xr.grad.permute(0, 2, 3, 1), 2e-2)
             allok &= report("dwconv bwd dw", dw, wr.grad, 2e-2)
             allok &= report("dwconv bwd db", dbias, br.grad, 2e-2)
+    elif group == "dw_perf":
+        # the four MixFFN depthwise shapes of MiT-b5 at 512x512, 16 tiles; HBM ideal = bytes moved once / measured copy rate
+        for B, H, W, C in [(16, 128, 128, 256), (16, 64, 64, 512), (16, 32, 32, 1280), (16, 16, 16, 2048)]:
+            x = torch.randn(B, H, W, C, device=dev).bfloat16()
+            w = torch.randn(C, 1, 3, 3, device=dev) * 0.3
+            bias = torch.randn(C, device=dev) * 0.1
+            wt = torch.empty(9, C, device=dev)
+            L.check(lib.sfk_dw_weight_to_tap(w.data_ptr(), wt.data_ptr(), C, L.stream_ptr()))
+            y = torch.empty_like(x)
+            dg = torch.randn(B, H, W, C, device=dev).bfloat16()
+            dpre = torch.empty_like(x)
+            dx = torch.empty_like(x)
+            dwt = torch.zeros(9, C, device=dev)
+            dbias = torch.zeros(C, device=dev)
+            db1 = torch.zeros(C, device=dev)
+
+            def fwd():
+                L.check(lib.sfk_dwconv3x3(x.data_ptr(), wt.data_ptr(), bias.data_ptr(), y.data_ptr(), B, H, W, C, 0, L.stream_ptr()))
+
+            def bwd():
+                L.check(lib.sfk_dwconv3x3_gelu_bwd(x.data_ptr(), wt.data_ptr(), bias.data_ptr(), dg.data_ptr(), dpre.data_ptr(),
+                                                   dwt.data_ptr(), dbias.data_ptr(), B, H, W, C, L.stream_ptr()))
+
+            def flip():
+                L.check(lib.sfk_dwconv3x3(dpre.data_ptr(), wt.data_ptr(), None, dx.data_ptr(), B, H, W, C, 1, L.stream_ptr()))
+
+            nbytes = x.numel() * 2
+            for name, fn, traffic in [("fwd", fwd, 2 * nbytes), ("bwd", bwd, 3 * nbytes), ("flip", flip, 2 * nbytes)]:
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(20):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                us = e0.elapsed_time(e1) / 20 * 1000
+                print(f"PERF dw {name} B{B} H{H} W{W} C{C}: {us:.1f} us  {traffic/us/1e3:.0f} GB/s algorithmic", flush=True)
     elif group == "im2col":
         for (B, H, W, C, K, S, P) in [(2, 16, 16, 64, 3, 2, 1), (2, 8, 8, 32, 8, 8, 0), (1, 12, 20, 128, 2, 2, 0), (2, 4, 4, 160, 3, 2, 1)]:
             x = torch.randn(B, H, W, C, device=dev).bfloat16()
