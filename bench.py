@@ -243,7 +243,7 @@ def run_sfk(args):
         torch.cuda.synchronize()
 
     lib = L.load()
-    for opt in ("gemm_occ2", "gemm_cluster2"):
+    for opt in ("gemm_occ2", "gemm_cluster2", "dw_bwd_vec"):
         if os.environ.get("SFK_" + opt.upper()) is not None:
             lib.sfk_set_option(opt.encode(), int(os.environ["SFK_" + opt.upper()]))
     imgs_per_step = (N_LABELED + N_UNLABELED) * world

@@ -54,6 +54,44 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2: two lanes per issue slot) ----
+typedef unsigned long long p2;  // two packed fp32 (lo, hi)
+__device__ __forceinline__ p2 p2_make(float lo, float hi) {
+  p2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ p2 p2_make_u(uint32_t lo, uint32_t hi) {
+  p2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void p2_split(p2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void p2_split_u(p2 v, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ p2 p2_splat(float a) { return p2_make(a, a); }
+__device__ __forceinline__ p2 p2_fma(p2 a, p2 b, p2 c) {
+  p2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ p2 p2_mul(p2 a, p2 b) {
+  p2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ p2 p2_add(p2 a, p2 b) {
+  p2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// bf16x2 word -> packed fp32 pair (exact): lo = u << 16, hi = u & 0xffff0000
+__device__ __forceinline__ p2 p2_from_bf16x2(uint32_t u) { return p2_make_u(u << 16, u & 0xffff0000u); }
+__device__ __forceinline__ uint32_t p2_to_bf16x2(p2 v) {
+  float lo, hi;
+  p2_split(v, lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+
 // exact-erf GELU (F.gelu default) and its derivative
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
@@ -169,6 +207,14 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t saddr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr) : "memory");
+  return v;
 }
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");

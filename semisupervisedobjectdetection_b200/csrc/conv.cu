@@ -67,42 +67,6 @@ __device__ __forceinline__ void dw_block_commit(float (&acc)[NV][VEC], float* sh
 //   * the next input row is prefetched (6 independent 8-byte loads) while the current one is consumed.
 // A warp = 32 channel quads of one (image, row chunk, 4-pixel segment): every load/store instruction covers 256 contiguous bytes.
 // ------------------------------------------------------------------------------------------------
-typedef unsigned long long p2;  // two packed fp32 (lo, hi)
-__device__ __forceinline__ p2 p2_make(float lo, float hi) {
-  p2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ p2 p2_make_u(uint32_t lo, uint32_t hi) {
-  p2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
-  return r;
-}
-__device__ __forceinline__ void p2_split(p2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ void p2_split_u(p2 v, uint32_t& lo, uint32_t& hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
-__device__ __forceinline__ p2 p2_splat(float a) { return p2_make(a, a); }
-__device__ __forceinline__ p2 p2_fma(p2 a, p2 b, p2 c) {
-  p2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ p2 p2_mul(p2 a, p2 b) {
-  p2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ p2 p2_add(p2 a, p2 b) {
-  p2 d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-// bf16x2 word -> packed fp32 pair (exact): lo = u << 16, hi = u & 0xffff0000
-__device__ __forceinline__ p2 p2_from_bf16x2(uint32_t u) { return p2_make_u(u << 16, u & 0xffff0000u); }
-__device__ __forceinline__ uint32_t p2_to_bf16x2(p2 v) {
-  float lo, hi;
-  p2_split(v, lo, hi);
-  return pack_bf16x2(lo, hi);
-}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

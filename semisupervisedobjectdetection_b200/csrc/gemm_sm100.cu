@@ -26,6 +26,10 @@ static constexpr int MAX_BLOCK_N = 256;
 static constexpr int TMEM_COLS = 512;  // 2 accumulator buffers x 256 fp32 columns
 static constexpr int GEMM_THREADS = 192;
 static constexpr int MAX_STAGES = 8;
+// behind the barrier block: the current tile's bias slice (MAX_BLOCK_N floats), staged by the epilogue before it waits for
+// the accumulator
+static constexpr uint32_t EPI_BIAS_OFF = 16 * MAX_STAGES + 64;
+static constexpr uint32_t EPI_BIAS_BYTES = 256 * 4;
 
 // runtime switch (sfk_set_option("gemm_cluster2", 0|1)); measured neutral on B200 for this workload (profiles/), default off
 int g_gemm_cluster2 = 0;
@@ -241,14 +245,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const int tile = unit / p.splits;
       const int n_blk = tile % p.n_tiles;
       const int m_blk = p.cluster2 ? 2 * (tile / p.n_tiles) + (int)crank : tile / p.n_tiles;
+      const int n0 = n_blk * p.block_n;
+      // ncu: the bias LDGs issued after the TMEM load were the largest stall of the epilogue.  The tile's bias slice goes to
+      // shared memory while the accumulator is still being produced; published by the epilogue-only named barrier below
+      // and released for the next tile by the one at the end of the tile.
+      if (p.bias != nullptr && warp == 2) {
+        float* sbias_gen = reinterpret_cast<float*>(smem_gen + bars_off + EPI_BIAS_OFF);
+        for (int j = lane; j < p.block_n; j += 32) sbias_gen[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+      }
+      const uint32_t sbias = smem_base + bars_off + EPI_BIAS_OFF;
       mbar_wait(bar_tfull + 8 * acc, acc_phase[acc]);
       tc_fence_after();
+      if (p.bias != nullptr) asm volatile("bar.sync 1, 128;" ::: "memory");
       if (threadIdx.x == 64 && unit == unit0) GEMM_TRACE(5);
       const long long row = (long long)m_blk * BLOCK_M + q * 32 + lane;
       const bool row_ok = row < p.M;
       float rscale = p.alpha;
       if (p.row_scale != nullptr && row_ok) rscale *= p.row_scale[row / p.rows_per_scale];
-      const int n0 = n_blk * p.block_n;
       const long long orow = gemm_map_row(row, p.out_map);
       for (int c = 0; c < p.block_n; c += 32) {
         uint32_t r[32];
@@ -262,15 +275,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         const bool full_chunk = (col0 + 32 <= p.N);
         if (p.bias != nullptr) {
-          if (full_chunk) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          } else {
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) v[j] += __ldg(p.bias + col0 + j);
+          for (int j = 0; j < 32; j += 4) {
+            const uint4 b4 = ld_shared_v4(sbias + (uint32_t)(c + j) * 4);   // broadcast read (zeros past N)
+            v[j] += __uint_as_float(b4.x); v[j + 1] += __uint_as_float(b4.y);
+            v[j + 2] += __uint_as_float(b4.z); v[j + 3] += __uint_as_float(b4.w);
           }
         }
 #pragma unroll
@@ -333,6 +342,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       if (threadIdx.x == 64 && unit == unit0) GEMM_TRACE(6);
+      if (p.bias != nullptr) asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with this tile's bias slice
       acc_phase[acc] ^= 1;
       acc ^= 1;
     }
@@ -441,7 +451,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   SFK_REQUIRE(splits == 1 || g.atomic_add, "gemm: split-K requires atomic accumulation");
   p.splits = splits;
   p.stage_bytes = BLOCK_M * BLOCK_K * 2 + p.block_n * BLOCK_K * 2;
-  const int smem_budget = (p.tmem_cols == 256 ? 110 * 1024 : 227 * 1024) - 2048;
+  const int smem_budget = (p.tmem_cols == 256 ? 110 * 1024 : 227 * 1024) - 2048 - (int)EPI_BIAS_BYTES;
   int stages = smem_budget / (int)p.stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages > p.k_blocks + 1 && p.tmem_cols == 256) stages = p.k_blocks + 1;
@@ -474,7 +484,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   else         rc = make_tmap_2d_bf16(&tb, g.b, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb * 2, 64, BLOCK_K);
   if (rc) return rc;
 
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 16 * MAX_STAGES + 64 + 1024;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + EPI_BIAS_OFF + EPI_BIAS_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
