@@ -306,7 +306,7 @@ struct AttBwdParams {
 };
 
 template <int D>
-__global__ void __launch_bounds__(160, 1)
+__global__ void __launch_bounds__(288, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
                 const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                 const AttBwdParams p) {
@@ -339,18 +339,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const int tile0 = qsplit * p.q_tiles_per_cta;
   const int ntiles = min(p.q_tiles_per_cta, p.q_tiles - tile0);
 
-  if (threadIdx.x == 128) {
+  if (threadIdx.x == 256) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
     mbar_init(b_kvfull, 1);
     mbar_init(b_qfull, 1); mbar_init(b_qfull + 8, 1);
-    mbar_init(b_spfull, 1); mbar_init(b_pdready, 128); mbar_init(b_dqfull, 1);
+    mbar_init(b_spfull, 1); mbar_init(b_pdready, 256); mbar_init(b_dqfull, 1);
     mbar_init(b_tilefree, 1); mbar_init(b_tilefree + 8, 1);
-    mbar_init(b_dqfree, 128);
-    mbar_init(b_statsfree, 128); mbar_init(b_statsfree + 8, 128);
+    mbar_init(b_dqfree, 256);
+    mbar_init(b_statsfree, 256); mbar_init(b_statsfree + 8, 256);
     mbar_init(b_final, 1);
     mbar_fence_init();
   }
-  if (warp == 4) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   pdl_wait();  // setup above overlaps the previous kernel's tail
   tc_fence_before();
   __syncthreads();
@@ -358,7 +358,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t tmem = *tmem_slot_gen;
   const uint32_t tST = tmem, tDPT = tmem + 128, tDV = tmem + 256, tDK = tmem + 256 + D, tDQ = tmem + 256 + 2 * D;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0 && ntiles > 0) {
       // ---------------- control thread ----------------
       const uint32_t idesc_s = umma_idesc_bf16(128, ATT_BM, 0, 0);   // S^T / dP^T : [kv x q]
@@ -426,9 +426,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
   } else if (ntiles > 0) {
-    // ---------------- 128 math threads: thread r owns K/V row kv0+r (S^T, dP^T, dK, dV) and query row r of dQ ----------------
-    const int r = threadIdx.x;
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    // ---------------- 256 math threads: threads r and r + 128 share K/V row kv0+r (S^T, dP^T, dK, dV) and query row r of
+    // dQ; each takes one half of the columns (two warps per TMEM lane quadrant) ----------------
+    const int r = threadIdx.x & 127;
+    const int hhalf = threadIdx.x >> 7;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const bool kv_ok = (kv0 + r) < p.Tk;
     const long long stat_base = ((long long)batch * p.heads + head) * p.T;
     for (int i = 0; i < ntiles; ++i) {
@@ -439,14 +441,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (i >= 2) mbar_wait(b_statsfree + 8 * buf, ((i - 2) >> 1) & 1);
       {
         const int t = t0 + r;
-        stats[buf * 256 + r] = t < p.T ? p.lse[stat_base + t] : INFINITY;
-        stats[buf * 256 + 128 + r] = t < p.T ? p.delta[stat_base + t] : 0.f;
+        if (hhalf == 0) stats[buf * 256 + r] = t < p.T ? p.lse[stat_base + t] : INFINITY;
+        else stats[buf * 256 + 128 + r] = t < p.T ? p.delta[stat_base + t] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       mbar_wait(b_spfull, ph);
       tc_fence_after();
 #pragma unroll 1
-      for (int cc = 0; cc < ATT_BM; cc += 32) {
+      for (int cc = hhalf * (ATT_BM / 2); cc < (hhalf + 1) * (ATT_BM / 2); cc += 32) {
         uint32_t s[32], dp[32];
         tmem_ld_32x32(tST + lane_base + cc, s);
         tmem_ld_32x32(tDPT + lane_base + cc, dp);
@@ -484,7 +486,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         const int t = t0 + r;
         float* dst = p.dq + batch * p.dq_batch_stride + (long long)t * p.ld_dq + head * D;
 #pragma unroll
-        for (int cc = 0; cc < D; cc += 32) {
+        for (int cc = hhalf * 32; cc < D; cc += 64) {
           uint32_t v[32];
           tmem_ld_32x32(tDQ + lane_base + cc, v);
           tmem_ld_wait();
@@ -506,7 +508,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       float* dkp = p.dk + batch * p.dkv_batch_stride + (long long)(kv0 + r) * p.ld_dkv + head * D;
       float* dvp = p.dv + batch * p.dkv_batch_stride + (long long)(kv0 + r) * p.ld_dkv + head * D;
 #pragma unroll
-      for (int cc = 0; cc < D; cc += 32) {
+      for (int cc = hhalf * 32; cc < D; cc += 64) {
         uint32_t a[32], b[32];
         tmem_ld_32x32(tDK + lane_base + cc, a);
         tmem_ld_32x32(tDV + lane_base + cc, b);
@@ -525,7 +527,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+  if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 template <int D>
@@ -577,7 +579,7 @@ static int attn_bwd_launch(const AttentionBwdDesc& a, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid(kv_blocks * qsplits, a.heads, a.B);
-  launch_k(attn_bwd_kernel<D>, dim3(grid), dim3(160), smem, stream, tq, tdo, tk, tv, p);
+  launch_k(attn_bwd_kernel<D>, dim3(grid), dim3(288), smem, stream, tq, tdo, tk, tv, p);
   return check_launch("attn_bwd_kernel");
 }
 
