@@ -45,8 +45,8 @@ int sfk_profile_gemm_end(double* total_ms, double* total_flops, long long* launc
 /* After sfk_profile_gemm_end: one CSV line per profiled GEMM launch (M,N,K,flags,microseconds). */
 int sfk_profile_gemm_dump(const char* path);
 
-/* Tuning switches: "gemm_cluster2" (default 0; measured neutral) = launch GEMMs as 2-CTA clusters that multicast the
- * shared B tiles; "gemm_occ2" (default 1) = two co-resident CTAs per SM for K <= 512 GEMMs; "dw_bwd_vec" (2 | 4, default 4)
+/* Tuning switches: "gemm_cluster2" = CTA-pair (tcgen05 cta_group::2, 256-row MMA, B split across the pair) GEMM tiles:
+ * 0 never, 1 (default) for large problems (M*N*K >= 1e11, K >= 1024), 2 whenever the shape allows; "gemm_occ2" (default 1) = two co-resident CTAs per SM for K <= 512 GEMMs; "dw_bwd_vec" (2 | 4, default 4)
  * = channels per thread of the depthwise-conv backward kernel. */
 int sfk_set_option(const char* name, int value);
 

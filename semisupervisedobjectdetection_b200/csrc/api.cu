@@ -11,7 +11,7 @@ namespace sfk { extern int g_gemm_cluster2; extern int g_gemm_occ2; extern unsig
 extern "C" {
 
 int sfk_set_option(const char* name, int value) {
-  if (name != nullptr && std::string(name) == "gemm_cluster2") { sfk::g_gemm_cluster2 = value ? 1 : 0; return 0; }
+  if (name != nullptr && std::string(name) == "gemm_cluster2") { sfk::g_gemm_cluster2 = value < 0 ? 0 : (value > 2 ? 2 : value); return 0; }
   if (name != nullptr && std::string(name) == "gemm_occ2") { sfk::g_gemm_occ2 = value ? 1 : 0; return 0; }
   if (name != nullptr && std::string(name) == "dw_bwd_vec") { sfk::set_dw_bwd_vec(value); return 0; }
   sfk::set_error("sfk_set_option: unknown option");

@@ -31,8 +31,14 @@ static constexpr int MAX_STAGES = 8;
 static constexpr uint32_t EPI_BIAS_OFF = 16 * MAX_STAGES + 64;
 static constexpr uint32_t EPI_BIAS_BYTES = 256 * 4;
 
-// runtime switch (sfk_set_option("gemm_cluster2", 0|1)); measured neutral on B200 for this workload (profiles/), default off
-int g_gemm_cluster2 = 0;
+// runtime switch (sfk_set_option("gemm_cluster2", 0|1|2)): CTA pairs (cta_group::2).  Two CTAs of a 2-cluster drive one
+// 256 x N MMA per k-step; each loads its own 128 A rows and HALF of the B tile, so the L2 -> shared-memory stream per
+// output element drops by a third and each SM's shared memory takes half of B.
+//   0 = never, 1 = large problems only (default), 2 = whenever the shape allows.
+// Measured on B200 inside the MiT-b5 step (per-launch CUDA events, profiles/): the three decode-head GEMMs
+// (262144 x 768 x 3072 and its two gradients) gain 12-15 % (1.24 -> 1.05 ms); every K <= 1280 / M <= 65536 shape LOSES
+// 5-25 % (half as many schedulable units, no two-CTAs-per-SM mode, TMEM taken after the grid dependency resolves).
+int g_gemm_cluster2 = 1;
 // small-K GEMMs: 2 resident CTAs per SM (<= 110 KB smem, 256 TMEM columns each) so one CTA's epilogue / pipeline fill
 // overlaps the other's main loop
 int g_gemm_occ2 = 1;
@@ -75,7 +81,7 @@ struct GemmKernelParams {
   int relu;
   unsigned long long* trace;
   int tmem_cols;   // 512 (1 CTA / SM) or 256 (2 CTAs / SM); accumulator buffer a lives at column a * tmem_cols / 2
-  int cluster2;  // launched as 2-CTA clusters: the pair works on two adjacent row tiles and shares (multicasts) the B tiles
+  int cluster2;  // CTA-pair mode: launched as 2-CTA clusters, one cta_group::2 MMA per pair (rows 256, B split across the pair)
 };
 
 __device__ __forceinline__ long long gemm_map_row(long long row, const RowMap& m) {
@@ -89,6 +95,8 @@ __device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, fl
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// PAIR = 1: CTA-pair kernel (must be launched in 2-CTA clusters: it contains cta_group::2 instructions)
+template <int PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 2)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          const GemmKernelParams p) {
@@ -117,36 +125,40 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     tma_prefetch_desc(&tmap_b);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, p.cluster2 ? 2 : 1);  // a multicast stage is free once BOTH CTAs' MMAs have retired it
+      mbar_init(bar_empty + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4);
+      mbar_init(bar_tempty + 8 * a, PAIR ? 8 : 4);   // pair: both CTAs' epilogue warps report to the leader
     }
     mbar_fence_init();
   }
+  // pair kernels take their (pair-collective) TMEM allocation only after the grid dependency has resolved: a dependent
+  // launched early under PDL that sits on both SMs' tensor memory while it waits was observed to deadlock against
+  // kernels of other streams
+  if (PAIR) pdl_wait();
   if (warp == 1) {
-    tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc_pair(tmem_slot, (uint32_t)p.tmem_cols); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols); tmem_relinquish(); }
   }
   // barrier init / TMEM allocation / descriptor prefetch above overlap the previous kernel's tail (PDL);
   // nothing before this point touches global memory produced by it.
-  pdl_wait();
+  if (!PAIR) pdl_wait();
   tc_fence_before();
   __syncthreads();
-  if (p.cluster2) cluster_sync_all();  // peer barriers are initialised before any multicast / remote arrive targets them
+  if (PAIR) cluster_sync_all();  // peer barriers are initialised before any remote arrive / commit targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
   if (threadIdx.x == 0) GEMM_TRACE(1);
 
   // work units: (row tile | row-tile pair, column tile, k split); in cluster mode the two CTAs of a pair walk the same
   // unit sequence in lockstep, CTA rank r owning row tile 2*pair + r
-  const uint32_t crank = p.cluster2 ? cluster_ctarank() : 0u;
-  const int m_groups = p.cluster2 ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const int m_groups = PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles;
   const int tiles_mn = m_groups * p.n_tiles;
   const int total_units = tiles_mn * p.splits;
-  const int unit0 = p.cluster2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int unit_stride = p.cluster2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -157,24 +169,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int split = unit % p.splits;
         const int tile = unit / p.splits;
         const int n_blk = tile % p.n_tiles;
-        const int m_blk = p.cluster2 ? 2 * (tile / p.n_tiles) + (int)crank : tile / p.n_tiles;
+        const int m_blk = PAIR ? 2 * (tile / p.n_tiles) + (int)crank : tile / p.n_tiles;
         const int kb0 = (int)(((long long)split * p.k_blocks) / p.splits);
         const int kb1 = (int)(((long long)(split + 1) * p.k_blocks) / p.splits);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_base + stage * p.stage_bytes;
           const uint32_t sb = sa + a_bytes;
-          const uint32_t full = bar_full + 8 * stage;
-          mbar_arrive_expect_tx(full, p.stage_bytes);
-          if (unit == unit0 && kb == kb0) GEMM_TRACE(2);
-          if (!p.a_mn) {
-            tma_load_2d(sa, &tmap_a, full, kb * BLOCK_K, m_blk * BLOCK_M);
-          } else {
-            // stored [K, M] (M contiguous): 2 boxes of [64 m, 64 k]
-            tma_load_2d(sa, &tmap_a, full, m_blk * BLOCK_M, kb * BLOCK_K);
-            tma_load_2d(sa + 8192, &tmap_a, full, m_blk * BLOCK_M + 64, kb * BLOCK_K);
-          }
-          if (!p.cluster2) {
+          if (!PAIR) {
+            const uint32_t full = bar_full + 8 * stage;
+            mbar_arrive_expect_tx(full, p.stage_bytes);
+            if (unit == unit0 && kb == kb0) GEMM_TRACE(2);
+            if (!p.a_mn) {
+              tma_load_2d(sa, &tmap_a, full, kb * BLOCK_K, m_blk * BLOCK_M);
+            } else {
+              // stored [K, M] (M contiguous): 2 boxes of [64 m, 64 k]
+              tma_load_2d(sa, &tmap_a, full, m_blk * BLOCK_M, kb * BLOCK_K);
+              tma_load_2d(sa + 8192, &tmap_a, full, m_blk * BLOCK_M + 64, kb * BLOCK_K);
+            }
             if (!p.b_mn) {
               tma_load_2d(sb, &tmap_b, full, kb * BLOCK_K, n_blk * p.block_n);
             } else {
@@ -182,13 +194,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 tma_load_2d(sb + j * 8192, &tmap_b, full, n_blk * p.block_n + j * 64, kb * BLOCK_K);
             }
           } else {
-            // each CTA fetches half of the B tile and multicasts it into both CTAs' stage (same offsets, own barriers)
-            if (!p.b_mn) {
-              const int half = p.block_n / 2;   // tmap_b box is [64, block_n / 2] rows in cluster mode
-              tma_load_2d_mc(sb + crank * half * 128, &tmap_b, full, kb * BLOCK_K, n_blk * p.block_n + (int)crank * half, 3);
+            // pair: both CTAs' bytes are counted by the LEADER's full barrier (the MMA issuer lives there); this CTA
+            // brings its own 128 A rows and its half of the B tile
+            const uint32_t full = mapa_shared(bar_full + 8 * stage, 0);
+            if (crank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * p.stage_bytes);
+            if (unit == unit0 && kb == kb0) GEMM_TRACE(2);
+            if (!p.a_mn) {
+              tma_load_2d_pair(sa, &tmap_a, full, kb * BLOCK_K, m_blk * BLOCK_M);
             } else {
-              for (int j = (int)crank; j < p.block_n / 64; j += 2)
-                tma_load_2d_mc(sb + j * 8192, &tmap_b, full, n_blk * p.block_n + j * 64, kb * BLOCK_K, 3);
+              tma_load_2d_pair(sa, &tmap_a, full, m_blk * BLOCK_M, kb * BLOCK_K);
+              tma_load_2d_pair(sa + 8192, &tmap_a, full, m_blk * BLOCK_M + 64, kb * BLOCK_K);
+            }
+            const int half = p.block_n / 2;
+            const int nb0 = n_blk * p.block_n + (int)crank * half;
+            if (!p.b_mn) {
+              tma_load_2d_pair(sb, &tmap_b, full, kb * BLOCK_K, nb0);   // box = [64 k, block_n / 2 rows]
+            } else {
+              for (int j = 0; j < half / 64; ++j)
+                tma_load_2d_pair(sb + j * 8192, &tmap_b, full, nb0 + j * 64, kb * BLOCK_K);
             }
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -196,13 +219,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = umma_idesc_bf16(BLOCK_M, p.block_n, p.a_mn, p.b_mn);
+    // ===================== MMA issuer (pair mode: the leader CTA issues for both) =====================
+    const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, p.block_n, p.a_mn, p.b_mn);
+    const bool issuer = !PAIR || crank == 0;
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase[2] = {0, 0};
-    for (int unit = unit0; unit < total_units; unit += unit_stride) {
+    for (int unit = unit0; issuer && unit < total_units; unit += unit_stride) {
       const int split = unit % p.splits;
       const int kb0 = (int)(((long long)split * p.k_blocks) / p.splits);
       const int kb1 = (int)(((long long)(split + 1) * p.k_blocks) / p.splits);
@@ -223,11 +247,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                                           : umma_smem_desc(sa + kk * 32, 16, 1024);
             const uint64_t bdesc = p.b_mn ? umma_smem_desc(sb + kk * 2048, 8192, 1024)
                                           : umma_smem_desc(sb + kk * 32, 16, 1024);
-            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            if (PAIR) umma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
-          if (p.cluster2) umma_commit_mc(bar_empty + 8 * stage, 3);  // tell both producers of the pair
-          else umma_commit(bar_empty + 8 * stage);              // smem slot reusable once these MMAs retire
-          if (kb == kb1 - 1) umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+          if (PAIR) {
+            umma_commit_pair(bar_empty + 8 * stage, 3);                       // both producers of the pair
+            if (kb == kb1 - 1) umma_commit_pair(bar_tfull + 8 * acc, 3);      // both epilogues
+          } else {
+            umma_commit(bar_empty + 8 * stage);                   // smem slot reusable once these MMAs retire
+            if (kb == kb1 - 1) umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+          }
           if (kb == kb1 - 1 && unit == unit0) GEMM_TRACE(4);
         }
         __syncwarp();
@@ -244,7 +273,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     for (int unit = unit0; unit < total_units; unit += unit_stride) {
       const int tile = unit / p.splits;
       const int n_blk = tile % p.n_tiles;
-      const int m_blk = p.cluster2 ? 2 * (tile / p.n_tiles) + (int)crank : tile / p.n_tiles;
+      const int m_blk = PAIR ? 2 * (tile / p.n_tiles) + (int)crank : tile / p.n_tiles;
       const int n0 = n_blk * p.block_n;
       // ncu: the bias LDGs issued after the TMEM load were the largest stall of the epilogue.  The tile's bias slice goes to
       // shared memory while the accumulator is still being produced; published by the epilogue-only named barrier below
@@ -340,7 +369,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(mapa_shared(bar_tempty + 8 * acc, 0));   // the leader's MMA issuer waits for both CTAs
+        else mbar_arrive(bar_tempty + 8 * acc);
+      }
       if (threadIdx.x == 64 && unit == unit0) GEMM_TRACE(6);
       if (p.bias != nullptr) asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with this tile's bias slice
       acc_phase[acc] ^= 1;
@@ -351,10 +383,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) GEMM_TRACE(7);
-  if (p.cluster2) cluster_sync_all();  // the peer may still multicast into our smem / arrive on our barriers until it is done
+  if (PAIR) cluster_sync_all();  // the peer may still read our smem / arrive on our barriers until it is done
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, (uint32_t)p.tmem_cols);
+    else tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
 
@@ -393,6 +426,30 @@ static int pick_block_n(int N, int b_mn, int M, int atomic_add) {
   return best;
 }
 
+// CTA-pair mode: a pair owns 256 rows; per k-block each CTA streams (BLOCK_M + bn / 2) operand rows.  Returns 0 when no
+// candidate covers N with <= 25 % padding (then the single-CTA kernel is used).
+static int pick_block_n_pair(int N, int b_mn, int M, int atomic_add) {
+  const int cands_k[] = {256, 224, 192, 160, 128, 96, 64};
+  const int cands_mn[] = {256, 128};
+  const int* cands = b_mn ? cands_mn : cands_k;
+  const int nc = b_mn ? 2 : 7;
+  const int m_pairs = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+  const int slots = num_sms() / 2;
+  int best = 0;
+  double best_cost = 1e30;
+  for (int i = 0; i < nc; ++i) {
+    const int bn = cands[i];
+    const int n_tiles = (N + bn - 1) / bn;
+    if ((double)n_tiles * bn > 1.25 * N) continue;
+    if (atomic_add) return bn;   // split-K fills the machine: widest acceptable tile
+    const long long tiles = (long long)m_pairs * n_tiles;
+    const long long waves = (tiles + slots - 1) / slots;
+    const double cost = (double)waves * (BLOCK_M + bn / 2 + 24);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   SFK_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
   SFK_REQUIRE(g.a != nullptr && g.b != nullptr && g.out != nullptr, "gemm: null pointer");
@@ -413,9 +470,20 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.a_mn = g.a_mn ? 1 : 0;
   p.b_mn = g.b_mn ? 1 : 0;
   p.k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
+  // CTA pairs (cta_group::2) when enabled and the shape allows it
+  int pair_bn = 0;
+  const bool pair_wanted = g_gemm_cluster2 == 2 || (g_gemm_cluster2 == 1 && (double)g.M * g.N * g.K >= 1.0e11 && g.K >= 1024);
+  if (pair_wanted && g.M > BLOCK_M && (num_sms() % 2 == 0)) {
+    if (g.block_n > 0) {
+      if (g.block_n % 32 == 0 && (!p.b_mn || g.block_n % 128 == 0)) pair_bn = g.block_n;
+    } else {
+      pair_bn = pick_block_n_pair(g.N, p.b_mn, g.M, g.atomic_add);
+    }
+  }
+  p.cluster2 = pair_bn > 0 ? 1 : 0;
   // latency-bound regime (few k-blocks per tile): prefer two co-resident CTAs per SM over wide tiles
-  const bool occ2 = g_gemm_occ2 && g.block_n <= 0 && !g.atomic_add && p.k_blocks <= 8 && g.N >= 64;
-  p.block_n = g.block_n > 0 ? g.block_n : pick_block_n(g.N, p.b_mn, g.M, g.atomic_add);
+  const bool occ2 = !p.cluster2 && g_gemm_occ2 && g.block_n <= 0 && !g.atomic_add && p.k_blocks <= 8 && g.N >= 64;
+  p.block_n = pair_bn > 0 ? pair_bn : (g.block_n > 0 ? g.block_n : pick_block_n(g.N, p.b_mn, g.M, g.atomic_add));
   if (occ2 && p.block_n > 128) {
     // widest tile <= 128 columns with the least padding
     const int c_k[] = {128, 96, 64}, c_mn[] = {128, 64};
@@ -438,8 +506,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   if (splits <= 0) {
     splits = 1;
     if (g.atomic_add) {
-      const long long tiles = (long long)p.m_tiles * p.n_tiles;
-      const int sms = num_sms();
+      const long long tiles = (long long)(p.cluster2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
+      const int sms = p.cluster2 ? num_sms() / 2 : num_sms();   // schedulable units: CTAs or CTA pairs
       if (tiles < 2 * sms) splits = (int)((2LL * sms + tiles - 1) / tiles);
       // keep at least 8 k-blocks per split so the pipeline has something to overlap
       const int max_splits = p.k_blocks >= 8 ? p.k_blocks / 8 : 1;
@@ -450,7 +518,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   if (splits < 1) splits = 1;
   SFK_REQUIRE(splits == 1 || g.atomic_add, "gemm: split-K requires atomic accumulation");
   p.splits = splits;
-  p.stage_bytes = BLOCK_M * BLOCK_K * 2 + p.block_n * BLOCK_K * 2;
+  p.stage_bytes = BLOCK_M * BLOCK_K * 2 + (p.cluster2 ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;   // per CTA
   const int smem_budget = (p.tmem_cols == 256 ? 110 * 1024 : 227 * 1024) - 2048 - (int)EPI_BIAS_BYTES;
   int stages = smem_budget / (int)p.stage_bytes;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -471,8 +539,6 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.atomic_add = g.atomic_add;
   p.relu = g.relu;
   p.trace = g_gemm_trace;
-  // 2-CTA clusters sharing B through TMA multicast: halves the dominant L2 -> smem stream of these small-K GEMMs
-  p.cluster2 = (g_gemm_cluster2 && p.m_tiles >= 2 && (num_sms() % 2 == 0)) ? 1 : 0;
 
   CUtensorMap ta, tb;
   int rc;
@@ -487,7 +553,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   const size_t smem = (size_t)p.stages * p.stage_bytes + EPI_BIAS_OFF + EPI_BIAS_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     SFK_REQUIRE(e == cudaSuccess, "gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -509,17 +576,17 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    attr[1].id = cudaLaunchAttributeClusterDimension;
-    attr[1].val.clusterDim.x = 2;
-    attr[1].val.clusterDim.y = 1;
-    attr[1].val.clusterDim.z = 1;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    (void)cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel, ta, tb, p);
+    (void)cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<1>, ta, tb, p);
   } else {
-    launch_k(gemm_bf16_tcgen05_kernel, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, p);
+    launch_k(gemm_bf16_tcgen05_kernel<0>, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, p);
   }
   prof_gemm_end(stream);
   return check_launch("gemm_bf16_tcgen05_kernel");

@@ -10,9 +10,9 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run(script, group, timeout=600):
+def _run(script, group, timeout=600, env=None):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", script), group], cwd=ROOT, capture_output=True, text=True,
-                       timeout=timeout)
+                       timeout=timeout, env=dict(os.environ, **(env or {})))
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-40:])
     assert r.returncode == 0 and "ALLOK" in r.stdout, f"{script} {group} failed:\n{tail}"
 
@@ -21,6 +21,13 @@ def _run(script, group, timeout=600):
 @pytest.mark.parametrize("group", ["nt", "nn", "tn", "epi"])
 def test_gemm_tcgen05_layouts(group):
     _run("check_gemm.py", group)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("group", ["nt", "nn", "tn", "epi"])
+def test_gemm_cta_pair_layouts(group):
+    """Same cases through the CTA-pair (tcgen05 cta_group::2, 2-CTA cluster) kernel, forced on for every eligible shape."""
+    _run("check_gemm.py", group, env={"SFK_GEMM_CLUSTER2": "1"})
 
 
 @pytest.mark.gpu

@@ -37,7 +37,7 @@ def report(name, got, ref):
 def main():
     group = sys.argv[1]
     if os.environ.get("SFK_GEMM_CLUSTER2") is not None:
-        L.check(L.load().sfk_set_option(b"gemm_cluster2", int(os.environ["SFK_GEMM_CLUSTER2"])))
+        L.check(L.load().sfk_set_option(b"gemm_cluster2", 2 * int(os.environ["SFK_GEMM_CLUSTER2"])))  # 1 -> "whenever possible"
         print("gemm_cluster2 =", os.environ["SFK_GEMM_CLUSTER2"], flush=True)
     if os.environ.get("SFK_GEMM_OCC2") is not None:
         L.check(L.load().sfk_set_option(b"gemm_occ2", int(os.environ["SFK_GEMM_OCC2"])))
