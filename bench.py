@@ -255,6 +255,7 @@ def run_sfk(args):
     if sampler:
         sampler.start()
     launches0 = lib.sfk_launch_count()
+    mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     prof = {}
     e0.record()
@@ -266,6 +267,7 @@ def run_sfk(args):
     barrier()
     ms = e0.elapsed_time(e1) / args.steps
     launches = lib.sfk_launch_count() - launches0
+    device_mallocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs0   # cudaMalloc calls inside the timed region
     # ---- roofline leg: ONE extra step (outside the timed region) with the side streams off, so that the CUDA events around
     # each GEMM launch time that kernel alone on the GPU instead of a kernel sharing SMs with the teacher / wgrad streams ----
     ops.WGRAD_OVERLAP = False
@@ -325,6 +327,7 @@ def run_sfk(args):
                 "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),
         "cpu_enqueue_ms_per_step": cpu_enqueue_ms,
+        "device_mallocs_in_timed_region": int(device_mallocs),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": achieved_tf, "peak": pk["tf_sustained"],
                      "unit": "TFLOP/s", "frac": (achieved_tf / pk["tf_sustained"]) if achieved_tf else None, "traffic": None,

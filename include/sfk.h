@@ -161,6 +161,10 @@ int sfk_upsample_concat(const void* in, void* out, int B, int h, int w, int C, i
                         sfk_stream_t stream);
 int sfk_upsample_concat_bwd(const void* dout, void* din, int B, int h, int w, int C, int H, int W, long long ld_out,
                             int ch_off, sfk_stream_t stream);
+/* Folded decode head (bilinear upsampling commutes with the 1x1 convs of MS:769-775):
+ * out[b,y,x,:] = z0[b,y,x,:] + sum_i bilinear(z_i)[b,y,x,:] + bias[:]; z0, out: bf16 [B,H,W,C]; z_i: bf16 [B,h_i,w_i,C]; bias f32 [C] */
+int sfk_upsample_add4(const void* z0, const void* z1, int h1, int w1, const void* z2, int h2, int w2, const void* z3, int h3,
+                      int w3, const float* bias, void* out, int B, int H, int W, int C, sfk_stream_t stream);
 /* out[row,:] (bf16) += vec[row / rows_per_sample, :] (f32): cls_proj broadcast add (MS:720-723) */
 int sfk_add_sample_bias(void* out, const float* vec, long long rows, int rows_per_sample, int C, sfk_stream_t stream);
 /* BatchNorm2d statistics over x bf16 [M, C]: batch mean / rstd (+ running-stat update) or eval-mode stats */

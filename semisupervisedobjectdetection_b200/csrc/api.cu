@@ -136,6 +136,10 @@ int sfk_upsample_concat_bwd(const void* dout, void* din, int B, int h, int w, in
                             int ch_off, sfk_stream_t stream) {
   return upsample_concat_bwd(dout, din, B, h, w, C, H, W, ld_out, ch_off, ST);
 }
+int sfk_upsample_add4(const void* z0, const void* z1, int h1, int w1, const void* z2, int h2, int w2, const void* z3, int h3,
+                      int w3, const float* bias, void* out, int B, int H, int W, int C, sfk_stream_t stream) {
+  return upsample_add4(z0, z1, h1, w1, z2, h2, w2, z3, h3, w3, bias, out, B, H, W, C, ST);
+}
 int sfk_add_sample_bias(void* out, const float* vec, long long rows, int rows_per_sample, int C, sfk_stream_t stream) {
   return add_sample_bias(out, vec, rows, rows_per_sample, C, ST);
 }

@@ -79,6 +79,91 @@ int upsample_concat(const void* in, void* out, int B, int h, int w, int C, int H
   return check_launch("upsample_concat_kernel");
 }
 
+// Folded decode head (algebraic shortcut): bilinear upsampling commutes with the 1x1 convs, so the fuse conv of
+// the concatenated, upsampled projections equals the SUM of per-stage projections (folded weights) upsampled to the
+// stage-1 grid.  out[b,y,x,:] = z0[b,y,x,:] + sum_{i=1..3} bilinear(z_i)[b,y,x,:] + bias[:]   (bf16 in / out, fp32 math)
+// One block per output row (b, y); the vertical taps of the three coarser levels are computed once per block.
+struct UpLevel {
+  const __nv_bfloat16* z;
+  int h, w;
+};
+__global__ void __launch_bounds__(256) upsample_add4_kernel(const __nv_bfloat16* __restrict__ z0, UpLevel l1, UpLevel l2, UpLevel l3,
+                                                            const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B,
+                                                            int H, int W, int C) {
+  pdl_sync();
+  const int C8 = C >> 3;
+  const int y = blockIdx.x % H;
+  const int b = blockIdx.x / H;
+  const UpLevel lv[3] = {l1, l2, l3};
+  const __nv_bfloat16* r0[3];
+  const __nv_bfloat16* r1[3];
+  float ly[3], sx[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    int y0, y1;
+    bilinear_src(y, (float)lv[k].h / (float)H, lv[k].h, y0, y1, ly[k]);
+    r0[k] = lv[k].z + ((size_t)b * lv[k].h + y0) * lv[k].w * C;
+    r1[k] = lv[k].z + ((size_t)b * lv[k].h + y1) * lv[k].w * C;
+    sx[k] = (float)lv[k].w / (float)W;
+  }
+  const __nv_bfloat16* zrow = z0 + ((size_t)b * H + y) * W * C;
+  __nv_bfloat16* orow = out + ((size_t)b * H + y) * W * C;
+  const int n = W * C8;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const int x = i / C8, c8 = i - x * C8;
+    float acc[8];
+    {
+      const uint4 a = *reinterpret_cast<const uint4*>(zrow + (size_t)x * C + c8 * 8);
+      const uint32_t* ap = reinterpret_cast<const uint32_t*>(&a);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + c8 * 8 + 4));
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(ap[k]);
+        acc[2 * k] = f.x + bb[2 * k];
+        acc[2 * k + 1] = f.y + bb[2 * k + 1];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      int x0, x1;
+      float lx;
+      bilinear_src(x, sx[k], lv[k].w, x0, x1, lx);
+      const float w00 = (1.f - ly[k]) * (1.f - lx), w01 = (1.f - ly[k]) * lx, w10 = ly[k] * (1.f - lx), w11 = ly[k] * lx;
+      const uint4 a = *reinterpret_cast<const uint4*>(r0[k] + (size_t)x0 * C + c8 * 8);
+      const uint4 bq = *reinterpret_cast<const uint4*>(r0[k] + (size_t)x1 * C + c8 * 8);
+      const uint4 c = *reinterpret_cast<const uint4*>(r1[k] + (size_t)x0 * C + c8 * 8);
+      const uint4 d = *reinterpret_cast<const uint4*>(r1[k] + (size_t)x1 * C + c8 * 8);
+      const uint32_t* ap = reinterpret_cast<const uint32_t*>(&a);
+      const uint32_t* bp = reinterpret_cast<const uint32_t*>(&bq);
+      const uint32_t* cp = reinterpret_cast<const uint32_t*>(&c);
+      const uint32_t* dp = reinterpret_cast<const uint32_t*>(&d);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 fa = unpack_bf16x2(ap[j]), fb = unpack_bf16x2(bp[j]), fc = unpack_bf16x2(cp[j]), fd = unpack_bf16x2(dp[j]);
+        acc[2 * j] += w00 * fa.x + w01 * fb.x + w10 * fc.x + w11 * fd.x;
+        acc[2 * j + 1] += w00 * fa.y + w01 * fb.y + w10 * fc.y + w11 * fd.y;
+      }
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(orow + (size_t)x * C + c8 * 8) = o;
+  }
+}
+
+int upsample_add4(const void* z0, const void* z1, int h1, int w1, const void* z2, int h2, int w2, const void* z3, int h3, int w3,
+                  const float* bias, void* out, int B, int H, int W, int C, cudaStream_t stream) {
+  SFK_REQUIRE(C % 8 == 0, "upsample_add4: C=%d must be a multiple of 8", C);
+  SFK_REQUIRE(h1 > 0 && w1 > 0 && h2 > 0 && w2 > 0 && h3 > 0 && w3 > 0, "upsample_add4: empty level");
+  if ((long long)B * H * W == 0) return 0;
+  UpLevel l1{(const __nv_bfloat16*)z1, h1, w1}, l2{(const __nv_bfloat16*)z2, h2, w2}, l3{(const __nv_bfloat16*)z3, h3, w3};
+  launch_k(upsample_add4_kernel, dim3((unsigned)(B * H)), dim3(256), 0, stream, (const __nv_bfloat16*)z0, l1, l2, l3, bias,
+           (__nv_bfloat16*)out, B, H, W, C);
+  return check_launch("upsample_add4_kernel");
+}
+
 // Transposed bilinear: din[b, yi, xi, c] = sum over hi-res (y, x) of weight(y,x -> yi,xi) * dout[b, y, x, ch_off + c].
 // Gather formulation (no atomics, deterministic). One block per low-res row (b, yi): the contributing hi-res rows and their
 // vertical weights are found once per block (shared memory), threads walk (xi, 8-channel chunk) with 32-bit arithmetic.

@@ -102,6 +102,8 @@ int dw_wgrad_from_tap(const float* dwt, float* dw, int C, cudaStream_t stream);
 // ---- decode.cu ----
 int upsample_concat(const void* in, void* out, int B, int h, int w, int C, int H, int W, long long ld_out, int ch_off,
                     cudaStream_t stream);
+int upsample_add4(const void* z0, const void* z1, int h1, int w1, const void* z2, int h2, int w2, const void* z3, int h3, int w3,
+                  const float* bias, void* out, int B, int H, int W, int C, cudaStream_t stream);
 int upsample_concat_bwd(const void* dout, void* din, int B, int h, int w, int C, int H, int W, long long ld_out, int ch_off,
                         cudaStream_t stream);
 int add_sample_bias(void* out, const float* vec, long long rows, int rows_per_sample, int C, cudaStream_t stream);

@@ -9,6 +9,7 @@ shapes and init) — their PyTorch forward is never called.
 from __future__ import annotations
 
 import ctypes
+import os
 import math
 from dataclasses import dataclass
 from typing import List, Optional, Tuple
@@ -376,7 +377,7 @@ class _LayerFn(torch.autograd.Function):
                  ops._p(dfront_out), dx.data_ptr(), ops._p(dfront), ctx.saved.data_ptr(), ctx.saved.numel(), scratch.data_ptr(),
                  scratch.numel(), ops.stream(), None if ws is None else ws.cuda_stream, parity)
         if ws is not None:
-            ctx.saved.record_stream(ws)  # the saved activations are still being read by the side-stream wgrad GEMMs
+            ops.defer_free(ctx.saved)  # the saved activations are still being read by the side-stream wgrad GEMMs
         ctx.saved = None
         return dx, dfront, None, None, None, None, None, None
 
@@ -731,6 +732,10 @@ class SegformerMLP(nn.Module):
         raise NotImplementedError("use SegformerDecodeHead (fused libsfk path); there is no PyTorch fallback")
 
 
+# SURVEY 7 algebraic shortcut for the decode head (default on; SFK_DECODE_FOLD=0 runs the reference's literal sequence)
+DECODE_FOLD = os.environ.get("SFK_DECODE_FOLD", "1") != "0"
+
+
 class _DecodeHeadFn(torch.autograd.Function):
     """linear_c x4 -> bilinear upsample + concat (c4,c3,c2,c1) -> 1x1 fuse GEMM -> BN -> ReLU -> Dropout -> classifier."""
 
@@ -744,15 +749,38 @@ class _DecodeHeadFn(torch.autograd.Function):
         M = B * H0 * W0
         sh = head._shadow()
         dev = toks[0].device
-        cat = torch.empty(M, 4 * dec, device=dev, dtype=torch.bfloat16)
-        for i, t in enumerate(toks):
-            Hi, Wi = dims_hw[i]
-            Ci = t.shape[2]
-            proj = ops.gemm(t.view(B * Hi * Wi, Ci), sh["wc"][i], B * Hi * Wi, dec, Ci, bias=head.linear_c[i].proj.bias, out_bf16=True)
-            if cls_vecs is not None:
-                ops.call("sfk_add_sample_bias", proj.data_ptr(), cls_vecs[i].contiguous().data_ptr(), B * Hi * Wi, Hi * Wi, dec, ops.stream())
-            ops.call("sfk_upsample_concat", proj.data_ptr(), cat.data_ptr(), B, Hi, Wi, dec, H0, W0, 4 * dec, (3 - i) * dec, ops.stream())
-        fused = ops.gemm(cat, sh["wf"], M, dec, 4 * dec, out_bf16=True)
+        fold = DECODE_FOLD and cls_vecs is None
+        folded = None
+        if fold:
+            # SURVEY 7 algebraic shortcut: fuse(concat(up(linear_c_i(x_i)))) == sum_i up((W_f,i W_c,i) x_i) + sum_i W_f,i b_c,i
+            # (bilinear weights sum to one, so biases pass through the upsampling).  Executes 25 GF instead of 1 237 GF per
+            # 16-tile batch and never materialises the [M, 4*dec] concat buffer.
+            wf16 = sh["wf"]
+            wf32 = head.linear_fuse.weight.detach().view(dec, 4 * dec)
+            folded, z = [], []
+            bias_f = torch.zeros(dec, device=dev, dtype=torch.float32)
+            for i, t in enumerate(toks):
+                Hi, Wi = dims_hw[i]
+                Ci = t.shape[2]
+                blk = slice((3 - i) * dec, (4 - i) * dec)
+                folded.append(ops.gemm(wf16[:, blk], sh["wc"][i], dec, Ci, dec, lda=4 * dec, ldb=Ci, b_mn=1, out_bf16=True))
+                bias_f += torch.mv(wf32[:, blk], head.linear_c[i].proj.bias.detach())   # [dec]-sized host-API op
+                z.append(ops.gemm(t.view(B * Hi * Wi, Ci), folded[i], B * Hi * Wi, dec, Ci, out_bf16=True))
+            fused = torch.empty(M, dec, device=dev, dtype=torch.bfloat16)
+            ops.call("sfk_upsample_add4", z[0].data_ptr(), z[1].data_ptr(), dims_hw[1][0], dims_hw[1][1], z[2].data_ptr(),
+                     dims_hw[2][0], dims_hw[2][1], z[3].data_ptr(), dims_hw[3][0], dims_hw[3][1], bias_f.data_ptr(),
+                     fused.data_ptr(), B, H0, W0, dec, ops.stream())
+            cat = None
+        else:
+            cat = torch.empty(M, 4 * dec, device=dev, dtype=torch.bfloat16)
+            for i, t in enumerate(toks):
+                Hi, Wi = dims_hw[i]
+                Ci = t.shape[2]
+                proj = ops.gemm(t.view(B * Hi * Wi, Ci), sh["wc"][i], B * Hi * Wi, dec, Ci, bias=head.linear_c[i].proj.bias, out_bf16=True)
+                if cls_vecs is not None:
+                    ops.call("sfk_add_sample_bias", proj.data_ptr(), cls_vecs[i].contiguous().data_ptr(), B * Hi * Wi, Hi * Wi, dec, ops.stream())
+                ops.call("sfk_upsample_concat", proj.data_ptr(), cat.data_ptr(), B, Hi, Wi, dec, H0, W0, 4 * dec, (3 - i) * dec, ops.stream())
+            fused = ops.gemm(cat, sh["wf"], M, dec, 4 * dec, out_bf16=True)
         bn = head.batch_norm
         mean = torch.empty(dec, device=dev, dtype=torch.float32)
         rstd = torch.empty(dec, device=dev, dtype=torch.float32)
@@ -774,7 +802,8 @@ class _DecodeHeadFn(torch.autograd.Function):
                  wc.data_ptr(), head.classifier.bias.data_ptr(), logits.data_ptr(), M, dec, NL, H0 * W0, drop_p, seed, ops.stream())
         if any(ctx.needs_input_grad):
             ctx.head, ctx.sh, ctx.meta = head, sh, (B, dec, NL, dims_hw, M, drop_p, seed, training, cls_vecs is not None)
-            ctx.save_for_backward(cat, fused, mean, rstd, *toks)
+            ctx.folded = folded
+            ctx.save_for_backward(cat if cat is not None else fused.new_empty(0), fused, mean, rstd, *toks)
         return logits
 
     @staticmethod
@@ -802,6 +831,8 @@ class _DecodeHeadFn(torch.autograd.Function):
         if gg is not None:
             ops.colsum_into(sums[1], gg, 1, dec)
         gwf = ops.grad_buffer(head.linear_fuse.weight)
+        if ctx.folded is not None:
+            return _DecodeHeadFn._backward_folded(ctx, dfused, gwf, toks)
         if gwf is not None:
             ops.gemm(dfused, cat, dec, 4 * dec, M, lda=dec, ldb=4 * dec, a_mn=1, b_mn=1, out=gwf.view(dec, 4 * dec), out_bf16=False,
                      atomic_add=True)
@@ -829,6 +860,51 @@ class _DecodeHeadFn(torch.autograd.Function):
             else:
                 dtoks.append(None)
         return dtoks[0], dtoks[1], dtoks[2], dtoks[3], dcls, None, None, None, None
+
+    @staticmethod
+    def _backward_folded(ctx, dfused, gwf, toks):
+        """Backward of the folded head: dz_0 = dfused, dz_i = up^T(dfused); per stage dx_i = dz_i W'_i, dW'_i = dz_i^T x_i,
+        then the chain rule through W'_i = W_f,i W_c,i and b' = sum_i W_f,i b_c,i onto the reference's parameters."""
+        head, sh = ctx.head, ctx.sh
+        B, dec, NL, dims_hw, M, drop_p, seed, training, has_cls = ctx.meta
+        dev = dfused.device
+        (H0, W0) = dims_hw[0]
+        wf16 = sh["wf"]
+        wf32 = head.linear_fuse.weight.detach().view(dec, 4 * dec)
+        dbias = torch.zeros(dec, device=dev, dtype=torch.float32)    # gradient of the folded bias b'
+        ops.colsum_into(dfused, dbias, M, dec)
+        gwf2 = gwf.view(dec, 4 * dec) if gwf is not None else None
+        dtoks = []
+        for i, t in enumerate(toks):
+            Hi, Wi = dims_hw[i]
+            Ci = t.shape[2]
+            rows = B * Hi * Wi
+            blk = slice((3 - i) * dec, (4 - i) * dec)
+            if i == 0:
+                dz = dfused
+            else:
+                dz = torch.empty(rows, dec, device=dev, dtype=torch.bfloat16)
+                ops.call("sfk_upsample_concat_bwd", dfused.data_ptr(), dz.data_ptr(), B, Hi, Wi, dec, H0, W0, dec, 0, ops.stream())
+            lin = head.linear_c[i].proj
+            gw, gbi = ops.grad_buffer(lin.weight), ops.grad_buffer(lin.bias)
+            if gw is not None or gwf2 is not None:
+                dwp = torch.zeros(dec, Ci, device=dev, dtype=torch.float32)      # dW'_i
+                ops.gemm(dz, t.view(rows, Ci), dec, Ci, rows, lda=dec, ldb=Ci, a_mn=1, b_mn=1, out=dwp, out_bf16=False, atomic_add=True)
+                dwp16 = ops.cast_bf16(dwp)
+                if gwf2 is not None:
+                    # dW_f,i += dW'_i W_c,i^T + db' (x) b_c,i
+                    ops.gemm(dwp16, sh["wc"][i], dec, dec, Ci, out=gwf2[:, blk], ldo=4 * dec, out_bf16=False, atomic_add=True)
+                    gwf2[:, blk].addr_(dbias, lin.bias.detach())
+                if gw is not None:
+                    # dW_c,i += W_f,i^T dW'_i
+                    ops.gemm(wf16[:, blk], dwp16, dec, Ci, dec, lda=4 * dec, ldb=Ci, a_mn=1, b_mn=1, out=gw, out_bf16=False, atomic_add=True)
+            if gbi is not None:
+                gbi += torch.mv(wf32[:, blk].t(), dbias)                            # db_c,i += W_f,i^T db'
+            if ctx.needs_input_grad[i]:
+                dtoks.append(ops.gemm(dz, ctx.folded[i], rows, Ci, dec, lda=dec, ldb=Ci, b_mn=1, out_bf16=True).view(B, Hi * Wi, Ci))
+            else:
+                dtoks.append(None)
+        return dtoks[0], dtoks[1], dtoks[2], dtoks[3], None, None, None, None, None
 
 
 class SegformerDecodeHead(SegformerPreTrainedModel):
