@@ -361,14 +361,26 @@ int bn_eval_stats(const float* rm, const float* rv, float eps, float* mean, floa
   return check_launch("bn_eval_stats_kernel");
 }
 
-// counter-based dropout mask: keep iff hash(seed, element) >= p  (regenerated identically in backward)
-__device__ __forceinline__ float hash_uniform(unsigned long long seed, unsigned long long idx) {
+// counter-based dropout mask (regenerated identically in backward)
+// 8 consecutive elements at once: two 64-bit hashes -> eight 16-bit uniforms (the per-element 64-bit mix above cost ~25
+// instructions per element and dominated the decode-head tail kernels).  m[e] = keep ? 1/(1-p) : 0; element index `elem0`
+// must be a multiple of 8.  Regenerated identically in backward.
+__device__ __forceinline__ unsigned long long hash64(unsigned long long seed, unsigned long long idx) {
   unsigned long long z = seed + idx * 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  z ^= z >> 31;
-  return (float)(z >> 40) * (1.0f / 16777216.0f);
+  return z ^ (z >> 31);
 }
+__device__ __forceinline__ void dropout_mult8(unsigned long long seed, unsigned long long elem0, unsigned thr16, float keep_scale,
+                                              float (&m)[8]) {
+  const unsigned long long z0 = hash64(seed, elem0 >> 2), z1 = hash64(seed, (elem0 >> 2) + 1);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    m[e] = ((unsigned)(z0 >> (16 * e)) & 0xffffu) >= thr16 ? keep_scale : 0.f;
+    m[4 + e] = ((unsigned)(z1 >> (16 * e)) & 0xffffu) >= thr16 ? keep_scale : 0.f;
+  }
+}
+__device__ __forceinline__ unsigned dropout_thr16(float p) { return (unsigned)(p * 65536.0f); }
 
 static constexpr int CLS_MAX_LABELS = 8;
 
@@ -416,9 +428,10 @@ __global__ void __launch_bounds__(256) bn_relu_cls_fwd_kernel(const __nv_bfloat1
         y[2 * k + 1] = fmaxf(fmaf(v.y, sa[c + 2 * k + 1], sb[c + 2 * k + 1]), 0.f);
       }
       if (drop_p > 0.f) {
+        float dm[8];
+        dropout_mult8(seed, (unsigned long long)row * C + c, dropout_thr16(drop_p), keep_scale, dm);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
-          y[k] = hash_uniform(seed, (unsigned long long)row * C + c + k) >= drop_p ? y[k] * keep_scale : 0.f;
+        for (int k = 0; k < 8; ++k) y[k] *= dm[k];
       }
 #pragma unroll
       for (int l = 0; l < CLS_MAX_LABELS; ++l) {
@@ -522,13 +535,14 @@ __global__ void __launch_bounds__(256) bn_relu_cls_bwd_a_kernel(const __nv_bfloa
       const int c = ch * 8;
       const uint4 u = *reinterpret_cast<const uint4*>(x + row * C + c);
       const uint32_t* up = reinterpret_cast<const uint32_t*>(&u);
+      float dm[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+      if (drop_p > 0.f) dropout_mult8(seed, (unsigned long long)row * C + c, dropout_thr16(drop_p), keep_scale, dm);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float2 v2 = unpack_bf16x2(up[j >> 1]);
         const float xv = (j & 1) ? v2.y : v2.x;
         const float bn = fmaf(xv, sa[c + j], sb[c + j]);
-        float m = bn > 0.f ? 1.f : 0.f;
-        if (drop_p > 0.f) m *= hash_uniform(seed, (unsigned long long)row * C + c + j) >= drop_p ? keep_scale : 0.f;
+        const float m = bn > 0.f ? dm[j] : 0.f;
         float dy = 0.f;
 #pragma unroll
         for (int l = 0; l < CLS_MAX_LABELS; ++l)
@@ -618,13 +632,14 @@ __global__ void __launch_bounds__(256) bn_relu_cls_bwd_b_kernel(const __nv_bfloa
       const uint4 u = *reinterpret_cast<const uint4*>(x + row * C + c);
       const uint32_t* up = reinterpret_cast<const uint32_t*>(&u);
       float o[8];
+      float dm[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+      if (drop_p > 0.f) dropout_mult8(seed, (unsigned long long)row * C + c, dropout_thr16(drop_p), keep_scale, dm);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float2 v2 = unpack_bf16x2(up[j >> 1]);
         const float xv = (j & 1) ? v2.y : v2.x;
         const float bn = fmaf(xv, sa[c + j], sb[c + j]);
-        float m = bn > 0.f ? 1.f : 0.f;
-        if (drop_p > 0.f) m *= hash_uniform(seed, (unsigned long long)row * C + c + j) >= drop_p ? keep_scale : 0.f;
+        const float m = bn > 0.f ? dm[j] : 0.f;
         float dy = 0.f;
 #pragma unroll
         for (int l = 0; l < CLS_MAX_LABELS; ++l)

@@ -16,12 +16,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def test_model_matches_reference_goldens():
+@pytest.mark.parametrize("decode_fold", ["1", "0"])
+def test_model_matches_reference_goldens(decode_fold):
     """Forward logits / hidden states / probabilities / losses and backward gradients for every golden case
     (eval, 128^2, 2-D and 3-D prompts, cls tokens, CE, BN train mode); bf16 tolerance: max rel err <= 5e-2 on gradients,
-    <= 2e-2 on logits (north_star)."""
+    <= 2e-2 on logits (north_star).  Run with the decode head's algebraic fold (default) and with the reference's literal
+    linear_c -> upsample -> concat -> fuse sequence."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_model.py"), "golden"], cwd=ROOT, capture_output=True,
-                       text=True, timeout=900)
+                       text=True, timeout=900, env=dict(os.environ, SFK_DECODE_FOLD=decode_fold))
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-30:])
     assert r.returncode == 0 and "GOLDEN ALLOK" in r.stdout, tail
 

@@ -277,6 +277,30 @@ def main():
             allok &= report("   dbeta", sums[0], br.grad, 2e-3)
             allok &= report("   dwc", dwc, wr.grad, 2e-3)
             allok &= report("   dbc", dbc, bcr.grad, 2e-3)
+        # dropout: the mask is observable through the eval-statistics backward (dx = gamma*rstd*dl*wc*mask with everything
+        # else set to one) and must be the mask the forward applied; keep fraction ~ 1 - p
+        M, C, pix, pdrop, seed = 4096, 256, 1024, 0.25, 12345
+        x = (torch.rand(M, C, device=dev) + 0.5).bfloat16()
+        one, zero = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+        wc1, bc0 = torch.ones(1, C, device=dev), torch.zeros(1, device=dev)
+        logits = torch.empty(M // pix, 1, pix, device=dev)
+        L.check(lib.sfk_bn_relu_cls_fwd(x.data_ptr(), zero.data_ptr(), one.data_ptr(), one.data_ptr(), zero.data_ptr(), wc1.data_ptr(),
+                                        bc0.data_ptr(), logits.data_ptr(), M, C, 1, pix, pdrop, seed, L.stream_ptr()))
+        dl1 = torch.ones(M // pix, 1, pix, device=dev)
+        sums = torch.empty(2, C, device=dev)
+        dwc, dbc = torch.zeros(1, C, device=dev), torch.zeros(1, device=dev)
+        mask = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
+        L.check(lib.sfk_bn_relu_cls_bwd(x.data_ptr(), zero.data_ptr(), one.data_ptr(), one.data_ptr(), zero.data_ptr(), wc1.data_ptr(),
+                                        dl1.data_ptr(), sums.data_ptr(), dwc.data_ptr(), dbc.data_ptr(), mask.data_ptr(), M, C, 1, pix,
+                                        pdrop, seed, 0, L.stream_ptr()))
+        torch.cuda.synchronize()
+        keep = (mask.float() > 0).float().mean().item()
+        vals = mask.float()[mask.float() > 0]
+        ok = abs(keep - (1 - pdrop)) < 5e-3 and bool(((vals - 1 / (1 - pdrop)).abs() < 1e-2).all())
+        print(f"{'OK ' if ok else 'BAD'} dropout keep fraction {keep:.4f} (expected {1 - pdrop:.4f}), kept scale {vals.mean().item():.4f}", flush=True)
+        allok &= ok
+        allok &= report("dropout forward uses the backward's mask", logits.reshape(-1), (x.float() * mask.float()).sum(1), 2e-3)
+        allok &= report("   dwc under dropout", dwc, (x.float() * mask.float()).sum(0, keepdim=True), 2e-3)
     elif group == "loss":
         for (B, C, h, w, H, W, act) in [(2, 1, 16, 16, 64, 64, 1), (2, 3, 16, 16, 64, 64, 0), (1, 2, 7, 9, 28, 36, 1), (2, 1, 128, 128, 512, 512, 1)]:
             x = torch.randn(B, C, h, w, device=dev) * 2
