@@ -258,11 +258,17 @@ def run_sfk(args):
     mallocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     prof = {}
+    prof_range = os.environ.get("SFK_CUDA_PROFILER_RANGE") is not None   # ncu --profile-from-start off: only the timed steps
+    if prof_range:
+        torch.cuda.profiler.start()
     e0.record()
     t_cpu0 = time.perf_counter()
     for i in range(args.steps):
         loss = step(dev_l, dev_u, dev_gt)
     e1.record()
+    if prof_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     cpu_enqueue_ms = 1000.0 * (time.perf_counter() - t_cpu0) / args.steps  # host time to enqueue a step (no sync inside)
     barrier()
     ms = e0.elapsed_time(e1) / args.steps

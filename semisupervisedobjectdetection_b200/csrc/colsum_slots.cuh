@@ -56,4 +56,36 @@ __device__ __forceinline__ void colsum_commit(const float* sh, int v0, int nv, i
   if (threadIdx.x == 0) g_colsum_ticket[ticket] = 0u;
 }
 
+// block-level reduction of per-thread channel partials (8 warps -> shared memory), then the slotted low-contention commit:
+// virtual column v = k * C + channel  (k-th output array)
+template <int VEC, int NV>
+__device__ __forceinline__ void dw_block_commit(float (&acc)[NV][VEC], float* sh, float* out_base, long long out_stride,
+                                                float* out_last, int c0, int C, bool lane_ok, int ns) {
+  const int lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < NV * 32 * VEC; i += 256) sh[i] = 0.f;
+  __syncthreads();
+  if (lane_ok) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) atomicAdd(&sh[(k * 32 + lane) * VEC + v], acc[k][v]);
+  }
+  __syncthreads();
+  const int cbase = c0 - lane * VEC;  // first channel of this block (same for every lane)
+  int ncol = C - cbase;
+  if (ncol > 32 * VEC) ncol = 32 * VEC;
+  // slots are laid out [ns][NV][ncol-wide window per blockIdx.x]: use V = gridDim.x * NV * 32 * VEC virtual columns
+  const int V = gridDim.x * NV * 32 * VEC;
+  const int v0 = blockIdx.x * NV * 32 * VEC;
+  colsum_commit(sh, v0, NV * 32 * VEC, V, ns, blockIdx.y, gridDim.y, blockIdx.x, [&](int v, float sum) {
+    const int local = v - v0;
+    const int k = local / (32 * VEC), j = local % (32 * VEC);
+    if (j < ncol) {
+      float* dst = (k == NV - 1) ? out_last : out_base + (long long)k * out_stride;
+      dst[cbase + j] += sum;
+    }
+  });
+}
+
+
 }  // namespace sfk
