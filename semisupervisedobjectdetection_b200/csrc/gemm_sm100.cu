@@ -81,6 +81,9 @@ struct GemmKernelParams {
   int relu;
   unsigned long long* trace;
   int tmem_cols;   // 512 (1 CTA / SM) or 256 (2 CTAs / SM); accumulator buffer a lives at column a * tmem_cols / 2
+  // patch-view operands (rank-5 TMA): rows per sample, ox-row length, k-blocks per ky
+  int a_patch, pa_rows_b, pa_wo, pa_kspan;
+  int b_patch, pb_rows_b, pb_wo, pb_span;   // pb_span = sr*C (elements per ky)
   int cluster2;  // CTA-pair mode: launched as 2-CTA clusters, one cta_group::2 MMA per pair (rows 256, B split across the pair)
 };
 
@@ -180,14 +183,27 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const uint32_t full = bar_full + 8 * stage;
             mbar_arrive_expect_tx(full, p.stage_bytes);
             if (unit == unit0 && kb == kb0) GEMM_TRACE(2);
-            if (!p.a_mn) {
+            if (p.a_patch) {
+              // implicit im2col: 128 patch rows = (128 / Wo) ox-rows of one sample; this k-block = 64 of the (kx, c) run of one ky
+              const int m0 = m_blk * BLOCK_M;
+              const int bi = m0 / p.pa_rows_b, oy0 = (m0 - bi * p.pa_rows_b) / p.pa_wo;
+              tma_load_5d(sa, &tmap_a, full, (kb % p.pa_kspan) * BLOCK_K, kb / p.pa_kspan, 0, oy0, bi);
+            } else if (!p.a_mn) {
               tma_load_2d(sa, &tmap_a, full, kb * BLOCK_K, m_blk * BLOCK_M);
             } else {
               // stored [K, M] (M contiguous): 2 boxes of [64 m, 64 k]
               tma_load_2d(sa, &tmap_a, full, m_blk * BLOCK_M, kb * BLOCK_K);
               tma_load_2d(sa + 8192, &tmap_a, full, m_blk * BLOCK_M + 64, kb * BLOCK_K);
             }
-            if (!p.b_mn) {
+            if (p.b_patch) {
+              // MN-major B = patch matrix [K = patch rows, N = (ky, kx, c)]: boxes of [64 n, 64 patch rows]
+              const int k0 = kb * BLOCK_K;
+              const int bi = k0 / p.pb_rows_b, oy0 = (k0 - bi * p.pb_rows_b) / p.pb_wo;
+              for (int j = 0; j < p.block_n / 64; ++j) {
+                const int n = n_blk * p.block_n + j * 64;
+                tma_load_5d(sb + j * 8192, &tmap_b, full, n % p.pb_span, n / p.pb_span, 0, oy0, bi);
+              }
+            } else if (!p.b_mn) {
               tma_load_2d(sb, &tmap_b, full, kb * BLOCK_K, n_blk * p.block_n);
             } else {
               for (int j = 0; j < p.block_n / 64; ++j)
@@ -472,7 +488,18 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
   // CTA pairs (cta_group::2) when enabled and the shape allows it
   int pair_bn = 0;
-  const bool pair_wanted = g_gemm_cluster2 == 2 || (g_gemm_cluster2 == 1 && (double)g.M * g.N * g.K >= 1.0e11 && g.K >= 1024);
+  const bool a_patch = g.a_patch.enabled != 0, b_patch = g.b_patch.enabled != 0;
+  if (a_patch) {
+    SFK_REQUIRE(!g.a_mn && patch_view_ok(g.a_patch, BLOCK_M), "gemm: A patch view not tileable (Wo=%d Ho=%d)", g.a_patch.Wo, g.a_patch.Ho);
+    SFK_REQUIRE(g.K == g.a_patch.sr * g.a_patch.sr * g.a_patch.C && g.M == g.a_patch.B * g.a_patch.Ho * g.a_patch.Wo,
+                "gemm: A patch view does not match M=%d K=%d", g.M, g.K);
+  }
+  if (b_patch) {
+    SFK_REQUIRE(g.b_mn && patch_view_ok(g.b_patch, 64), "gemm: B patch view not tileable (Wo=%d Ho=%d)", g.b_patch.Wo, g.b_patch.Ho);
+    SFK_REQUIRE(g.N == g.b_patch.sr * g.b_patch.sr * g.b_patch.C && g.K == g.b_patch.B * g.b_patch.Ho * g.b_patch.Wo,
+                "gemm: B patch view does not match N=%d K=%d", g.N, g.K);
+  }
+  const bool pair_wanted = !a_patch && !b_patch && g_gemm_cluster2 == 2 || (g_gemm_cluster2 == 1 && (double)g.M * g.N * g.K >= 1.0e11 && g.K >= 1024);
   if (pair_wanted && g.M > BLOCK_M && (num_sms() % 2 == 0)) {
     if (g.block_n > 0) {
       if (g.block_n % 32 == 0 && (!p.b_mn || g.block_n % 128 == 0)) pair_bn = g.block_n;
@@ -542,10 +569,28 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
 
   CUtensorMap ta, tb;
   int rc;
-  if (!p.a_mn) rc = make_tmap_2d_bf16(&ta, g.a, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda * 2, BLOCK_K, BLOCK_M);
+  auto patch_map = [&](CUtensorMap* t, const void* base, const PatchView& v, int rows) {
+    const long long W = (long long)v.Wo * v.sr;
+    const uint64_t dims[5] = {(uint64_t)v.sr * v.C, (uint64_t)v.sr, (uint64_t)v.Wo, (uint64_t)v.Ho, (uint64_t)v.B};
+    const uint64_t strides[4] = {(uint64_t)W * v.C * 2, (uint64_t)v.sr * v.C * 2, (uint64_t)v.sr * W * v.C * 2,
+                                 (uint64_t)v.batch_stride * 2};
+    const uint32_t box[5] = {64, 1, (uint32_t)v.Wo, (uint32_t)(rows / v.Wo), 1};
+    return make_tmap_5d_bf16(t, base, dims, strides, box);
+  };
+  p.a_patch = a_patch ? 1 : 0;
+  p.pa_rows_b = a_patch ? g.a_patch.Ho * g.a_patch.Wo : 1;
+  p.pa_wo = a_patch ? g.a_patch.Wo : 1;
+  p.pa_kspan = a_patch ? g.a_patch.sr * g.a_patch.C / BLOCK_K : 1;
+  p.b_patch = b_patch ? 1 : 0;
+  p.pb_rows_b = b_patch ? g.b_patch.Ho * g.b_patch.Wo : 1;
+  p.pb_wo = b_patch ? g.b_patch.Wo : 1;
+  p.pb_span = b_patch ? g.b_patch.sr * g.b_patch.C : 1;
+  if (a_patch) rc = patch_map(&ta, g.a, g.a_patch, BLOCK_M);
+  else if (!p.a_mn) rc = make_tmap_2d_bf16(&ta, g.a, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda * 2, BLOCK_K, BLOCK_M);
   else         rc = make_tmap_2d_bf16(&ta, g.a, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda * 2, 64, BLOCK_K);
   if (rc) return rc;
-  if (!p.b_mn) rc = make_tmap_2d_bf16(&tb, g.b, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb * 2, BLOCK_K,
+  if (b_patch) rc = patch_map(&tb, g.b, g.b_patch, 64);
+  else if (!p.b_mn) rc = make_tmap_2d_bf16(&tb, g.b, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.ldb * 2, BLOCK_K,
                                       p.cluster2 ? p.block_n / 2 : p.block_n);
   else         rc = make_tmap_2d_bf16(&tb, g.b, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb * 2, 64, BLOCK_K);
   if (rc) return rc;

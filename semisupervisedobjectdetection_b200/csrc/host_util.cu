@@ -82,6 +82,27 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return 0;
 }
 
+// rank-5 tiled map (bf16, SWIZZLE_128B, inner box = 64 elements): used for the k == stride patch view of a channels-last map
+int make_tmap_5d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
+                      const uint32_t box[5]) {
+  PFN_encodeTiled enc = get_encode();
+  SFK_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  SFK_REQUIRE(box[0] * 2 == 128, "tensor map: inner box must be 128 bytes for SWIZZLE_128B");
+  SFK_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map: base must be 16-byte aligned");
+  cuuint64_t gdim[5], gstride[4];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < 5; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; SFK_REQUIRE(box[i] >= 1 && box[i] <= 256, "tensor map: box out of range"); }
+  for (int i = 0; i < 4; ++i) {
+    gstride[i] = strides_bytes[i];
+    SFK_REQUIRE(strides_bytes[i] % 16 == 0, "tensor map: stride %llu not a multiple of 16 bytes", (unsigned long long)strides_bytes[i]);
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstride, bx, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SFK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(5d) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                       uint64_t stride2_bytes, uint32_t box0, uint32_t box1, uint32_t box2, int swizzle_bytes) {
   PFN_encodeTiled enc = get_encode();

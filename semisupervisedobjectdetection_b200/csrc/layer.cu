@@ -12,6 +12,9 @@
 
 namespace sfk {
 
+// sfk_set_option("sr_tma_patch", 0|1): read the SR conv's patches through a rank-5 TMA view (default) or gather them first
+int g_sr_tma_patch = 1;
+
 namespace {
 
 struct Arena {
@@ -159,6 +162,13 @@ static int side_end(cudaStream_t side, int parity) {
     if (_rc != 0) return _rc; \
   } while (0)
 
+PatchView sr_patch_view(const Dims& d) {
+  PatchView v;
+  v.enabled = g_sr_tma_patch;
+  v.B = (int)d.B; v.Ho = (int)(d.H / d.sr); v.Wo = (int)(d.W / d.sr); v.sr = (int)d.sr; v.C = (int)d.C;
+  v.batch_stride = d.T * d.C;
+  return v;
+}
 GemmDesc linear_fwd(const void* a, long long lda, const void* w, long long ldw, long long M, long long N, long long K,
                     const float* bias, void* out, long long ldo, int out_bf16) {
   GemmDesc g;
@@ -240,8 +250,17 @@ int layer_forward(const sfk_layer_dims& dd, const sfk_layer_params& p, const flo
     const long long Ksr = d.sr * d.sr * C;
     __nv_bfloat16* A = sc.take<__nv_bfloat16>(d.B * d.Nkv * Ksr);
     SFK_REQUIRE(sc.off <= scratch_bytes, "layer_forward: scratch arena too small");
-    TRY(im2col_nhwc(s.xn1, A, (int)d.B, (int)d.H, (int)d.W, (int)C, (int)d.sr, (int)d.sr, 0, d.T, d.P, st));
-    GemmDesc g = linear_fwd(A, Ksr, p.wsr, Ksr, d.B * d.Nkv, C, Ksr, p.bsr, s.sr_out, C, 0);
+    // k == stride conv as a GEMM over the patch view of xn1: TMA tiles the rank-5 strided tensor directly (implicit
+    // im2col); the gather kernel is only the fallback for grids whose ox-rows do not tile a 128-row block
+    const PatchView pv = sr_patch_view(d);
+    GemmDesc g;
+    if (patch_view_ok(pv, 128)) {
+      g = linear_fwd(s.xn1 + d.P * C, Ksr, p.wsr, Ksr, d.B * d.Nkv, C, Ksr, p.bsr, s.sr_out, C, 0);
+      g.a_patch = pv;
+    } else {
+      TRY(im2col_nhwc(s.xn1, A, (int)d.B, (int)d.H, (int)d.W, (int)C, (int)d.sr, (int)d.sr, 0, d.T, d.P, st));
+      g = linear_fwd(A, Ksr, p.wsr, Ksr, d.B * d.Nkv, C, Ksr, p.bsr, s.sr_out, C, 0);
+    }
     g.out_map = kv_spatial_map(d);
     TRY(gemm_bf16(g, st));
     if (d.P > 0)  // prompt rows bypass the conv but do go through the SR LayerNorm (MS:194-205)
@@ -410,8 +429,15 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
       cudaStream_t ws = side_fork(st, side);  // dsr_sp is final here; patch gather + wgrad + layout fix all run off-path
       cudaError_t e = cudaMemsetAsync(dwsr, 0, (size_t)C * Ksr * sizeof(float), ws);
       SFK_REQUIRE(e == cudaSuccess, "layer_backward: memset failed");
-      TRY(im2col_nhwc(s.xn1, A, (int)d.B, (int)d.H, (int)d.W, (int)C, (int)d.sr, (int)d.sr, 0, d.T, d.P, ws));
-      TRY(gemm_bf16(linear_wgrad(dsr_sp, C, A, Ksr, rows_red, C, Ksr, dwsr, Ksr), ws));
+      const PatchView pv = sr_patch_view(d);
+      if (patch_view_ok(pv, 64)) {
+        GemmDesc g = linear_wgrad(dsr_sp, C, s.xn1 + d.P * C, Ksr, rows_red, C, Ksr, dwsr, Ksr);
+        g.b_patch = pv;
+        TRY(gemm_bf16(g, ws));
+      } else {
+        TRY(im2col_nhwc(s.xn1, A, (int)d.B, (int)d.H, (int)d.W, (int)C, (int)d.sr, (int)d.sr, 0, d.T, d.P, ws));
+        TRY(gemm_bf16(linear_wgrad(dsr_sp, C, A, Ksr, rows_red, C, Ksr, dwsr, Ksr), ws));
+      }
       TRY(conv_wgrad_ohwi_to_oihw(dwsr, gr.dwsr, (int)C, (int)C, (int)d.sr, (int)d.sr, Ksr, ws));
     }
     if (gr.dbsr) TRY(colsum(dsr_sp, 1, C, gr.dbsr, rows_red, (int)C, st));

@@ -13,6 +13,20 @@ struct RowMap {
   long long offset = 0;
 };
 
+// k == stride patch view of a channels-last bf16 map x[b][y][x][c] (the SR conv's implicit im2col, MS:171-173):
+//   P[m, (ky*sr + kx)*C + c] = x[b, oy*sr + ky, ox*sr + kx, c],  m = (b*Ho + oy)*Wo + ox
+// For fixed ky the (kx, c) run is contiguous in memory, so the matrix is a rank-5 strided tensor TMA can tile directly:
+// no gather kernel, no materialised [M, sr*sr*C] copy.  The operand pointer is x + first spatial token.
+struct PatchView {
+  int enabled = 0;
+  int B = 0, Ho = 0, Wo = 0, sr = 0, C = 0;
+  long long batch_stride = 0;   // elements between samples (tokens per sample * C, prompt rows included)
+};
+// rows of the patch matrix one TMA box can cover: `rows` consecutive m must be whole ox-rows inside one sample
+inline bool patch_view_ok(const PatchView& v, int rows) {
+  return v.enabled && v.Wo >= 1 && v.Wo <= rows && rows % v.Wo == 0 && v.Ho % (rows / v.Wo) == 0 && (v.sr * v.C) % 64 == 0;
+}
+
 struct GemmDesc {
   // D[M,N] = alpha * A·B^T (+bias[N]) (*row_scale[row / rows_per_scale]) (+residual fp32) -> out (fp32 | bf16 | fp32 +=)
   int M = 0, N = 0, K = 0;
@@ -37,6 +51,8 @@ struct GemmDesc {
   int relu = 0;
   int splits = 0;   // 0 = auto
   int block_n = 0;  // 0 = auto
+  PatchView a_patch;   // A (K-major, M = B*Ho*Wo rows, K = sr*sr*C) read through the patch view of `a`
+  PatchView b_patch;   // B (MN-major: [K = B*Ho*Wo rows, N = sr*sr*C]) read through the patch view of `b`  (wgrad)
 };
 
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream);

@@ -28,6 +28,14 @@ def test_model_matches_reference_goldens(decode_fold):
     assert r.returncode == 0 and "GOLDEN ALLOK" in r.stdout, tail
 
 
+def test_sr_conv_tma_patch_view_matches_gather():
+    """The implicit-im2col (rank-5 TMA) SR conv operands against the gathered copy on the same inputs (b0, 512x512)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_model.py"), "patch"], cwd=ROOT, capture_output=True,
+                       text=True, timeout=600)
+    tail = "\n".join((r.stdout + r.stderr).splitlines()[-20:])
+    assert r.returncode == 0 and "PATCH ALLOK" in r.stdout, tail
+
+
 def _b0_wrapper(num_labels=1, lr=1e-3, wd=5e-5):
     from semisupervisedobjectdetection_b200.wrapper import SegFormerModel
     w = SegFormerModel(None, lr=lr, weight_decay=wd, scheduler=0.97, device="cuda:0", num_labels=num_labels, variant="nvidia/mit-b0")

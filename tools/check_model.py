@@ -150,7 +150,47 @@ def run_b5(batch):
     print(f"b5 batch {batch} fwd only: {ms:.2f} ms -> {batch/ms*1000:.1f} img/s, {219.27*batch/ms:.1f} TFLOP/s", flush=True)
 
 
+def run_patch_parity():
+    """SR conv through the rank-5 TMA patch view vs the gathered (im2col) copy: same GEMM on the same values, so logits and
+    gradients must agree to fp32-summation-order noise.  MiT-b0 at 512x512 (every stage tiles: Wo = 16)."""
+    from semisupervisedobjectdetection_b200 import _lib as L
+    lib = L.load()
+    torch.manual_seed(0)
+    cfg = SegformerConfig.from_variant("b0", num_labels=1)
+    model = SegformerForSemanticSegmentation(cfg).cuda().eval()
+    x = torch.rand(2, 3, 512, 512, device="cuda")
+    mask = (torch.rand(2, 512, 512, device="cuda") > 0.9).to(torch.int64)
+    lossf = SegmentationLoss(1, loss_type="dice", activation="none")
+    res = {}
+    for mode in (1, 0):
+        L.check(lib.sfk_set_option(b"sr_tma_patch", mode))
+        model.zero_grad(set_to_none=False)
+        out, _ = model(pixel_values=x)
+        probs = torch.squeeze(upsample_bilinear(out.logits, (512, 512), sigmoid=True), 1)
+        lossf(probs, mask).backward()
+        torch.cuda.synchronize()
+        res[mode] = (out.logits.detach().clone(), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None})
+    L.check(lib.sfk_set_option(b"sr_tma_patch", 1))
+    ok = True
+    dl = (res[1][0] - res[0][0]).abs().max().item() / (res[0][0].abs().max().item() + 1e-12)
+    print(f"{'OK ' if dl < 1e-5 else 'BAD'} logits patch-view vs gather: rel {dl:.2e}", flush=True)
+    ok &= dl < 1e-5
+    worst, wn = 0.0, ""
+    for n, g0 in res[0][1].items():
+        if ".key." in n:
+            continue   # softmax is invariant to a key shift: these gradients are mostly summation-order noise around zero
+        e = (res[1][1][n] - g0).abs().max().item() / (g0.abs().max().item() + 1e-12)
+        if e > worst:
+            worst, wn = e, n
+    print(f"{'OK ' if worst < 1e-3 else 'BAD'} gradients patch-view vs gather: worst rel {worst:.2e} ({wn})", flush=True)
+    ok &= worst < 1e-3
+    print("PATCH", "ALLOK" if ok else "FAILED", flush=True)
+    return ok
+
+
 if __name__ == "__main__":
+    if sys.argv[1] == "patch":
+        sys.exit(0 if run_patch_parity() else 1)
     if sys.argv[1] == "golden":
         sys.exit(0 if run_golden() else 1)
     run_b5(int(sys.argv[2]) if len(sys.argv) > 2 else 2)
