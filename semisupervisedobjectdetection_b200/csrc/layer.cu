@@ -356,8 +356,16 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
   TRY(gemm_bf16(linear_dgrad(dh1, Hd, p.w1, C, rows_sp, Hd, C, dxn2, C, 1), st));
   if (gr.dw1) TRY(gemm_bf16(linear_wgrad(dh1, Hd, s.xn2, C, rows_sp, Hd, C, gr.dw1, C), side_fork(st, side)));
   // LN2 backward + residual gradient -> dx1 (spatial rows); front rows of dx1 come from the returned cls/prompt rows
-  TRY(layernorm_bwd(dxn2, 1, s.x1, 0, spatial_map(d), s.mean2, s.rstd2, p.ln2_g, dout, id, dx1, 0, spatial_map(d), gr.dln2_g,
-                    gr.dln2_b, rows_sp, (int)C, st));
+  // without prompt rows LN2's dx IS the whole dx1, so the same pass also emits the drop-path-scaled bf16 copy (+ its column
+  // sums = o-proj bias gradient) the attention branch consumes
+  const bool fuse_da = d.P == 0 && gr.dln2_g != nullptr && gr.dln2_b != nullptr;
+  if (fuse_da) {
+    TRY(layernorm_bwd_aux(dxn2, s.x1, s.mean2, s.rstd2, p.ln2_g, dout, dx1, gr.dln2_g, gr.dln2_b, rows_sp, (int)C, da,
+                          p.drop_scale_attn, (int)d.T, gr.dbo, st));
+  } else {
+    TRY(layernorm_bwd(dxn2, 1, s.x1, 0, spatial_map(d), s.mean2, s.rstd2, p.ln2_g, dout, id, dx1, 0, spatial_map(d), gr.dln2_g,
+                      gr.dln2_b, rows_sp, (int)C, st));
+  }
   if (d.P > 0) {
     if (dfront_out != nullptr) {
       TRY(scale_cast(dfront_out, 0, id, dx1, 0, front_map(d.P, d.N), nullptr, 1, d.B * d.P, (int)C, st));
@@ -369,7 +377,7 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
     }
   }
   // ---- attention branch ----
-  TRY(scale_cast_sum(dx1, 0, id, da, 1, id, p.drop_scale_attn, (int)d.T, rows_all, (int)C, gr.dbo, nullptr, 0, st));
+  if (!fuse_da) TRY(scale_cast_sum(dx1, 0, id, da, 1, id, p.drop_scale_attn, (int)d.T, rows_all, (int)C, gr.dbo, nullptr, 0, st));
   TRY(gemm_bf16(linear_dgrad(da, C, p.wo, C, rows_all, C, C, dctx, C, 1), st));
   if (gr.dwo) TRY(gemm_bf16(linear_wgrad(da, C, s.ctx, C, rows_all, C, C, gr.dwo, C), side_fork(st, side)));
   {

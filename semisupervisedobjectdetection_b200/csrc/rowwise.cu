@@ -117,21 +117,27 @@ int layernorm_fwd(const void* x, int x_bf16, RowMap in_map, const float* gamma, 
 // LayerNorm backward:  dx = rstd * (dy*g - mean_c(dy*g) - xhat * mean_c(dy*g*xhat))  (+ dres)
 //                      dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy
 // ------------------------------------------------------------------------------------------------
-template <typename TDy, typename TX, typename TDx, int LN_MAX_CHUNKS>
+// AUX: additionally emit aux = bf16(dx * aux_scale[row / aux_rps]) and aux_colsum[c] += sum_rows of the scaled fp32 values —
+// the drop-path-scaled bf16 copy (and bias gradient) the next GEMMs of the layer backward consume, which used to be a
+// separate scale_cast pass over dx.
+template <typename TDy, typename TX, typename TDx, int LN_MAX_CHUNKS, bool AUX>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDy* __restrict__ dy, const TX* __restrict__ x, RowMap x_map,
                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                      const float* __restrict__ gamma, const float* __restrict__ dres,
                                                      RowMap dres_map, TDx* __restrict__ dx, RowMap dx_map,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows,
-                                                     int C, int rows_per_block, int ns) {
+                                                     int C, int rows_per_block, int ns, __nv_bfloat16* __restrict__ aux,
+                                                     const float* __restrict__ aux_scale, int aux_rps,
+                                                     float* __restrict__ aux_colsum) {
   pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = C >> 2;
-  float4 gacc[LN_MAX_CHUNKS], bacc[LN_MAX_CHUNKS], g[LN_MAX_CHUNKS];
+  float4 gacc[LN_MAX_CHUNKS], bacc[LN_MAX_CHUNKS], g[LN_MAX_CHUNKS], cacc[AUX ? LN_MAX_CHUNKS : 1];
 #pragma unroll
   for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
     gacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     bacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (AUX) cacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int ci = lane + 32 * k;
     g[k] = ci < nchunk ? __ldg(reinterpret_cast<const float4*>(gamma) + ci) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
@@ -171,6 +177,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDy* __restrict__ dy,
     s1 = warp_sum(s1) / (float)C;
     s2 = warp_sum(s2) / (float)C;
     TDx* dxr = dx + map_row(row, dx_map) * C;
+    float asc = 1.f;
+    if (AUX && aux_scale != nullptr) asc = aux_scale[row / aux_rps];
 #pragma unroll
     for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
       const int ci = lane + 32 * k;
@@ -181,8 +189,35 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDy* __restrict__ dy,
         o.z = rs * (dyv[k].z * g[k].z - s1 - xh[k].z * s2) + rv[k].z;
         o.w = rs * (dyv[k].w * g[k].w - s1 - xh[k].w * s2) + rv[k].w;
         Ld4<TDx>::st(dxr + ci * 4, o);
+        if (AUX) {
+          o.x *= asc; o.y *= asc; o.z *= asc; o.w *= asc;
+          Ld4<__nv_bfloat16>::st(aux + row * C + ci * 4, o);
+          cacc[k].x += o.x; cacc[k].y += o.y; cacc[k].z += o.z; cacc[k].w += o.w;
+        }
       }
     }
+  }
+  if (AUX && aux_colsum != nullptr) {
+    // same cross-warp reduce + slotted commit as below, on the third per-column partial
+    extern __shared__ float red[];
+    float* my = red + warp * 2 * C;
+#pragma unroll
+    for (int k = 0; k < LN_MAX_CHUNKS; ++k) {
+      const int ci = lane + 32 * k;
+      if (ci < nchunk) *reinterpret_cast<float4*>(my + ci * 4) = cacc[k];
+    }
+    __syncthreads();
+    float* tot = red + 8 * 2 * C;
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w * 2 * C + c];
+      tot[c] = t;
+    }
+    __syncthreads();
+    // slot columns [2C, 3C): disjoint from the dgamma / dbeta commit below (blocks reach the two commits at different times)
+    colsum_commit(tot, 2 * C, C, 3 * C, ns, blockIdx.x, gridDim.x, 1, [&](int c, float sum) { aux_colsum[c - 2 * C] += sum; });
+    __syncthreads();
   }
   if (dgamma == nullptr) return;
   // cross-warp reduction of the per-column partials, then one atomic per column per block
@@ -205,15 +240,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const TDy* __restrict__ dy,
     tot[c] = t;
   }
   __syncthreads();
-  colsum_commit(tot, 0, 2 * C, 2 * C, ns, blockIdx.x, gridDim.x, 0, [&](int c, float sum) {
+  colsum_commit(tot, 0, 2 * C, AUX ? 3 * C : 2 * C, ns, blockIdx.x, gridDim.x, 0, [&](int c, float sum) {
     if (c < C) dgamma[c] += sum;
     else dbeta[c - C] += sum;
   });
 }
 
-int layernorm_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, RowMap x_map, const float* mean,
-                  const float* rstd, const float* gamma, const float* dres, RowMap dres_map, void* dx, int dx_bf16,
-                  RowMap dx_map, float* dgamma, float* dbeta, long long rows, int C, cudaStream_t stream) {
+static int layernorm_bwd_impl(const void* dy, int dy_bf16, const void* x, int x_bf16, RowMap x_map, const float* mean,
+                              const float* rstd, const float* gamma, const float* dres, RowMap dres_map, void* dx, int dx_bf16,
+                              RowMap dx_map, float* dgamma, float* dbeta, long long rows, int C, void* aux, const float* aux_scale,
+                              int aux_rps, float* aux_colsum, cudaStream_t stream) {
   SFK_REQUIRE(C % 4 == 0 && C <= 4 * 32 * LN_CHUNK_LIMIT, "layernorm_bwd: C=%d unsupported", C);
   if (rows == 0) return 0;
   // one even wave: two resident blocks per SM (register-limited), every block the same number of rows (multiple of the
@@ -223,12 +259,13 @@ int layernorm_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, RowMap
   rows_per_block = (rows_per_block + 7) / 8 * 8;
   const long long grid = (rows + rows_per_block - 1) / rows_per_block;
   const size_t smem = (size_t)9 * 2 * C * sizeof(float);
-  const int ns = colsum_num_slots(2 * C, grid);
-#define LAUNCH_N(TD, TX, TO, NCH)                                                                                       \
-  if (smem > 48 * 1024) cudaFuncSetAttribute(ln_bwd_kernel<TD, TX, TO, NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-  launch_k(ln_bwd_kernel<TD, TX, TO, NCH>, dim3((unsigned)grid), dim3(256), smem, stream, (const TD*)dy, (const TX*)x, x_map, mean, rstd, gamma, \
+  const int ns = colsum_num_slots((aux != nullptr ? 3 : 2) * C, grid);
+#define LAUNCH_NA(TD, TX, TO, NCH, AUXF)                                                                                \
+  if (smem > 48 * 1024) cudaFuncSetAttribute(ln_bwd_kernel<TD, TX, TO, NCH, AUXF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  launch_k(ln_bwd_kernel<TD, TX, TO, NCH, AUXF>, dim3((unsigned)grid), dim3(256), smem, stream, (const TD*)dy, (const TX*)x, x_map, mean, rstd, gamma, \
                                                                         dres, dres_map, (TO*)dx, dx_map, dgamma, dbeta, rows, \
-                                                                        C, rows_per_block, ns)
+                                                                        C, rows_per_block, ns, (__nv_bfloat16*)aux, aux_scale, aux_rps, aux_colsum)
+#define LAUNCH_N(TD, TX, TO, NCH) LAUNCH_NA(TD, TX, TO, NCH, false)
 #define LAUNCH(TD, TX, TO)                               \
   do {                                                   \
     if (C <= 128) { LAUNCH_N(TD, TX, TO, 1); }           \
@@ -238,6 +275,16 @@ int layernorm_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, RowMap
     else { LAUNCH_N(TD, TX, TO, 8); }                    \
   } while (0)
   const int key = (dy_bf16 ? 4 : 0) | (x_bf16 ? 2 : 0) | (dx_bf16 ? 1 : 0);
+  if (aux != nullptr) {
+    SFK_REQUIRE(key == 4, "layernorm_bwd: the fused bf16 copy is built for bf16 dy / fp32 x / fp32 dx only");
+    SFK_REQUIRE(dgamma != nullptr, "layernorm_bwd: the fused bf16 copy needs the parameter-gradient path (shared reduction buffers)");
+    if (C <= 128) { LAUNCH_NA(__nv_bfloat16, float, float, 1, true); }
+    else if (C <= 256) { LAUNCH_NA(__nv_bfloat16, float, float, 2, true); }
+    else if (C <= 384) { LAUNCH_NA(__nv_bfloat16, float, float, 3, true); }
+    else if (C <= 512) { LAUNCH_NA(__nv_bfloat16, float, float, 4, true); }
+    else { LAUNCH_NA(__nv_bfloat16, float, float, 8, true); }
+    return check_launch("ln_bwd_kernel");
+  }
   switch (key) {
     case 0: LAUNCH(float, float, float); break;
     case 1: LAUNCH(float, float, __nv_bfloat16); break;
@@ -250,7 +297,24 @@ int layernorm_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, RowMap
   }
 #undef LAUNCH
 #undef LAUNCH_N
+#undef LAUNCH_NA
   return check_launch("ln_bwd_kernel");
+}
+
+int layernorm_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, RowMap x_map, const float* mean,
+                  const float* rstd, const float* gamma, const float* dres, RowMap dres_map, void* dx, int dx_bf16,
+                  RowMap dx_map, float* dgamma, float* dbeta, long long rows, int C, cudaStream_t stream) {
+  return layernorm_bwd_impl(dy, dy_bf16, x, x_bf16, x_map, mean, rstd, gamma, dres, dres_map, dx, dx_bf16, dx_map, dgamma, dbeta,
+                            rows, C, nullptr, nullptr, 1, nullptr, stream);
+}
+
+// same, also writing aux = bf16(dx * aux_scale[row / aux_rps]) [rows, C] (identity row map) and aux_colsum += column sums
+int layernorm_bwd_aux(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, const float* dres,
+                      void* dx, float* dgamma, float* dbeta, long long rows, int C, void* aux, const float* aux_scale, int aux_rps,
+                      float* aux_colsum, cudaStream_t stream) {
+  RowMap id;
+  return layernorm_bwd_impl(dy, 1, x, 0, id, mean, rstd, gamma, dres, id, dx, 0, id, dgamma, dbeta, rows, C, aux, aux_scale, aux_rps,
+                            aux_colsum, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

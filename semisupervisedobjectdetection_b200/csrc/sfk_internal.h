@@ -85,6 +85,9 @@ int attention_bwd(const AttentionBwdDesc& a, cudaStream_t stream);
 // ---- rowwise.cu ----
 int layernorm_fwd(const void* x, int x_bf16, RowMap in_map, const float* gamma, const float* beta, void* y, int y_bf16,
                   float* mean, float* rstd, long long rows, int C, float eps, cudaStream_t stream);
+int layernorm_bwd_aux(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, const float* dres,
+                      void* dx, float* dgamma, float* dbeta, long long rows, int C, void* aux, const float* aux_scale, int aux_rps,
+                      float* aux_colsum, cudaStream_t stream);
 int layernorm_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, RowMap x_map, const float* mean,
                   const float* rstd, const float* gamma, const float* dres, RowMap dres_map, void* dx, int dx_bf16,
                   RowMap dx_map, float* dgamma, float* dbeta, long long rows, int C, cudaStream_t stream);
