@@ -299,8 +299,19 @@ def run_sfk(args):
         t_ms, t_fl, t_n = ctypes.c_double(), ctypes.c_double(), ctypes.c_longlong()
         lib.sfk_profile_gemm_end(ctypes.byref(t_ms), ctypes.byref(t_fl), ctypes.byref(t_n))
         prof = dict(ms=t_ms.value, flops=t_fl.value, launches=t_n.value)
-        if args.gemm_csv:
-            lib.sfk_profile_gemm_dump(args.gemm_csv.encode())
+        import tempfile
+        csv_path = args.gemm_csv or os.path.join(tempfile.gettempdir(), f"sfk_gemm_shapes_{os.getpid()}.csv")
+        lib.sfk_profile_gemm_dump(csv_path.encode())
+        try:
+            nbytes = 0.0
+            with open(csv_path) as f:
+                for ln in f:
+                    if ln[:1].isdigit():
+                        M_, N_, K_ = (int(v) for v in ln.split(",")[:3])
+                        nbytes += 2.0 * (M_ * K_ + N_ * K_ + M_ * N_)   # both bf16 operands read once + a bf16-sized output
+            prof["bytes"] = nbytes
+        except OSError:
+            pass
     ops.WGRAD_OVERLAP = True
     clocks = sampler.stop() if sampler else None
     # ---- the same step with the decode head's literal sequence (no algebraic fold), reported next to the headline ----
@@ -332,6 +343,12 @@ def run_sfk(args):
             dist.destroy_process_group()
         return
     pk = peaks()
+    traffic = None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "gemm_traffic_r1.json")) as f:
+            traffic = json.load(f)
+    except (OSError, ValueError):
+        pass
     achieved_tf = prof["flops"] / (prof["ms"] * 1e-3) / 1e12 if prof.get("ms") else None
     gemm_share = prof["ms"] / ms_serial if prof.get("ms") else None
     cpu = time_oracle(1, 0, budget_s=60.0) if world == 1 and not args.no_cpu_baseline else None
@@ -362,7 +379,11 @@ def run_sfk(args):
         "device_mallocs_in_timed_region": int(device_mallocs),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel", "achieved": achieved_tf, "peak": pk["tf_sustained"],
-                     "unit": "TFLOP/s", "frac": (achieved_tf / pk["tf_sustained"]) if achieved_tf else None, "traffic": None,
+                     "unit": "TFLOP/s", "frac": (achieved_tf / pk["tf_sustained"]) if achieved_tf else None,
+                     "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
+                     "traffic_how": (traffic["how"] + " (committed under profiles/; dram__bytes_read + write per GEMM launch)") if traffic else None,
+                     "algorithmic_bytes_per_launch": (prof["bytes"] / prof["launches"]) if prof.get("launches") and prof.get("bytes") else None,
+                     "executed_gemm_tflop_per_step": (prof["flops"] / 1e12) if prof.get("flops") else None,
                      "peak_source": pk["source"] + " (sustained cuBLAS bf16: kernel timed inside a long step)",
                      "launches_per_step": prof.get("launches"), "share_of_step": gemm_share,
                      "avg_launch_us": (1000.0 * prof["ms"] / prof["launches"]) if prof.get("launches") else None,
