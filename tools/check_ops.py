@@ -231,7 +231,22 @@ def main():
             din = torch.empty(B, h, w, C, device=dev, dtype=torch.bfloat16)
             L.check(lib.sfk_upsample_concat_bwd(dout.data_ptr(), din.data_ptr(), B, h, w, C, H, W, 2 * C, C, L.stream_ptr()))
             allok &= report("upsample_concat_bwd", din, xr.grad.permute(0, 2, 3, 1), 1e-2)
-        for (M, C, NL, pix, train) in [(2 * 256, 64, 1, 256, 1), (3 * 100, 128, 3, 100, 1), (2 * 256, 768, 1, 256, 0), (512, 256, 2, 128, 1)]:
+        # folded decode head's upsample-add: z0 + sum_i bilinear(z_i) + bias against F.interpolate
+        for (B, H, W, C, dims) in [(2, 32, 32, 64, ((16, 16), (8, 8), (4, 4))), (1, 24, 40, 256, ((12, 20), (6, 10), (3, 5))),
+                                   (2, 16, 16, 768, ((8, 8), (4, 4), (2, 2)))]:
+            z0 = torch.randn(B, H, W, C, device=dev).bfloat16()
+            zs = [torch.randn(B, h, w, C, device=dev).bfloat16() for (h, w) in dims]
+            bias = torch.randn(C, device=dev)
+            out = torch.empty(B, H, W, C, device=dev, dtype=torch.bfloat16)
+            L.check(lib.sfk_upsample_add4(z0.data_ptr(), zs[0].data_ptr(), dims[0][0], dims[0][1], zs[1].data_ptr(), dims[1][0], dims[1][1],
+                                          zs[2].data_ptr(), dims[2][0], dims[2][1], bias.data_ptr(), out.data_ptr(), B, H, W, C,
+                                          L.stream_ptr()))
+            ref = z0.float() + bias
+            for z in zs:
+                ref = ref + F.interpolate(z.float().permute(0, 3, 1, 2), size=(H, W), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+            allok &= report(f"upsample_add4 B{B} {H}x{W} C{C}", out, ref, 1e-2)
+        for (M, C, NL, pix, train) in [(2 * 256, 64, 1, 256, 1), (3 * 100, 128, 3, 100, 1), (2 * 256, 768, 1, 256, 0), (512, 256, 2, 128, 1),
+                                       (4 * 4096, 768, 1, 4096, 1)]:
             x = (torch.randn(M, C, device=dev) * 1.5 + 0.3).bfloat16()
             gamma = torch.rand(C, device=dev) + 0.5
             beta = torch.randn(C, device=dev) * 0.2
