@@ -114,8 +114,9 @@ int layernorm_fwd(const void* x, int x_bf16, RowMap in_map, const float* gamma, 
                   float* mean, float* rstd, long long rows, int C, float eps, cudaStream_t stream) {
   SFK_REQUIRE(C % 4 == 0 && C <= 4 * 32 * LN_CHUNK_LIMIT, "layernorm: C=%d unsupported (need C %% 4 == 0, C <= 1024)", C);
   if (rows == 0) return 0;
-  // ~3 resident blocks per SM, each warp walks rows_per_block / 8 rows
-  const long long slots = (long long)num_sms() * 3;
+  // ~3 resident blocks per SM (8 for narrow rows, where a row is only 256-512 bytes in flight per warp); each warp walks
+  // rows_per_block / 8 rows
+  const long long slots = (long long)num_sms() * (C <= 128 ? 8 : 3);
   int rows_per_block = (int)((rows + slots - 1) / slots);
   rows_per_block = (rows_per_block + 7) / 8 * 8;
   const unsigned grid = (unsigned)((rows + rows_per_block - 1) / rows_per_block);
