@@ -453,12 +453,96 @@ __global__ void __launch_bounds__(256) bn_relu_cls_fwd_kernel(const __nv_bfloat1
   }
 }
 
+// num_labels == 1 forward: per-channel affine and classifier row in registers (each lane owns the same <= 4 chunks of 8
+// channels for every row), two rows in flight per warp, no shared memory in the loop.
+template <int NK, int R>   // NK chunks of 8 channels per lane (C <= 256 * NK), R rows in flight per warp
+__global__ void __launch_bounds__(256) bn_relu_cls1_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ mean,
+                                                               const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, const float* __restrict__ wc,
+                                                               const float* __restrict__ bc, float* __restrict__ logits, long long M,
+                                                               int C, float drop_p, unsigned long long seed, int rows_per_block) {
+  pdl_sync();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunk = C >> 3;
+  float a[NK][8], b[NK][8], w[NK][8];
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    const int ch = lane + 32 * k;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = ch * 8 + j;
+      const bool ok = ch < nchunk;
+      const float aa = ok ? rstd[c] * gamma[c] : 0.f;
+      a[k][j] = aa;
+      b[k][j] = ok ? beta[c] - mean[c] * aa : 0.f;
+      w[k][j] = ok ? wc[c] : 0.f;
+    }
+  }
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const unsigned thr = dropout_thr16(drop_p);
+  const float bias0 = bc[0];
+  const long long row0 = (long long)blockIdx.x * rows_per_block;
+  long long row_end = row0 + rows_per_block;
+  if (row_end > M) row_end = M;
+  for (long long rb = row0 + warp; rb < row_end; rb += 8 * R) {
+    uint4 u[R][NK];
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const long long row = rb + 8 * q;
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const int ch = lane + 32 * k;
+        u[q][k] = (row < row_end && ch < nchunk) ? __ldg(reinterpret_cast<const uint4*>(x + row * C + ch * 8)) : make_uint4(0, 0, 0, 0);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      const long long row = rb + 8 * q;
+      if (row >= row_end) break;
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const int ch = lane + 32 * k;
+        if (ch >= nchunk) break;
+        const uint32_t* up = reinterpret_cast<const uint32_t*>(&u[q][k]);
+        float dm[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        if (drop_p > 0.f) dropout_mult8(seed, (unsigned long long)row * C + ch * 8, thr, keep_scale, dm);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float2 v2 = unpack_bf16x2(up[j >> 1]);
+          const float xv = (j & 1) ? v2.y : v2.x;
+          const float yv = fmaxf(fmaf(xv, a[k][j], b[k][j]), 0.f) * dm[j];
+          acc = fmaf(yv, w[k][j], acc);
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) logits[row] = acc + bias0;   // one label: logits is [B, 1, pix] == [M]
+    }
+  }
+}
+
 int bn_relu_cls_fwd(const void* x, const float* mean, const float* rstd, const float* gamma, const float* beta, const float* wc,
                     const float* bc, float* logits, long long M, int C, int NL, int pix_per_sample, float drop_p,
                     unsigned long long seed, cudaStream_t stream) {
   SFK_REQUIRE(NL >= 1 && NL <= CLS_MAX_LABELS, "bn_relu_cls: num_labels=%d unsupported (1..%d)", NL, CLS_MAX_LABELS);
   SFK_REQUIRE(C % 8 == 0, "bn_relu_cls: C must be a multiple of 8");
   if (M == 0) return 0;
+  if (NL == 1 && C <= 1024) {
+    const long long slots = (long long)num_sms();   // register-heavy: one resident block per SM, one wave
+    int rpb1 = (int)((M + slots - 1) / slots);
+    rpb1 = (rpb1 + 31) / 32 * 32;
+    const long long g1 = (M + rpb1 - 1) / rpb1;
+    if (C <= 256)
+      launch_k(bn_relu_cls1_fwd_kernel<1, 4>, dim3((unsigned)g1), dim3(256), 0, stream, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, wc,
+               bc, logits, M, C, drop_p, seed, rpb1);
+    else if (C <= 768)
+      launch_k(bn_relu_cls1_fwd_kernel<3, 4>, dim3((unsigned)g1), dim3(256), 0, stream, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, wc,
+               bc, logits, M, C, drop_p, seed, rpb1);
+    else
+      launch_k(bn_relu_cls1_fwd_kernel<4, 2>, dim3((unsigned)g1), dim3(256), 0, stream, (const __nv_bfloat16*)x, mean, rstd, gamma, beta, wc,
+               bc, logits, M, C, drop_p, seed, rpb1);
+    return check_launch("bn_relu_cls1_fwd_kernel");
+  }
   const size_t smem = (size_t)(2 + NL) * C * sizeof(float);
   SFK_REQUIRE(smem <= 48 * 1024, "bn_relu_cls: C*(2+NL) too large for shared memory");
   int rpb = 64;
