@@ -27,7 +27,6 @@ struct Arena {
     off += n * sizeof(T);
     return p;
   }
-  bool ok() const { return base == nullptr || off <= cap; }
 };
 
 struct Dims {
