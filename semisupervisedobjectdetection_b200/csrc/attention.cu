@@ -292,8 +292,12 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
+// sfk_set_option("attn_bwd_persist", 0|1): one persistent CTA per SM walking an equal share of the (batch, head, K/V block,
+// query tile) units (default) instead of one CTA per (K/V block, query range)
+int g_attn_bwd_persist = 1;
+
 struct AttBwdParams {
-  int T, Tk, heads;
+  int T, Tk, heads, batches;
   int q_tiles_per_cta, q_tiles;
   float scale, scale_log2;
   const float* lse;    // [B, heads, T] log2 domain
@@ -531,6 +535,276 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 }
 
 template <int D>
+__global__ void __launch_bounds__(288, 1)
+attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
+                const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
+                const AttBwdParams p) {
+  pdl_launch_dependents();
+  using Cfg = AttCfg<D>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  // tiles: K, V (resident), Q[2], dO[2] (double buffered), P^T (32 KB), dS^T (32 KB), lse/delta [2][2][128] floats
+  const uint32_t sK = base, sV = sK + Cfg::TILE;
+  const uint32_t sQ = sV + Cfg::TILE;             // 2 buffers
+  const uint32_t sDO = sQ + 2 * Cfg::TILE;        // 2 buffers
+  const uint32_t sPT = sDO + 2 * Cfg::TILE;
+  const uint32_t sDS = sPT + 32768;
+  const uint32_t off_stats = 6 * Cfg::TILE + 65536;
+  uint8_t* sPT_gen = gen + 6 * Cfg::TILE;
+  uint8_t* sDS_gen = sPT_gen + 32768;
+  float* stats = reinterpret_cast<float*>(gen + off_stats);  // [buf][0: lse, 1: delta][128]
+  const uint32_t bars = base + off_stats + 2048;
+  const uint32_t b_kvfull = bars, b_qfull = bars + 8 /*2*/, b_spfull = bars + 24, b_pdready = bars + 32, b_dqfull = bars + 40,
+                 b_tilefree = bars + 48 /*2*/, b_dqfree = bars + 64, b_statsfree = bars + 72 /*2*/, b_final = bars + 88,
+                 b_kvdrained = bars + 96, tmem_slot = bars + 104;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(gen + off_stats + 2048 + 104);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // persistent even split: the (batch, head, K/V block, query tile) units, query tile fastest, form one list; CTA c owns the
+  // contiguous range [c U / G, (c+1) U / G).  Consecutive units with the same K/V block form a segment: K/V stay in shared
+  // memory and dK/dV in tensor memory across it, then flush by atomics (they are atomics anyway: several CTAs share a block).
+  const int kv_blocks = (p.Tk + ATT_BN - 1) / ATT_BN;
+  const long long U = (long long)p.batches * p.heads * kv_blocks * p.q_tiles;
+  const long long u_begin = U * blockIdx.x / gridDim.x, u_end = U * (blockIdx.x + 1) / gridDim.x;
+  const int ntiles = (int)(u_end - u_begin);
+  auto decode = [&](long long u, int& qt, int& kvb, int& hd, int& bt) {
+    qt = (int)(u % p.q_tiles);
+    long long t = u / p.q_tiles;
+    kvb = (int)(t % kv_blocks);
+    t /= kv_blocks;
+    hd = (int)(t % p.heads);
+    bt = (int)(t / p.heads);
+  };
+
+  if (threadIdx.x == 256) {
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
+    mbar_init(b_kvfull, 1);
+    mbar_init(b_qfull, 1); mbar_init(b_qfull + 8, 1);
+    mbar_init(b_spfull, 1); mbar_init(b_pdready, 256); mbar_init(b_dqfull, 1);
+    mbar_init(b_tilefree, 1); mbar_init(b_tilefree + 8, 1);
+    mbar_init(b_dqfree, 256);
+    mbar_init(b_statsfree, 256); mbar_init(b_statsfree + 8, 256);
+    mbar_init(b_final, 1);
+    mbar_init(b_kvdrained, 256);
+    mbar_fence_init();
+  }
+  if (warp == 8) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  pdl_wait();  // setup above overlaps the previous kernel's tail
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_gen;
+  const uint32_t tST = tmem, tDPT = tmem + 128, tDV = tmem + 256, tDK = tmem + 256 + D, tDQ = tmem + 256 + 2 * D;
+
+  if (warp == 8) {
+    if (lane == 0 && ntiles > 0) {
+      // ---------------- control thread ----------------
+      const uint32_t idesc_s = umma_idesc_bf16(128, ATT_BM, 0, 0);   // S^T / dP^T : [kv x q]
+      const uint32_t idesc_kv = umma_idesc_bf16(128, D, 0, 1);       // dV / dK    : A = P^T|dS^T (K-major), B = dO|Q (MN-major)
+      const uint32_t idesc_dq = umma_idesc_bf16(128, D, 1, 1);       // dQ         : A = dS^T as MN-major, B = K (MN-major)
+      int qt, kvb, head, batch;
+      decode(u_begin, qt, kvb, head, batch);
+      mbar_arrive_expect_tx(b_kvfull, 2 * Cfg::TILE);
+      tma_load_3d(sK, &tmap_k, b_kvfull, head * D, kvb * ATT_BN, batch);
+      tma_load_3d(sV, &tmap_v, b_kvfull, head * D, kvb * ATT_BN, batch);
+      // prefetch first query tile
+      mbar_arrive_expect_tx(b_qfull, 2 * Cfg::TILE);
+      tma_load_3d(sQ, &tmap_q, b_qfull, head * D, qt * ATT_BM, batch);
+      tma_load_3d(sDO, &tmap_do, b_qfull, head * D, qt * ATT_BM, batch);
+      mbar_wait(b_kvfull, 0);
+      int seg = 0;           // segment index (K/V block changes)
+      bool seg_first = true; // first tile of the current segment: dV / dK start from zero
+      for (int i = 0; i < ntiles; ++i) {
+        const int buf = i & 1;
+        const uint32_t ph_buf = (i >> 1) & 1;   // phase of per-buffer barriers
+        const uint32_t ph = i & 1;              // phase of once-per-tile barriers
+        // coordinates of the next unit; does it start a new segment?
+        int nqt = 0, nkvb = kvb, nhead = head, nbatch = batch;
+        const bool has_next = i + 1 < ntiles;
+        if (has_next) decode(u_begin + i + 1, nqt, nkvb, nhead, nbatch);
+        const bool seg_last = !has_next || nkvb != kvb || nhead != head || nbatch != batch;
+        // prefetch the next tile into the other buffer once the MMAs that read it (tile i-1) have retired
+        if (has_next) {
+          const int nb = buf ^ 1;
+          if (i >= 1) mbar_wait(b_tilefree + 8 * nb, ((i - 1) >> 1) & 1);
+          mbar_arrive_expect_tx(b_qfull + 8 * nb, 2 * Cfg::TILE);
+          tma_load_3d(sQ + nb * Cfg::TILE, &tmap_q, b_qfull + 8 * nb, nhead * D, nqt * ATT_BM, nbatch);
+          tma_load_3d(sDO + nb * Cfg::TILE, &tmap_do, b_qfull + 8 * nb, nhead * D, nqt * ATT_BM, nbatch);
+        }
+        mbar_wait(b_qfull + 8 * buf, ph_buf);
+        tc_fence_after();
+        const uint32_t q_s = sQ + buf * Cfg::TILE, do_s = sDO + buf * Cfg::TILE;
+#pragma unroll
+        for (int kk = 0; kk < Cfg::KSTEPS; ++kk)
+          umma_bf16(tST, umma_smem_desc_lt(sK + kk * 32, 16, 8 * Cfg::RB, Cfg::LT),
+                    umma_smem_desc_lt(q_s + kk * 32, 16, 8 * Cfg::RB, Cfg::LT), idesc_s, kk > 0 ? 1u : 0u);
+#pragma unroll
+        for (int kk = 0; kk < Cfg::KSTEPS; ++kk)
+          umma_bf16(tDPT, umma_smem_desc_lt(sV + kk * 32, 16, 8 * Cfg::RB, Cfg::LT),
+                    umma_smem_desc_lt(do_s + kk * 32, 16, 8 * Cfg::RB, Cfg::LT), idesc_s, kk > 0 ? 1u : 0u);
+        umma_commit(b_spfull);
+        mbar_wait(b_pdready, ph);
+        if (i >= 1) mbar_wait(b_dqfree, (i - 1) & 1);   // dQ TMEM of tile i-1 drained
+        if (seg_first && seg >= 1) mbar_wait(b_kvdrained, (seg - 1) & 1);   // previous segment's dK / dV read out
+        tc_fence_after();
+#pragma unroll
+        for (int ks = 0; ks < ATT_BM / 16; ++ks) {
+          const uint32_t a_off = (ks >> 2) * 16384 + (ks & 3) * 32;
+          umma_bf16(tDV, umma_smem_desc_lt(sPT + a_off, 16, 1024, 2u),
+                    umma_smem_desc_lt(do_s + ks * 16 * Cfg::RB, 128 * Cfg::RB, 8 * Cfg::RB, Cfg::LT), idesc_kv,
+                    (!seg_first || ks > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < ATT_BM / 16; ++ks) {
+          const uint32_t a_off = (ks >> 2) * 16384 + (ks & 3) * 32;
+          umma_bf16(tDK, umma_smem_desc_lt(sDS + a_off, 16, 1024, 2u),
+                    umma_smem_desc_lt(q_s + ks * 16 * Cfg::RB, 128 * Cfg::RB, 8 * Cfg::RB, Cfg::LT), idesc_kv,
+                    (!seg_first || ks > 0) ? 1u : 0u);
+        }
+        // dQ[q, d] = sum_kv dS[q, kv] K[kv, d]: A = dS^T tile read as MN-major (m = q contiguous, k = kv rows)
+#pragma unroll
+        for (int ks = 0; ks < ATT_BN / 16; ++ks)
+          umma_bf16(tDQ, umma_smem_desc_lt(sDS + ks * 2048, 16384, 1024, 2u),
+                    umma_smem_desc_lt(sK + ks * 16 * Cfg::RB, 128 * Cfg::RB, 8 * Cfg::RB, Cfg::LT), idesc_dq,
+                    ks > 0 ? 1u : 0u);
+        umma_commit(b_dqfull);
+        umma_commit(b_tilefree + 8 * buf);
+        seg_first = false;
+        if (seg_last) {
+          umma_commit(b_final);
+          if (has_next) {
+            // next segment: K / V may be overwritten once every MMA of this one has retired
+            mbar_wait(b_final, seg & 1);
+            mbar_arrive_expect_tx(b_kvfull, 2 * Cfg::TILE);
+            tma_load_3d(sK, &tmap_k, b_kvfull, nhead * D, nkvb * ATT_BN, nbatch);
+            tma_load_3d(sV, &tmap_v, b_kvfull, nhead * D, nkvb * ATT_BN, nbatch);
+            mbar_wait(b_kvfull, (seg + 1) & 1);
+            ++seg;
+            seg_first = true;
+          }
+        }
+        qt = nqt; kvb = nkvb; head = nhead; batch = nbatch;
+      }
+    }
+  } else if (ntiles > 0) {
+    // ---------------- 256 math threads: threads r and r + 128 share K/V row kv0+r (S^T, dP^T, dK, dV) and query row r of
+    // dQ; each takes one half of the columns (two warps per TMEM lane quadrant) ----------------
+    const int r = threadIdx.x & 127;
+    const int hhalf = threadIdx.x >> 7;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    int qt, kvb, head, batch;
+    decode(u_begin, qt, kvb, head, batch);
+    int seg = 0;
+    for (int i = 0; i < ntiles; ++i) {
+      const int buf = i & 1;
+      const uint32_t ph = i & 1;
+      int nqt = 0, nkvb = kvb, nhead = head, nbatch = batch;
+      const bool has_next = i + 1 < ntiles;
+      if (has_next) decode(u_begin + i + 1, nqt, nkvb, nhead, nbatch);
+      const bool seg_last = !has_next || nkvb != kvb || nhead != head || nbatch != batch;
+      const int kv0 = kvb * ATT_BN;
+      const bool kv_ok = (kv0 + r) < p.Tk;
+      const long long stat_base = ((long long)batch * p.heads + head) * p.T;
+      const int t0 = qt * ATT_BM;
+      // stage lse / delta of this query tile (thread r loads query t0 + r)
+      if (i >= 2) mbar_wait(b_statsfree + 8 * buf, ((i - 2) >> 1) & 1);
+      {
+        const int t = t0 + r;
+        if (hhalf == 0) stats[buf * 256 + r] = t < p.T ? p.lse[stat_base + t] : INFINITY;
+        else stats[buf * 256 + 128 + r] = t < p.T ? p.delta[stat_base + t] : 0.f;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      mbar_wait(b_spfull, ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int cc = hhalf * (ATT_BM / 2); cc < (hhalf + 1) * (ATT_BM / 2); cc += 32) {
+        uint32_t s[32], dp[32];
+        tmem_ld_32x32(tST + lane_base + cc, s);
+        tmem_ld_32x32(tDPT + lane_base + cc, dp);
+        tmem_ld_wait();
+        float pv[32], dsv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float l2 = stats[buf * 256 + cc + j];
+          const float dl = stats[buf * 256 + 128 + cc + j];
+          const float pr = kv_ok ? exp2f(fmaf(__uint_as_float(s[j]), p.scale_log2, -l2)) : 0.f;
+          pv[j] = pr;
+          dsv[j] = pr * (__uint_as_float(dp[j]) - dl) * p.scale;
+        }
+        uint8_t* tp = sPT_gen + (cc >> 6) * 16384;
+        uint8_t* td = sDS_gen + (cc >> 6) * 16384;
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          uint4 o;
+          o.x = pack_bf16x2(pv[j8 * 8 + 0], pv[j8 * 8 + 1]); o.y = pack_bf16x2(pv[j8 * 8 + 2], pv[j8 * 8 + 3]);
+          o.z = pack_bf16x2(pv[j8 * 8 + 4], pv[j8 * 8 + 5]); o.w = pack_bf16x2(pv[j8 * 8 + 6], pv[j8 * 8 + 7]);
+          st_swizzled_chunk(tp, r, ((cc & 63) >> 3) + j8, o);
+          o.x = pack_bf16x2(dsv[j8 * 8 + 0], dsv[j8 * 8 + 1]); o.y = pack_bf16x2(dsv[j8 * 8 + 2], dsv[j8 * 8 + 3]);
+          o.z = pack_bf16x2(dsv[j8 * 8 + 4], dsv[j8 * 8 + 5]); o.w = pack_bf16x2(dsv[j8 * 8 + 6], dsv[j8 * 8 + 7]);
+          st_swizzled_chunk(td, r, ((cc & 63) >> 3) + j8, o);
+        }
+      }
+      mbar_arrive(b_statsfree + 8 * buf);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(b_pdready);
+      // dQ tile -> global (thread r = query row t0 + r)
+      mbar_wait(b_dqfull, ph);
+      tc_fence_after();
+      {
+        const int t = t0 + r;
+        float* dst = p.dq + batch * p.dq_batch_stride + (long long)t * p.ld_dq + head * D;
+#pragma unroll
+        for (int cc = hhalf * 32; cc < D; cc += 64) {
+          uint32_t v[32];
+          tmem_ld_32x32(tDQ + lane_base + cc, v);
+          tmem_ld_wait();
+          if (t < p.T) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              red_add_v4_f32_g(dst + cc + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                               __uint_as_float(v[j + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(b_dqfree);
+      if (seg_last) {
+        // dK / dV of this segment's K/V block
+        mbar_wait(b_final, seg & 1);
+        tc_fence_after();
+        float* dkp = p.dk + batch * p.dkv_batch_stride + (long long)(kv0 + r) * p.ld_dkv + head * D;
+        float* dvp = p.dv + batch * p.dkv_batch_stride + (long long)(kv0 + r) * p.ld_dkv + head * D;
+#pragma unroll
+        for (int cc = hhalf * 32; cc < D; cc += 64) {
+          uint32_t a[32], b[32];
+          tmem_ld_32x32(tDK + lane_base + cc, a);
+          tmem_ld_32x32(tDV + lane_base + cc, b);
+          tmem_ld_wait();
+          if (kv_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              red_add_v4_f32_g(dkp + cc + j, __uint_as_float(a[j]), __uint_as_float(a[j + 1]), __uint_as_float(a[j + 2]),
+                               __uint_as_float(a[j + 3]));
+              red_add_v4_f32_g(dvp + cc + j, __uint_as_float(b[j]), __uint_as_float(b[j + 1]), __uint_as_float(b[j + 2]),
+                               __uint_as_float(b[j + 3]));
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(b_kvdrained);
+        ++seg;
+      }
+      qt = nqt; kvb = nkvb; head = nhead; batch = nbatch;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+template <int D>
 static int attn_bwd_launch(const AttentionBwdDesc& a, cudaStream_t stream) {
   using Cfg = AttCfg<D>;
   CUtensorMap tq, tdo, tk, tv;
@@ -577,6 +851,19 @@ static int attn_bwd_launch(const AttentionBwdDesc& a, cudaStream_t stream) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     SFK_REQUIRE(e == cudaSuccess, "attention_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
+  }
+  p.batches = a.B;
+  if (g_attn_bwd_persist) {
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaError_t e = cudaFuncSetAttribute(attn_bwd_persist_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      SFK_REQUIRE(e == cudaSuccess, "attention_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      attr2 = true;
+    }
+    const long long units = base_ctas * p.q_tiles;
+    const int grid_p = (int)(units < num_sms() ? units : num_sms());
+    launch_k(attn_bwd_persist_kernel<D>, dim3(grid_p), dim3(288), smem, stream, tq, tdo, tk, tv, p);
+    return check_launch("attn_bwd_persist_kernel");
   }
   dim3 grid(kv_blocks * qsplits, a.heads, a.B);
   launch_k(attn_bwd_kernel<D>, dim3(grid), dim3(288), smem, stream, tq, tdo, tk, tv, p);

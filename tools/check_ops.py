@@ -184,7 +184,9 @@ def main():
         allok &= report("im2col_nchw_f32 pad zero", A[:, 147:], torch.zeros(128, 5, device=dev), 1.0) if False else allok
     elif group in ("attn_fwd", "attn_bwd"):
         cases = [(2, 1, 256, 128, 64), (2, 2, 300, 256, 64), (1, 5, 1024, 266, 64), (2, 8, 64, 64, 64), (2, 1, 16, 4, 32),
-                 (2, 2, 67, 19, 32), (1, 8, 256, 259, 32), (1, 1, 16384, 256, 64), (2, 2, 130, 700, 64)]
+                 (2, 2, 67, 19, 32), (1, 8, 256, 259, 32), (1, 1, 16384, 256, 64), (2, 2, 130, 700, 64),
+                 # more units than SMs: persistent CTAs whose ranges cross K/V blocks, heads and samples
+                 (16, 5, 1024, 256, 64), (4, 3, 900, 300, 32), (3, 2, 2000, 130, 64)]
         for (B, heads, T, Tk, D) in cases:
             C = heads * D
             q = (torch.randn(B, T, C, device=dev) * 1.5).bfloat16()
