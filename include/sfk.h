@@ -47,7 +47,7 @@ int sfk_profile_gemm_dump(const char* path);
 
 /* Tuning switches: "gemm_cluster2" = CTA-pair (tcgen05 cta_group::2, 256-row MMA, B split across the pair) GEMM tiles:
  * 0 never, 1 (default) for large problems (M*N*K >= 1e11, K >= 1024), 2 whenever the shape allows; "gemm_occ2" (default 1) = two co-resident CTAs per SM for K <= 512 GEMMs; "dw_bwd_vec" (2 | 4, default 4)
- * = channels per thread of the depthwise-conv backward kernel; "sr_tma_patch" (default 1) = the SR conv's GEMMs read their
+ * = channels per thread of the depthwise-conv backward kernel; "attn_bwd_persist" (default 1) = persistent evenly split attention backward; "sr_tma_patch" (default 1) = the SR conv's GEMMs read their
  * k == stride patches through a rank-5 TMA view of the activation (implicit im2col) instead of a gathered copy. */
 int sfk_set_option(const char* name, int value);
 
