@@ -535,10 +535,20 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     if (g.atomic_add) {
       const long long tiles = (long long)(p.cluster2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
       const int sms = p.cluster2 ? num_sms() / 2 : num_sms();   // schedulable units: CTAs or CTA pairs
-      if (tiles < 2 * sms) splits = (int)((2LL * sms + tiles - 1) / tiles);
-      // keep at least 8 k-blocks per split so the pipeline has something to overlap
-      const int max_splits = p.k_blocks >= 8 ? p.k_blocks / 8 : 1;
-      if (splits > max_splits) splits = max_splits;
+      // Split-K count by a round model instead of "fill 2 x SMs": cost = rounds x (k-blocks per split + fixed per-unit
+      // cost), rounds = ceil(tiles x splits / SMs).  The old rule gave e.g. 20 tiles x 15 splits = 300 units = 3 rounds
+      // on 148 SMs for the 1280 x 320 x 16384 wgrad; 7 splits = 140 units = 1 round does the same work in ~60 % of
+      // the time with half the atomic traffic.  The fixed cost (prologue + fp32 red.add epilogue of a 128 x bn tile)
+      // is worth ~8 k-blocks.
+      const int kOver = 8;
+      const int max_s = p.k_blocks < 2 * sms ? p.k_blocks : 2 * sms;
+      long long best_cost = -1;
+      for (int sp = 1; sp <= max_s; ++sp) {
+        const long long per = (p.k_blocks + sp - 1) / sp;
+        const long long rounds = (tiles * sp + sms - 1) / sms;
+        const long long cost = rounds * (per + kOver);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; splits = sp; }
+      }
     }
   }
   if (splits > p.k_blocks) splits = p.k_blocks;
