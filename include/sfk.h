@@ -56,6 +56,11 @@ int sfk_set_option(const char* name, int value);
  * 6 first tile stored, 7 CTA done.  NULL switches it off. */
 int sfk_debug_gemm_trace(void* device_u64x8);
 
+/* Launch plan sfk_gemm_bf16 would use for this shape, without touching the device (host logic, testable on CPU):
+ * out8 = {block_n, splits, pipeline stages, grid (CTAs), cta_pair mode, TMEM columns per CTA (256 = two CTAs per SM),
+ *         dynamic shared memory bytes, output tiles}.  splits / block_n: 0 = automatic, as in sfk_gemm_bf16. */
+int sfk_gemm_plan(int M, int N, int K, int a_mn, int b_mn, int out_bf16, int atomic_add, int splits, int block_n, int* out8);
+
 /* ---- dense contractions (tcgen05 + TMA + TMEM) ------------------------------------------------------------
  * D[M,N] = alpha * (A · B^T) (+ bias[N]) (* row_scale[row / rows_per_scale]) (+ residual[M,N] f32) (relu)
  *   a: bf16.  a_mn == 0: stored [M, lda], K contiguous.   a_mn == 1: stored [K, lda], M contiguous.

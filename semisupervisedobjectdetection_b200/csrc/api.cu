@@ -26,6 +26,14 @@ int sfk_debug_gemm_trace(void* device_u64x8) {
   return 0;
 }
 
+int sfk_gemm_plan(int M, int N, int K, int a_mn, int b_mn, int out_bf16, int atomic_add, int splits, int block_n, int* out8) {
+  if (out8 == nullptr) { set_error("sfk_gemm_plan: null output"); return -1; }
+  GemmDesc g;
+  g.M = M; g.N = N; g.K = K; g.a_mn = a_mn; g.b_mn = b_mn; g.out_bf16 = out_bf16; g.atomic_add = atomic_add;
+  g.splits = splits; g.block_n = block_n;
+  return gemm_plan(g, out8);
+}
+
 int sfk_gemm_bf16(const void* a, long long lda, int a_mn, const void* b, long long ldb, int b_mn, int M, int N, int K,
                   float alpha, const float* bias, const float* residual, long long ldr, const float* row_scale,
                   int rows_per_scale, void* out, long long ldo, int out_bf16, int atomic_add, int relu, int splits,

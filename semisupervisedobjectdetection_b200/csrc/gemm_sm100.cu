@@ -466,22 +466,12 @@ static int pick_block_n_pair(int N, int b_mn, int M, int atomic_add) {
   return best;
 }
 
-int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
+// Host-side launch plan: tile width, residency mode (1 CTA/SM, 2 CTAs/SM, CTA pairs), split-K count, pipeline depth, grid.
+// Pure arithmetic on the problem shape (no device access beyond the cached SM count), so tests can exercise it without a GPU
+// through sfk_gemm_plan().
+static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, size_t& smem_bytes) {
   SFK_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
-  SFK_REQUIRE(g.a != nullptr && g.b != nullptr && g.out != nullptr, "gemm: null pointer");
-  SFK_REQUIRE((reinterpret_cast<uintptr_t>(g.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.b) & 15) == 0,
-              "gemm: operands must be 16-byte aligned");
-  SFK_REQUIRE((g.lda % 8) == 0 && (g.ldb % 8) == 0, "gemm: lda/ldb must be multiples of 8 elements (lda=%lld ldb=%lld)",
-              g.lda, g.ldb);
-  const int esz = g.out_bf16 ? 2 : 4;
-  SFK_REQUIRE((reinterpret_cast<uintptr_t>(g.out) & 15) == 0 && ((g.ldo * esz) % 16) == 0,
-              "gemm: output must be 16-byte aligned with a 16-byte multiple row pitch");
   SFK_REQUIRE(!(g.atomic_add && g.out_bf16), "gemm: atomic accumulation needs an fp32 output");
-  if (g.residual) SFK_REQUIRE((reinterpret_cast<uintptr_t>(g.residual) & 15) == 0 && (g.ldr % 4) == 0,
-                              "gemm: residual must be 16-byte aligned");
-  if (g.bias) SFK_REQUIRE((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
-
-  GemmKernelParams p;
   p.M = g.M; p.N = g.N; p.K = g.K;
   p.a_mn = g.a_mn ? 1 : 0;
   p.b_mn = g.b_mn ? 1 : 0;
@@ -499,7 +489,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     SFK_REQUIRE(g.N == g.b_patch.sr * g.b_patch.sr * g.b_patch.C && g.K == g.b_patch.B * g.b_patch.Ho * g.b_patch.Wo,
                 "gemm: B patch view does not match N=%d K=%d", g.N, g.K);
   }
-  const bool pair_wanted = !a_patch && !b_patch && g_gemm_cluster2 == 2 || (g_gemm_cluster2 == 1 && (double)g.M * g.N * g.K >= 1.0e11 && g.K >= 1024);
+  const bool pair_wanted = !a_patch && !b_patch &&
+                           (g_gemm_cluster2 == 2 || (g_gemm_cluster2 == 1 && (double)g.M * g.N * g.K >= 1.0e11 && g.K >= 1024));
   if (pair_wanted && g.M > BLOCK_M && (num_sms() % 2 == 0)) {
     if (g.block_n > 0) {
       if (g.block_n % 32 == 0 && (!p.b_mn || g.block_n % 128 == 0)) pair_bn = g.block_n;
@@ -577,6 +568,60 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   p.relu = g.relu;
   p.trace = g_gemm_trace;
 
+  p.a_patch = a_patch ? 1 : 0;
+  p.pa_rows_b = a_patch ? g.a_patch.Ho * g.a_patch.Wo : 1;
+  p.pa_wo = a_patch ? g.a_patch.Wo : 1;
+  p.pa_kspan = a_patch ? g.a_patch.sr * g.a_patch.C / BLOCK_K : 1;
+  p.b_patch = b_patch ? 1 : 0;
+  p.pb_rows_b = b_patch ? g.b_patch.Ho * g.b_patch.Wo : 1;
+  p.pb_wo = b_patch ? g.b_patch.Wo : 1;
+  p.pb_span = b_patch ? g.b_patch.sr * g.b_patch.C : 1;
+  smem_bytes = (size_t)p.stages * p.stage_bytes + EPI_BIAS_OFF + EPI_BIAS_BYTES + 1024;
+  const long long units = (long long)(p.cluster2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles * p.splits;
+  if (p.cluster2) {
+    const long long clusters = units < num_sms() / 2 ? units : num_sms() / 2;
+    grid = (int)(2 * clusters);
+  } else {
+    const long long slots = (long long)num_sms() * (p.tmem_cols == 256 ? 2 : 1);
+    grid = (int)(units < slots ? units : slots);
+  }
+  return 0;
+}
+
+int gemm_plan(const GemmDesc& g, int out[8]) {
+  GemmKernelParams p;
+  int grid = 0;
+  size_t smem = 0;
+  const int rc = gemm_make_plan(g, p, grid, smem);
+  if (rc) return rc;
+  out[0] = p.block_n; out[1] = p.splits; out[2] = p.stages; out[3] = grid;
+  out[4] = p.cluster2; out[5] = p.tmem_cols; out[6] = (int)smem; out[7] = p.m_tiles * p.n_tiles;
+  return 0;
+}
+
+int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
+  SFK_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  SFK_REQUIRE(g.a != nullptr && g.b != nullptr && g.out != nullptr, "gemm: null pointer");
+  SFK_REQUIRE((reinterpret_cast<uintptr_t>(g.a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g.b) & 15) == 0,
+              "gemm: operands must be 16-byte aligned");
+  SFK_REQUIRE((g.lda % 8) == 0 && (g.ldb % 8) == 0, "gemm: lda/ldb must be multiples of 8 elements (lda=%lld ldb=%lld)",
+              g.lda, g.ldb);
+  const int esz = g.out_bf16 ? 2 : 4;
+  SFK_REQUIRE((reinterpret_cast<uintptr_t>(g.out) & 15) == 0 && ((g.ldo * esz) % 16) == 0,
+              "gemm: output must be 16-byte aligned with a 16-byte multiple row pitch");
+  SFK_REQUIRE(!(g.atomic_add && g.out_bf16), "gemm: atomic accumulation needs an fp32 output");
+  if (g.residual) SFK_REQUIRE((reinterpret_cast<uintptr_t>(g.residual) & 15) == 0 && (g.ldr % 4) == 0,
+                              "gemm: residual must be 16-byte aligned");
+  if (g.bias) SFK_REQUIRE((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
+
+  GemmKernelParams p;
+  int grid = 0;
+  size_t smem = 0;
+  {
+    const int prc = gemm_make_plan(g, p, grid, smem);
+    if (prc) return prc;
+  }
+  const bool a_patch = p.a_patch != 0, b_patch = p.b_patch != 0;
   CUtensorMap ta, tb;
   int rc;
   auto patch_map = [&](CUtensorMap* t, const void* base, const PatchView& v, int rows) {
@@ -587,14 +632,6 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     const uint32_t box[5] = {64, 1, (uint32_t)v.Wo, (uint32_t)(rows / v.Wo), 1};
     return make_tmap_5d_bf16(t, base, dims, strides, box);
   };
-  p.a_patch = a_patch ? 1 : 0;
-  p.pa_rows_b = a_patch ? g.a_patch.Ho * g.a_patch.Wo : 1;
-  p.pa_wo = a_patch ? g.a_patch.Wo : 1;
-  p.pa_kspan = a_patch ? g.a_patch.sr * g.a_patch.C / BLOCK_K : 1;
-  p.b_patch = b_patch ? 1 : 0;
-  p.pb_rows_b = b_patch ? g.b_patch.Ho * g.b_patch.Wo : 1;
-  p.pb_wo = b_patch ? g.b_patch.Wo : 1;
-  p.pb_span = b_patch ? g.b_patch.sr * g.b_patch.C : 1;
   if (a_patch) rc = patch_map(&ta, g.a, g.a_patch, BLOCK_M);
   else if (!p.a_mn) rc = make_tmap_2d_bf16(&ta, g.a, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda * 2, BLOCK_K, BLOCK_M);
   else         rc = make_tmap_2d_bf16(&ta, g.a, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)g.lda * 2, 64, BLOCK_K);
@@ -605,22 +642,12 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   else         rc = make_tmap_2d_bf16(&tb, g.b, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb * 2, 64, BLOCK_K);
   if (rc) return rc;
 
-  const size_t smem = (size_t)p.stages * p.stage_bytes + EPI_BIAS_OFF + EPI_BIAS_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     SFK_REQUIRE(e == cudaSuccess, "gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
-  }
-  const long long units = (long long)(p.cluster2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles * p.splits;
-  int grid;
-  if (p.cluster2) {
-    const long long clusters = units < num_sms() / 2 ? units : num_sms() / 2;
-    grid = (int)(2 * clusters);
-  } else {
-    const long long slots = (long long)num_sms() * (p.tmem_cols == 256 ? 2 : 1);
-    grid = (int)(units < slots ? units : slots);
   }
   prof_gemm_shape(g.M, g.N, g.K, (g.a_mn ? 1 : 0) | (g.b_mn ? 2 : 0) | (g.atomic_add ? 4 : 0) | (p.splits << 8) | ((long long)p.block_n << 20));
   prof_gemm_begin(2.0 * (double)g.M * (double)g.N * (double)g.K, stream);

@@ -56,6 +56,8 @@ struct GemmDesc {
 };
 
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream);
+// launch plan only (no device work): out = {block_n, splits, stages, grid, cta_pair, tmem_cols, smem_bytes, tiles}
+int gemm_plan(const GemmDesc& g, int out[8]);
 
 // ---- attention.cu ----
 struct AttentionDesc {

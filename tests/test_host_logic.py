@@ -121,3 +121,75 @@ def test_grad_bucketer_allreduce_world2_gloo():
     port = 29500 + (os.getpid() % 500)
     mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
     assert out[0] and out[1]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GEMM launch planner (host logic of csrc/gemm_sm100.cu, reachable without a GPU through sfk_gemm_plan)
+# ---------------------------------------------------------------------------------------------------------------
+def _plan(M, N, K, a_mn=0, b_mn=0, out_bf16=1, atomic=0, splits=0, block_n=0):
+    import ctypes
+    from semisupervisedobjectdetection_b200 import _lib as L
+    lib = L.load()
+    out = (ctypes.c_int * 8)()
+    rc = lib.sfk_gemm_plan(M, N, K, a_mn, b_mn, out_bf16, atomic, splits, block_n, out)
+    assert rc == 0, L.last_error()
+    keys = ("block_n", "splits", "stages", "grid", "pair", "tmem_cols", "smem", "tiles")
+    return dict(zip(keys, list(out)))
+
+
+def test_gemm_plan_invariants_over_the_mit_shapes():
+    """Every forward / dgrad / wgrad shape of MiT-b0..b5 at 512x512 (batch 16): legal tile widths, pipeline depth, grids that
+    fit the machine, shared memory within the 227 KB (113 KB when two CTAs share an SM) budgets."""
+    SMS = 148   # num_sms() falls back to the B200 count without a device
+    stages_cfg = [(262144, 64, 256), (65536, 128, 512), (16384, 320, 1280), (4096, 512, 2048),     # b1..b5: (tokens, C, 4C)
+                  (262144, 32, 128), (65536, 64, 256), (16384, 160, 640), (4096, 256, 1024)]       # b0
+    shapes = []
+    for T, C, H4 in stages_cfg:
+        shapes += [(T, C, C, 0, 0, 0), (T, H4, C, 0, 0, 0), (T, C, H4, 0, 0, 0),           # q/o, dense1, dense2
+                   (T, C, C, 0, 1, 0), (T, C, H4, 0, 1, 0), (T, H4, C, 0, 1, 0),           # dgrads (MN-major B)
+                   (C, C, T, 1, 1, 1), (H4, C, T, 1, 1, 1), (C, H4, T, 1, 1, 1)]           # wgrads (split-K, atomics)
+    shapes += [(262144, 768, 3072, 0, 0, 0), (262144, 3072, 768, 0, 1, 0), (768, 3072, 262144, 1, 1, 1)]   # literal decode head
+    for (M, N, K, a_mn, b_mn, atomic) in shapes:
+        p = _plan(M, N, K, a_mn=a_mn, b_mn=b_mn, out_bf16=0 if atomic else 1, atomic=atomic)
+        kb = (K + 63) // 64
+        assert p["block_n"] % 32 == 0 and 32 <= p["block_n"] <= 256, (M, N, K, p)
+        if b_mn:
+            assert p["block_n"] % 64 == 0, (M, N, K, p)
+        assert 2 <= p["stages"] <= 8 and 1 <= p["splits"] <= kb, (M, N, K, p)
+        assert p["splits"] == 1 or atomic, (M, N, K, p)
+        two_per_sm = p["tmem_cols"] == 256
+        assert p["grid"] <= SMS * (2 if two_per_sm else 1) and p["grid"] >= 1, (M, N, K, p)
+        assert p["smem"] <= (113 if two_per_sm else 227) * 1024, (M, N, K, p)
+        if p["pair"]:
+            assert p["grid"] % 2 == 0 and (not b_mn or p["block_n"] % 128 == 0), (M, N, K, p)
+
+
+def test_gemm_plan_split_k_takes_whole_rounds():
+    """The wgrad split count follows the rounds model: the stage-3 MixFFN wgrads fit ONE round of the 148 SMs (the old
+    'fill 2 x SMs' rule produced 300 units = 3 rounds), and tiny-output wgrads still spread over the machine."""
+    for (M, N, K) in [(1280, 320, 16384), (320, 1280, 16384), (320, 320, 16384)]:
+        p = _plan(M, N, K, a_mn=1, b_mn=1, out_bf16=0, atomic=1)
+        units = p["tiles"] * p["splits"]
+        assert units <= 148 and units >= 148 * 0.8, (M, N, K, p)
+    p = _plan(64, 64, 262144, a_mn=1, b_mn=1, out_bf16=0, atomic=1)      # one output tile, 4096 k-blocks
+    assert p["tiles"] == 1 and 100 <= p["splits"] <= 296, p
+    p = _plan(128, 64, 64, a_mn=1, b_mn=1, out_bf16=0, atomic=1)         # nothing to split
+    assert p["splits"] == 1, p
+
+
+def test_gemm_plan_modes():
+    """CTA pairs only for the large problems (default option), two CTAs per SM only for K <= 512 non-atomic GEMMs, explicit
+    requests honoured."""
+    big = _plan(262144, 768, 3072)
+    assert big["pair"] == 1 and big["block_n"] == 256 and big["tmem_cols"] == 512, big
+    small_k = _plan(16384, 320, 320)
+    assert small_k["pair"] == 0 and small_k["tmem_cols"] == 256 and small_k["block_n"] <= 128, small_k
+    long_k = _plan(16384, 320, 1280)
+    assert long_k["pair"] == 0 and long_k["tmem_cols"] == 512, long_k
+    forced = _plan(4096, 256, 256, block_n=64, splits=0)
+    assert forced["block_n"] == 64, forced
+    import ctypes
+    from semisupervisedobjectdetection_b200 import _lib as L
+    out = (ctypes.c_int * 8)()
+    assert L.load().sfk_gemm_plan(128, 64, 64, 0, 0, 1, 1, 0, 0, out) != 0     # atomics need an fp32 output
+    assert b"atomic" in L.load().sfk_last_error()
