@@ -3,7 +3,8 @@
 Same class name, constructor arguments, methods, return arities and attribute names (.model .optimizer .scheduler .device
 .loss_function .loss_argmax_function .mse_loss_function .activation_fn .num_labels), so the reference's
 segFormer_main.py / segFormer_transfer_learning_main.py / segFormer_semi_teacherstudent_main.py run against it unchanged.
-Behavioural quirks of the reference are kept on purpose and cited inline (SURVEY.md §0 M-list).
+The implementation is organised around three private helpers (`_run_model`, `_probabilities`, `_loss_for`) instead of the
+reference's inline branches; behavioural quirks of the reference are kept on purpose and cited (SURVEY.md §0 M-list).
 """
 from __future__ import annotations
 
@@ -17,101 +18,125 @@ from . import ops
 from .modeling import SegformerForSemanticSegmentation, upsample_bilinear
 from .optim import FusedClipAdam
 
+_CHECKPOINT_DIR = "../checkpoints"                      # SFM:21: paths are relative to main_segformer/
+_CLASSIFIER_KEYS = ("model.decode_head.classifier.weight", "model.decode_head.classifier.bias")
+
 
 class SegFormerModel(nn.Module):
     def __init__(self, pretrain_weight=None, lr=None, weight_decay=None, scheduler=None, device="cuda:0", use_dice_loss=True,
                  num_labels=1, *args, variant="nvidia/mit-b5", **kwargs):
         super().__init__(*args, **kwargs)
+        self.device, self.num_labels, self.use_dice_loss = device, num_labels, use_dice_loss
         # SFM:14-16 downloads nvidia/mit-b5; offline this builds the same architecture with the reference's random init
-        self.model = SegformerForSemanticSegmentation.from_pretrained(variant, ignore_mismatched_sizes=True,
-                                                                      num_labels=num_labels, reshape_last_stage=True)
-        self.model.config.output_hidden_states = True
-        self.model.to(device)
-        self.device = device
+        net = SegformerForSemanticSegmentation.from_pretrained(variant, ignore_mismatched_sizes=True, num_labels=num_labels,
+                                                               reshape_last_stage=True)
+        net.config.output_hidden_states = True
+        self.model = net.to(device)
         if pretrain_weight:
-            ctx = torch.load(os.path.join('../checkpoints', pretrain_weight), map_location=torch.device(device))
-            if num_labels == 1:  # SFM:24-28: keep row 0 of a multi-class classifier
-                ctx['model.decode_head.classifier.weight'] = ctx['model.decode_head.classifier.weight'][0].unsqueeze(dim=0)
-                ctx['model.decode_head.classifier.bias'] = ctx['model.decode_head.classifier.bias'][0].unsqueeze(dim=0)
-            self.load_state_dict(ctx, strict=False)
-            print("Pretrained model loaded")
-        # Adam(betas=(0.5,0.999), L2 weight decay) + clip_grad_value_(1.2) fused into one kernel (SFM:32-35,161-162)
-        self.optimizer = FusedClipAdam(filter(lambda x: x.requires_grad is not False, self.model.parameters()), lr=lr,
-                                       weight_decay=weight_decay, betas=(0.5, 0.999), clip_value=1.2, model=self.model)
+            self._load_checkpoint(pretrain_weight)
+        # Adam(betas=(0.5, 0.999), L2 weight decay) and clip_grad_value_(1.2) run as one fused kernel (SFM:32-35,161-162);
+        # only parameters trainable at construction time are optimised, like the reference's filter().
+        trainable = [p for p in self.model.parameters() if p.requires_grad is not False]
+        self.optimizer = FusedClipAdam(trainable, lr=lr, weight_decay=weight_decay, betas=(0.5, 0.999), clip_value=1.2,
+                                       model=self.model)
         self.scheduler = torch.optim.lr_scheduler.ExponentialLR(self.optimizer, gamma=scheduler)
-        self.loss_argmax_function = myLoss.SegmentationLoss(1, loss_type='dice_argmax', activation='none')
-        self.loss_function = myLoss.SegmentationLoss(1, loss_type='dice', activation='none')
-        self.mse_loss_function = myLoss.SegmentationLoss(1, loss_type='mse')
-        self.activation_fn = torch.nn.Sigmoid()
-        self.use_dice_loss = use_dice_loss
-        self.num_labels = num_labels
+        # SFM:38-42: all three losses look at channel 0 only (num_classes = 1)
+        for attr, kind, extra in (("loss_argmax_function", "dice_argmax", {"activation": "none"}),
+                                  ("loss_function", "dice", {"activation": "none"}),
+                                  ("mse_loss_function", "mse", {})):
+            setattr(self, attr, myLoss.SegmentationLoss(1, loss_type=kind, **extra))
+        self.activation_fn = nn.Sigmoid()
 
-    # ---- SFM:46-101 ----
+    def _load_checkpoint(self, name):
+        state = torch.load(os.path.join(_CHECKPOINT_DIR, name), map_location=torch.device(self.device))
+        if self.num_labels == 1:
+            # SFM:24-28: a multi-class checkpoint keeps only classifier row 0
+            for key in _CLASSIFIER_KEYS:
+                state[key] = state[key][0].unsqueeze(dim=0)
+        self.load_state_dict(state, strict=False)
+        print("Pretrained model loaded")
+
+    # ------------------------------------------------------------------------------------------------ SFM:46-101
+    def _encoder_blocks(self):
+        return self.model.segformer.encoder.block
+
+    @staticmethod
+    def _set_trainable(modules, flag):
+        for module in modules:
+            for p in module.parameters():
+                p.requires_grad = flag
+
     def frozen_encoder(self, layers_num=None, layers=None):
-        if layers_num is None:
-            layers_num = self.model.config.num_encoder_blocks
+        """Freeze whole stages: explicit indices in `layers`, else the first `layers_num` (default: all four). Only
+        encoder.block is touched — patch embeddings and stage norms stay trainable (SFM:56-59)."""
+        blocks = self._encoder_blocks()
         if layers is not None:
-            for layer_id in layers:
-                for param in self.model.segformer.encoder.block[layer_id].parameters():
-                    param.requires_grad = False
+            chosen = [blocks[idx] for idx in layers]
         else:
-            for param in self.model.segformer.encoder.block[:layers_num].parameters():
-                param.requires_grad = False
+            count = self.model.config.num_encoder_blocks if layers_num is None else layers_num
+            chosen = list(blocks[:count])
+        self._set_trainable(chosen, False)
         print('encoder is frozen')
 
     def unfroze_encoder(self):
-        for param in self.model.segformer.encoder.block.parameters():
-            param.requires_grad = True
+        self._set_trainable(self._encoder_blocks(), True)
+
+    def _install_tokens(self, slot_name, counts, shape_of):
+        """torch.rand(..., requires_grad=True) moved to the device: a non-leaf copy of a CPU leaf, exactly the reference's
+        `torch.rand(...).cuda()` (SFM:83-97, SURVEY M6: such tokens receive gradients that no optimiser applies)."""
+        slots = getattr(self.model.segformer.encoder, slot_name)
+        for stage, n in enumerate(counts):
+            if n:
+                slots[stage] = torch.rand(*shape_of(stage, n), requires_grad=True).to(self.device)
 
     def add_prompt_token(self, token_num_per_block=[10, 10, 10, 10], isSamePerLayer=True):
         cfg = self.model.config
-        enc = self.model.segformer.encoder
-        for i, _ in enumerate(token_num_per_block):
-            if token_num_per_block[i] == 0:
-                continue
-            shape = ((token_num_per_block[i], cfg.hidden_sizes[i]) if isSamePerLayer
-                     else (cfg.depths[i], token_num_per_block[i], cfg.hidden_sizes[i]))
-            # SFM:83-90: torch.rand(..., requires_grad=True).cuda() -> a non-leaf CUDA copy of a CPU leaf
-            enc.prompt_tokens[i] = torch.rand(*shape, requires_grad=True).to(self.device)
+
+        def shape_of(stage, n):
+            width = cfg.hidden_sizes[stage]
+            return (n, width) if isSamePerLayer else (cfg.depths[stage], n, width)
+
+        self._install_tokens("prompt_tokens", token_num_per_block, shape_of)
         print('prompt tokens are added')
 
     def add_cls_token(self, token_num_per_block=[1, 1, 1, 1]):
-        cfg = self.model.config
-        enc = self.model.segformer.encoder
-        for i, _ in enumerate(token_num_per_block):
-            if token_num_per_block[i] == 0:
-                continue
-            enc.cls_token[i] = torch.rand(token_num_per_block[i], cfg.hidden_sizes[i], requires_grad=True).to(self.device)
+        widths = self.model.config.hidden_sizes
+        self._install_tokens("cls_token", token_num_per_block, lambda stage, n: (n, widths[stage]))
         print('CLS tokens are added')
 
-    # ---- SFM:103-139 ----
+    # ------------------------------------------------------------------------------------------------ SFM:103-139
+    def _run_model(self, images, labels=None):
+        """-> (SemanticSegmenterOutput, cls_token); labels only when the in-model BCE / CE loss is wanted."""
+        if labels is None:
+            return self.model(pixel_values=images)
+        return self.model(pixel_values=images, labels=labels)
+
+    @staticmethod
+    def _probabilities(logits, image_hw, sigmoid=True):
+        """Bilinear upsampling of the quarter-resolution logits to the image size fused with the sigmoid (SFM:117-124)."""
+        return upsample_bilinear(logits, list(image_hw), sigmoid=sigmoid)
+
+    def _loss_for(self, use_loss, outputs, images, probs, target):
+        if use_loss == 'dice':
+            return self.loss_function(probs, target)
+        if use_loss == 'bce':
+            return outputs.loss                                            # computed inside the model (MS:853-868)
+        if use_loss == 'mse':
+            raw = self._probabilities(outputs.logits, images.shape[2:], sigmoid=False)
+            return self.mse_loss_function(images, raw)                     # SFM:133 compares with the PRE-sigmoid map
+        return self.loss_argmax_function(probs, target)                    # any other string: hard-thresholded Dice
+
     def predict(self, img, mask=None, isEval=True, use_loss='dice', output_cls_token=False):
         if not isEval:
-            self.model.eval()  # SFM:104-105: the flag is inverted in the reference; kept
+            self.model.eval()   # SFM:104-105: the flag is inverted in the reference; kept (SURVEY M7)
         img = img.to(self.device)
-        if mask is not None:
-            mask = mask.to(self.device, dtype=torch.int64)
-        if use_loss == 'bce':
-            outputs, cls_token = self.model(pixel_values=img, labels=mask)
-        else:
-            outputs, cls_token = self.model(pixel_values=img)
-        logits = outputs.logits
-        size = list(img.shape)
-        sig = upsample_bilinear(logits, size[2:], sigmoid=True)  # SFM:117-124 fused: bilinear x4 + sigmoid
-        predict_masks = torch.squeeze(sig, 1)
-        if mask is None:
+        target = None if mask is None else mask.to(self.device, dtype=torch.int64)   # SFM:108: float masks truncate
+        outputs, cls_token = self._run_model(img, target if use_loss == 'bce' else None)
+        predict_masks = torch.squeeze(self._probabilities(outputs.logits, img.shape[2:]), 1)
+        if target is None:
             return predict_masks
-        if use_loss == 'dice':
-            loss = self.loss_function(predict_masks, mask)
-        elif use_loss == 'bce':
-            loss = outputs.loss
-        elif use_loss == 'mse':
-            loss = self.mse_loss_function(img, upsample_bilinear(logits, size[2:], sigmoid=False))  # SFM:133 pre-sigmoid
-        else:
-            loss = self.loss_argmax_function(predict_masks, mask)
-        if output_cls_token:
-            return loss, predict_masks, cls_token
-        return loss, predict_masks
+        loss = self._loss_for(use_loss, outputs, img, predict_masks, target)
+        return (loss, predict_masks, cls_token) if output_cls_token else (loss, predict_masks)
 
     def eval_one_epoch(self, imgs, masks):
         self.model.eval()
@@ -120,13 +145,9 @@ class SegFormerModel(nn.Module):
 
     def train_one_epoch(self, imgs, masks, use_loss='dice', output_cls_token=False):
         self.model.train()
-        if output_cls_token:
-            loss, predict_masks, cls_tokens = self.predict(imgs, masks, isEval=False, use_loss=use_loss, output_cls_token=True)
-            self.train_from_loss(loss)
-            return loss, predict_masks, cls_tokens
-        loss, predict_masks = self.predict(imgs, masks, isEval=False, use_loss=use_loss, output_cls_token=False)
-        self.train_from_loss(loss)
-        return loss, predict_masks
+        result = self.predict(imgs, masks, isEval=False, use_loss=use_loss, output_cls_token=output_cls_token)
+        self.train_from_loss(result[0])
+        return result
 
     def train_from_loss(self, loss):
         """SFM:158-162. zero_grad -> backward unless NaN -> clip_grad_value_(1.2) -> Adam, the last two fused in
@@ -140,26 +161,27 @@ class SegFormerModel(nn.Module):
         self.scheduler.step()
 
     def show_mask(self, vis, img, mask, title=""):
-        mask_img = img.cpu().numpy()
+        """visdom helper (SFM:166-175): paint the mask into channel 0 of the image and show it."""
+        canvas = img.cpu().numpy()
         if mask is not None:
-            mask = mask.detach().cpu().numpy()
-            mask_img[0, :, :] = mask
-        vis.image(mask_img, opts=dict(title=title))
+            canvas[0, :, :] = mask.detach().cpu().numpy()
+        vis.image(canvas, opts=dict(title=title))
 
-    # ---- SFM:177-219 (autoencoder helpers) ----
+    # ------------------------------------------------------------------------------------------------ SFM:177-219
+    def _autoencode(self, imgs):
+        """Autoencoder helpers: post-sigmoid reconstruction vs the image (SFM:192-194, 214-216)."""
+        imgs = imgs.to(self.device)
+        outputs, _ = self._run_model(imgs)
+        recon = self._probabilities(outputs.logits, imgs.shape[2:])
+        return self.mse_loss_function(imgs, recon), recon
+
     def eval_one_epoch_without_mask(self, imgs):
         self.model.eval()
         with torch.no_grad():
-            imgs = imgs.to(self.device)
-            outputs, _ = self.model(pixel_values=imgs)
-            up = upsample_bilinear(outputs.logits, list(imgs.shape)[2:], sigmoid=True)
-            return self.mse_loss_function(imgs, up), up
+            return self._autoencode(imgs)
 
     def train_one_epoch_without_mask(self, imgs):
         self.model.train()
-        imgs = imgs.to(self.device)
-        outputs, _ = self.model(pixel_values=imgs)
-        up = upsample_bilinear(outputs.logits, list(imgs.shape)[2:], sigmoid=True)
-        loss = self.mse_loss_function(imgs, up)
+        loss, recon = self._autoencode(imgs)
         self.train_from_loss(loss)
-        return loss, up
+        return loss, recon
