@@ -193,3 +193,21 @@ def test_gemm_plan_modes():
     out = (ctypes.c_int * 8)()
     assert L.load().sfk_gemm_plan(128, 64, 64, 0, 0, 1, 1, 0, 0, out) != 0     # atomics need an fp32 output
     assert b"atomic" in L.load().sfk_last_error()
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU oracle port timed on the host cores) prints ONE JSON line carrying the contract keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "mit_b5_512_teacher_student_train_images_per_sec"
+    assert d["unit"] == "images/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
