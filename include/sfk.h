@@ -198,12 +198,15 @@ int sfk_upsample_nchw_fwd(const float* x, float* y, long long planes, int h, int
 int sfk_upsample_nchw_bwd(const float* dy, const float* yact, float* dx, long long planes, int h, int w, int H, int W,
                           int accumulate, sfk_stream_t stream);
 size_t sfk_dice_workspace_bytes(int N);
-/* sums f32 [N,3] = {tp, fp, fn}; loss[0] = 1 - mean_n (2|tp|+s)/(fp+fn+s); target g is i64 or f32 */
+/* sums f32 [N,3] = {tp, fp, fn}; target g is i64 or f32.  sample_weight == NULL: loss[0] = 1 - mean_n score_n with
+ * score_n = (2|tp|+s)/(fp+fn+s) (LOSS:33-41).  sample_weight f32 [N] (north-star EMA step: keep flags of the unlabeled tiles):
+ * loss[0] = (1/N) sum_n w_n (1 - score_n), so a rejected tile (w = 0) contributes neither loss nor gradient. */
 int sfk_dice_fwd(const float* p, long long p_stride, const void* g, int g_is_i64, long long g_stride, int N, long long P,
-                 int hard_threshold, float smooth, float* workspace, float* sums, float* loss, sfk_stream_t stream);
-int sfk_dice_bwd(const float* p, long long p_stride, const void* g, int g_is_i64, long long g_stride, const float* sums,
-                 const float* dloss, float smooth, float* dp, long long dp_stride, int N, long long P, int accumulate,
+                 int hard_threshold, float smooth, const float* sample_weight, float* workspace, float* sums, float* loss,
                  sfk_stream_t stream);
+int sfk_dice_bwd(const float* p, long long p_stride, const void* g, int g_is_i64, long long g_stride, const float* sums,
+                 const float* dloss, float smooth, const float* sample_weight, float* dp, long long dp_stride, int N,
+                 long long P, int accumulate, sfk_stream_t stream);
 size_t sfk_loss_workspace_bytes(void);
 /* out[0] = mean over ALL pixels of BCEWithLogits(z, y) * [y >= 0 && y != ignore] (MS:863-866); out[1] = #valid */
 int sfk_bce_valid_fwd(const float* z, const void* labels_i64, long long ignore_index, long long n, float* workspace,

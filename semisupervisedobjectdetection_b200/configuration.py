@@ -55,11 +55,13 @@ class SegformerConfig:
     @classmethod
     def from_variant(cls, name: str, **overrides) -> "SegformerConfig":
         """`name` like 'nvidia/mit-b5', 'b5', 'nvidia/segformer-b2-finetuned-ade-512-512'."""
-        key = None
-        low = name.lower()
-        for k in MIT_VARIANTS:
-            if f"-{k}" in low or low == k or low.endswith(k):
-                key = k
+        import re
+        low = name.lower().rstrip("/")
+        # the variant tag is a whole path/dash-separated token: 'mit-b5', 'segformer-b2-finetuned-...', 'b0'
+        found = re.findall(r"(?:^|[-/_.])(b[0-5])(?=$|[-/_.])", low)
+        key = found[-1] if found and len(set(found)) == 1 else None
+        if key is not None and key not in MIT_VARIANTS:
+            key = None
         if key is None:
             raise ValueError(f"unknown SegFormer variant in {name!r}; expected one of {sorted(MIT_VARIANTS)}")
         kw = copy.deepcopy(MIT_VARIANTS[key])

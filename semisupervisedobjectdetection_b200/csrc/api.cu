@@ -182,13 +182,14 @@ int sfk_upsample_nchw_bwd(const float* dy, const float* yact, float* dx, long lo
 }
 size_t sfk_dice_workspace_bytes(int N) { return dice_workspace_bytes(N); }
 int sfk_dice_fwd(const float* p, long long p_stride, const void* g, int g_is_i64, long long g_stride, int N, long long P,
-                 int hard_threshold, float smooth, float* workspace, float* sums, float* loss, sfk_stream_t stream) {
-  return dice_fwd(p, p_stride, g, g_is_i64, g_stride, N, P, hard_threshold, smooth, workspace, sums, loss, ST);
+                 int hard_threshold, float smooth, const float* sample_weight, float* workspace, float* sums, float* loss,
+                 sfk_stream_t stream) {
+  return dice_fwd(p, p_stride, g, g_is_i64, g_stride, N, P, hard_threshold, smooth, sample_weight, workspace, sums, loss, ST);
 }
 int sfk_dice_bwd(const float* p, long long p_stride, const void* g, int g_is_i64, long long g_stride, const float* sums,
-                 const float* dloss, float smooth, float* dp, long long dp_stride, int N, long long P, int accumulate,
-                 sfk_stream_t stream) {
-  return dice_bwd(p, p_stride, g, g_is_i64, g_stride, sums, dloss, smooth, dp, dp_stride, N, P, accumulate, ST);
+                 const float* dloss, float smooth, const float* sample_weight, float* dp, long long dp_stride, int N,
+                 long long P, int accumulate, sfk_stream_t stream) {
+  return dice_bwd(p, p_stride, g, g_is_i64, g_stride, sums, dloss, smooth, sample_weight, dp, dp_stride, N, P, accumulate, ST);
 }
 size_t sfk_loss_workspace_bytes(void) { return loss_workspace_bytes(); }
 int sfk_bce_valid_fwd(const float* z, const void* labels_i64, long long ignore_index, long long n, float* workspace,

@@ -4,8 +4,11 @@
 //   1. every block adds its partials into one of NS slot copies   g_slots[slot][v]   (contention / NS),
 //   2. the last block to finish (ticket counter per blockIdx.x) sums the NS copies, adds them into the real destinations
 //      with plain read-modify-write, and zeroes the slots + ticket again (self-cleaning static device memory).
-// All libsfk work of a process is ordered on one stream, and every kernel starts with griddepcontrol.wait, so the static
-// slot area is never shared by two running kernels.
+// Invariant the host code keeps: kernels that use the slot area (LayerNorm / depthwise / cast-and-sum BACKWARD kernels and
+// sfk_colsum) are only ever enqueued on the stream that runs backward; the side streams of the step carry other kernels
+// (teacher forward: no column sums; weight-gradient stream: GEMMs, patch gathers, layout fixes).  Every kernel starts with
+// griddepcontrol.wait, so on that one stream the static slot area is never shared by two running kernels.  Two models
+// running backward concurrently on different streams of ONE process are not supported (one process per GPU).
 #pragma once
 #include "common.cuh"
 

@@ -285,6 +285,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ===================== epilogue warps =====================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     int acc = 0;
+    int trace_tile = 0;
     uint32_t acc_phase[2] = {0, 0};
     for (int unit = unit0; unit < total_units; unit += unit_stride) {
       const int tile = unit / p.splits;
@@ -303,6 +304,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       tc_fence_after();
       if (p.bias != nullptr) asm volatile("bar.sync 1, 128;" ::: "memory");
       if (threadIdx.x == 64 && unit == unit0) GEMM_TRACE(5);
+      if (threadIdx.x == 64 && trace_tile < 28) GEMM_TRACE(8 + 2 * trace_tile);
       const long long row = (long long)m_blk * BLOCK_M + q * 32 + lane;
       const bool row_ok = row < p.M;
       float rscale = p.alpha;
@@ -390,6 +392,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         else mbar_arrive(bar_tempty + 8 * acc);
       }
       if (threadIdx.x == 64 && unit == unit0) GEMM_TRACE(6);
+      if (threadIdx.x == 64 && trace_tile < 28) GEMM_TRACE(9 + 2 * trace_tile);
+      ++trace_tile;
       if (p.bias != nullptr) asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with this tile's bias slice
       acc_phase[acc] ^= 1;
       acc ^= 1;

@@ -149,9 +149,9 @@ __global__ void __launch_bounds__(256) dice_partial_kernel(const float* __restri
   }
 }
 
-// sums[n] = {tp, fp, fn};  loss = 1 - mean_n score   (one block)
+// sums[n] = {tp, fp, fn};  loss = mean_n w_n * (1 - score_n), w_n = 1 without sample weights   (one block)
 __global__ void dice_finish_kernel(const float* __restrict__ partial, int N, int chunks, float smooth, float* __restrict__ sums,
-                                   float* __restrict__ loss) {
+                                   float* __restrict__ loss, const float* __restrict__ sample_weight) {
   pdl_sync();
   __shared__ float sc[256];
   float local = 0.f;
@@ -162,21 +162,23 @@ __global__ void dice_finish_kernel(const float* __restrict__ partial, int N, int
       tp += o[0]; fp += o[1]; fn += o[2];
     }
     sums[n * 3 + 0] = tp; sums[n * 3 + 1] = fp; sums[n * 3 + 2] = fn;
-    local += (2.f * fabsf(tp) + smooth) / (fp + fn + smooth);
+    const float score = (2.f * fabsf(tp) + smooth) / (fp + fn + smooth);
+    local += sample_weight != nullptr ? sample_weight[n] * (1.f - score) : score;
   }
   sc[threadIdx.x] = local;
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < 256; ++i) t += sc[i];
-    loss[0] = 1.f - t / (float)N;
+    loss[0] = sample_weight != nullptr ? t / (float)N : 1.f - t / (float)N;
   }
 }
 
 size_t dice_workspace_bytes(int N) { return (size_t)N * RED_CHUNKS * 4 * sizeof(float); }
 
 int dice_fwd(const float* p, long long p_stride, const void* g, int g_is_i64, long long g_stride, int N, long long P,
-             int hard_threshold, float smooth, float* workspace, float* sums, float* loss, cudaStream_t stream) {
+             int hard_threshold, float smooth, const float* sample_weight, float* workspace, float* sums, float* loss,
+             cudaStream_t stream) {
   SFK_REQUIRE(N > 0 && N <= 65535 && P > 0, "dice: bad shape N=%d P=%lld", N, P);
   dim3 grid(RED_CHUNKS, N);
   if (g_is_i64)
@@ -185,7 +187,7 @@ int dice_fwd(const float* p, long long p_stride, const void* g, int g_is_i64, lo
     launch_k(dice_partial_kernel<float>, dim3(grid), dim3(256), 0, stream, p, p_stride, (const float*)g, g_stride, workspace, P, hard_threshold);
   int rc = check_launch("dice_partial_kernel");
   if (rc) return rc;
-  launch_k(dice_finish_kernel, dim3(1), dim3(256), 0, stream, workspace, N, RED_CHUNKS, smooth, sums, loss);
+  launch_k(dice_finish_kernel, dim3(1), dim3(256), 0, stream, workspace, N, RED_CHUNKS, smooth, sums, loss, sample_weight);
   return check_launch("dice_finish_kernel");
 }
 
@@ -193,7 +195,8 @@ int dice_fwd(const float* p, long long p_stride, const void* g, int g_is_i64, lo
 template <typename TG>
 __global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__ p, long long p_stride, const TG* __restrict__ g,
                                                        long long g_stride, const float* __restrict__ sums,
-                                                       const float* __restrict__ dloss, float smooth, float* __restrict__ dp,
+                                                       const float* __restrict__ dloss, float smooth,
+                                                       const float* __restrict__ sample_weight, float* __restrict__ dp,
                                                        long long dp_stride, int N, long long P, int accumulate) {
   pdl_sync();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -206,23 +209,24 @@ __global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__
   const float pv = p[n * p_stride + i];
   const float sp = pv > 0.f ? 1.f : (pv < 0.f ? -1.f : 0.f);
   const float gv = (float)g[n * g_stride + i];
-  const float d = -(dloss[0] / (float)N) * (2.f * stp * gv * F - num * sp) / (F * F);
+  const float wn = sample_weight != nullptr ? sample_weight[n] : 1.f;
+  const float d = -(wn * dloss[0] / (float)N) * (2.f * stp * gv * F - num * sp) / (F * F);
   float* o = dp + n * dp_stride + i;
   *o = accumulate ? *o + d : d;
 }
 
 int dice_bwd(const float* p, long long p_stride, const void* g, int g_is_i64, long long g_stride, const float* sums,
-             const float* dloss, float smooth, float* dp, long long dp_stride, int N, long long P, int accumulate,
-             cudaStream_t stream) {
+             const float* dloss, float smooth, const float* sample_weight, float* dp, long long dp_stride, int N, long long P,
+             int accumulate, cudaStream_t stream) {
   const long long total = (long long)N * P;
   if (total == 0) return 0;
   const unsigned grid = (unsigned)((total + 255) / 256);
   if (g_is_i64)
-    launch_k(dice_bwd_kernel<long long>, dim3(grid), dim3(256), 0, stream, p, p_stride, (const long long*)g, g_stride, sums, dloss, smooth, dp,
-                                                         dp_stride, N, P, accumulate);
+    launch_k(dice_bwd_kernel<long long>, dim3(grid), dim3(256), 0, stream, p, p_stride, (const long long*)g, g_stride, sums, dloss, smooth, sample_weight,
+                                                         dp, dp_stride, N, P, accumulate);
   else
-    launch_k(dice_bwd_kernel<float>, dim3(grid), dim3(256), 0, stream, p, p_stride, (const float*)g, g_stride, sums, dloss, smooth, dp, dp_stride,
-                                                     N, P, accumulate);
+    launch_k(dice_bwd_kernel<float>, dim3(grid), dim3(256), 0, stream, p, p_stride, (const float*)g, g_stride, sums, dloss, smooth, sample_weight, dp,
+                                                     dp_stride, N, P, accumulate);
   return check_launch("dice_bwd_kernel");
 }
 

@@ -145,10 +145,11 @@ int upsample_nchw_bwd(const float* dy, const float* yact, float* dx, long long p
                       int accumulate, cudaStream_t stream);
 size_t dice_workspace_bytes(int N);
 int dice_fwd(const float* p, long long p_stride, const void* g, int g_is_i64, long long g_stride, int N, long long P,
-             int hard_threshold, float smooth, float* workspace, float* sums, float* loss, cudaStream_t stream);
-int dice_bwd(const float* p, long long p_stride, const void* g, int g_is_i64, long long g_stride, const float* sums,
-             const float* dloss, float smooth, float* dp, long long dp_stride, int N, long long P, int accumulate,
+             int hard_threshold, float smooth, const float* sample_weight, float* workspace, float* sums, float* loss,
              cudaStream_t stream);
+int dice_bwd(const float* p, long long p_stride, const void* g, int g_is_i64, long long g_stride, const float* sums,
+             const float* dloss, float smooth, const float* sample_weight, float* dp, long long dp_stride, int N, long long P,
+             int accumulate, cudaStream_t stream);
 size_t loss_workspace_bytes();
 int bce_valid_fwd(const float* z, const long long* labels, long long ignore_index, long long n, float* workspace, float* out,
                   cudaStream_t stream);

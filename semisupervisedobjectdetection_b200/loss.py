@@ -22,7 +22,7 @@ class _DiceLossFn(torch.autograd.Function):
     """loss = 1 - mean_n (2|sum g p| + s) / (sum |p| + sum g + s) over channel 0 of pred/gt [N, C, ...]."""
 
     @staticmethod
-    def forward(ctx, pred, gt, smooth, hard_threshold):
+    def forward(ctx, pred, gt, smooth, hard_threshold, sample_weight=None):
         pred = ops._chk(pred, torch.float32, "dice prediction")
         if not gt.is_cuda:
             raise RuntimeError("dice target must be a CUDA tensor")
@@ -37,24 +37,30 @@ class _DiceLossFn(torch.autograd.Function):
         ws = ops.scratch(lib.sfk_dice_workspace_bytes(N), pred.device, "loss")
         sums = torch.empty(N, 3, device=pred.device, dtype=torch.float32)
         loss = torch.empty(1, device=pred.device, dtype=torch.float32)
+        if sample_weight is not None:
+            sample_weight = ops._chk(sample_weight.detach(), torch.float32, "dice sample weights")
+            if sample_weight.numel() != N:
+                raise ValueError(f"dice: {sample_weight.numel()} sample weights for {N} samples")
         ops.call("sfk_dice_fwd", pred.data_ptr(), p_stride, gt.data_ptr(), int(gt.dtype == torch.int64), g_stride, N, P,
-                 int(hard_threshold), float(smooth), ws.data_ptr(), sums.data_ptr(), loss.data_ptr(), ops.stream())
+                 int(hard_threshold), float(smooth), ops._p(sample_weight), ws.data_ptr(), sums.data_ptr(), loss.data_ptr(),
+                 ops.stream())
         ctx.meta = (N, P, p_stride, g_stride, float(smooth), hard_threshold)
+        ctx.weighted = sample_weight is not None
         if ctx.needs_input_grad[0] and not hard_threshold:
-            ctx.save_for_backward(pred, gt, sums)
+            ctx.save_for_backward(pred, gt, sums, *([sample_weight] if sample_weight is not None else []))
         return loss[0]
 
     @staticmethod
     def backward(ctx, dloss):
         N, P, p_stride, g_stride, smooth, hard = ctx.meta
         if hard:
-            return None, None, None, None
-        pred, gt, sums = ctx.saved_tensors
+            return None, None, None, None, None
+        pred, gt, sums, *w = ctx.saved_tensors
         dp = torch.zeros_like(pred)  # channels other than 0 get no gradient (LOSS:83 slices channel 0)
         dl = dloss.reshape(1).float().contiguous()
         ops.call("sfk_dice_bwd", pred.data_ptr(), p_stride, gt.data_ptr(), int(gt.dtype == torch.int64), g_stride, sums.data_ptr(),
-                 dl.data_ptr(), smooth, dp.data_ptr(), p_stride, N, P, 0, ops.stream())
-        return dp, None, None, None
+                 dl.data_ptr(), smooth, ops._p(w[0] if w else None), dp.data_ptr(), p_stride, N, P, 0, ops.stream())
+        return dp, None, None, None, None
 
 
 class _MseFn(torch.autograd.Function):
@@ -91,6 +97,12 @@ def mse(predicted, gt):
     """LOSS:44-54: mean_n( sum((gt - predicted)^2) / (N*C) )."""
     n, c = gt.shape[0], gt.shape[1]
     return _MseFn.apply(gt.float().contiguous(), predicted.float().contiguous(), float(n * c * n))
+
+
+def weighted_dice_loss(pred, gt, sample_weight, smooth_value: float = 1.0):
+    """(1/N) sum_n w_n * (1 - dice_n): the per-sample form of LOSS:33-41 used by the north-star EMA step, where w_n is the
+    keep flag of an unlabeled tile (TS:43 drops such tiles from the batch; here they stay, with zero loss and gradient)."""
+    return _DiceLossFn.apply(_as4d(pred).float(), _as4d(gt), smooth_value, False, sample_weight)
 
 
 class SegmentationLoss(nn.Module):

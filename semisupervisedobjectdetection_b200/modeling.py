@@ -628,7 +628,8 @@ class SegformerEncoder(nn.Module):
     def forward(self, pixel_values, output_attentions=False, output_hidden_states=False, return_dict=True):
         if output_attentions:
             raise NotImplementedError("output_attentions=True is not supported by the fused attention kernel")
-        stages, cls_out = self._forward_tokens(pixel_values)
+        with ops.device_of(pixel_values):
+            stages, cls_out = self._forward_tokens(pixel_values)
         maps = tuple(_tokens_to_nchw(t, H, W) for (t, H, W) in stages)
         last = maps[-1]
         if not self.config.reshape_last_stage:
@@ -668,27 +669,90 @@ class SegformerPreTrainedModel(nn.Module):
 
     @classmethod
     def from_pretrained(cls, pretrained_model_name_or_path, *model_args, ignore_mismatched_sizes=False, **kwargs):
-        """Offline stand-in for PreTrainedModel.from_pretrained (called at SFM:14-16): builds the named MiT variant from
-        its architecture table with the reference's random init. If the argument is a path to a torch state dict it is
-        loaded with strict=False (mismatched classifier shapes are skipped when ignore_mismatched_sizes=True)."""
-        import os
+        """Offline stand-in for PreTrainedModel.from_pretrained (called at SFM:14-16).  The architecture comes from the MiT
+        variant named in the argument.  Weights are taken, in this order, from
+          * the argument itself when it is a state-dict file or a Hugging Face snapshot directory
+            (pytorch_model.bin / model.safetensors),
+          * $SFK_PRETRAINED_DIR/<name> or $SFK_PRETRAINED_DIR/<basename of name> (same formats),
+        loaded with strict=False (mismatched shapes skipped when ignore_mismatched_sizes=True, like the reference's call).
+        Without either the network keeps the reference's random init (MS:500-514) and a warning says so: there is no
+        network access to fetch nvidia/mit-b5."""
+        import warnings
         cfg_kwargs = {k: v for k, v in kwargs.items() if k in ("num_labels", "reshape_last_stage", "drop_path_rate",
                                                                "classifier_dropout_prob", "decoder_hidden_size")}
         name = str(pretrained_model_name_or_path)
-        state = None
-        if os.path.isfile(name):
-            state = torch.load(name, map_location="cpu")
-            variant = kwargs.get("variant", "b5")
-        else:
-            variant = name
+        source = _find_checkpoint(name)
+        variant = kwargs.get("variant")
+        if variant is None:
+            try:
+                SegformerConfig.from_variant(name)
+                variant = name
+            except ValueError:
+                if source is None:
+                    raise
+                variant = "b5"   # the reference only ever loads MiT-b5 (SFM:14)
         config = SegformerConfig.from_variant(variant, **cfg_kwargs)
         model = cls(config, *model_args)
-        if state is not None:
-            own = model.state_dict()
-            if ignore_mismatched_sizes:
-                state = {k: v for k, v in state.items() if k not in own or own[k].shape == v.shape}
-            model.load_state_dict(state, strict=False)
+        if source is None:
+            warnings.warn(f"from_pretrained({name!r}): no local checkpoint found (set SFK_PRETRAINED_DIR or pass a state-dict / "
+                          "snapshot path); the model keeps its RANDOM initialisation, unlike the reference which starts from "
+                          "the ImageNet-pretrained encoder", RuntimeWarning, stacklevel=2)
+            return model
+        state = _normalise_checkpoint_keys(_read_checkpoint(source), model)
+        own = model.state_dict()
+        if ignore_mismatched_sizes:
+            state = {k: v for k, v in state.items() if k not in own or own[k].shape == v.shape}
+        missing, unexpected = model.load_state_dict(state, strict=False)
+        loaded = len([k for k in state if k in own])
+        if loaded == 0:
+            raise RuntimeError(f"from_pretrained: {source} shares no parameter name with {cls.__name__}")
+        print(f"from_pretrained: loaded {loaded} tensors from {source} ({len(missing)} missing, {len(unexpected)} unexpected)")
         return model
+
+
+def _find_checkpoint(name: str):
+    """Path of a local checkpoint for `name`, or None."""
+    cands = [name]
+    root = os.environ.get("SFK_PRETRAINED_DIR")
+    if root:
+        cands += [os.path.join(root, name), os.path.join(root, os.path.basename(name.rstrip("/")))]
+    for c in cands:
+        if os.path.isfile(c):
+            return c
+        if os.path.isdir(c):
+            for fn in ("pytorch_model.bin", "model.safetensors", "model.pth", "model.pt"):
+                if os.path.isfile(os.path.join(c, fn)):
+                    return os.path.join(c, fn)
+    return None
+
+
+def _read_checkpoint(path: str) -> dict:
+    if path.endswith(".safetensors"):
+        try:
+            from safetensors.torch import load_file
+        except ImportError as e:   # no silent fallback: say what is missing
+            raise RuntimeError(f"{path}: reading .safetensors needs the `safetensors` package") from e
+        return load_file(path)
+    state = torch.load(path, map_location="cpu")
+    if isinstance(state, dict) and "state_dict" in state and isinstance(state["state_dict"], dict):
+        state = state["state_dict"]
+    return state
+
+
+def _normalise_checkpoint_keys(state: dict, model: nn.Module) -> dict:
+    """Map Hugging Face / reference-wrapper key spellings onto this module's: HF SegFormer checkpoints use
+    'segformer.encoder.*' / 'decode_head.*' (identical to ours); encoder-only dumps use 'encoder.*'; the reference wrapper
+    saves 'model.segformer.*' (SFM:22-29)."""
+    own = set(model.state_dict().keys())
+    out = {}
+    for k, v in state.items():
+        for cand in (k, k[len("model."):] if k.startswith("model.") else None, "segformer." + k if k.startswith("encoder.") else None):
+            if cand is not None and cand in own:
+                out[cand] = v
+                break
+        else:
+            out[k] = v
+    return out
 
 
 class SegformerModel(SegformerPreTrainedModel):
@@ -956,7 +1020,8 @@ class SegformerDecodeHead(SegformerPreTrainedModel):
                 h = h.reshape(batch_size, side, side, -1).permute(0, 3, 1, 2)
             B, C, H, W = h.shape
             stages.append((h.permute(0, 2, 3, 1).reshape(B, H * W, C).to(torch.bfloat16).contiguous(), H, W))
-        return self._forward_tokens(stages, cls_token)
+        with ops.device_of(stages[0][0]):
+            return self._forward_tokens(stages, cls_token)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -1046,14 +1111,7 @@ class SegformerForSemanticSegmentation(SegformerPreTrainedModel):
         self.decode_head = SegformerDecodeHead(config)
         self.post_init()
 
-    def forward(self, pixel_values, labels=None, output_attentions=None, output_hidden_states=None, return_dict=None):
-        """Returns (SemanticSegmenterOutput, cls_token) exactly like the reference's modified forward (MS:800-882)."""
-        return_dict = return_dict if return_dict is not None else self.config.use_return_dict
-        output_hidden_states = output_hidden_states if output_hidden_states is not None else self.config.output_hidden_states
-        if output_attentions:
-            raise NotImplementedError("output_attentions=True is not supported by the fused attention kernel")
-        if not return_dict:
-            raise NotImplementedError("return_dict=False is not used by any reference script and is not supported")
+    def _forward_impl(self, pixel_values, labels):
         enc = self.segformer.encoder
         stages, cls_list = enc._forward_tokens(pixel_values)
         cls_token = None
@@ -1069,5 +1127,17 @@ class SegformerForSemanticSegmentation(SegformerPreTrainedModel):
                 loss = _BceValidFn.apply(up.squeeze(1), labels, int(self.config.semantic_loss_ignore_index))
             else:
                 raise ValueError(f"Number of labels should be >=0: {self.config.num_labels}")
+        return logits, loss, stages, cls_token
+
+    def forward(self, pixel_values, labels=None, output_attentions=None, output_hidden_states=None, return_dict=None):
+        """Returns (SemanticSegmenterOutput, cls_token) exactly like the reference's modified forward (MS:800-882)."""
+        return_dict = return_dict if return_dict is not None else self.config.use_return_dict
+        output_hidden_states = output_hidden_states if output_hidden_states is not None else self.config.output_hidden_states
+        if output_attentions:
+            raise NotImplementedError("output_attentions=True is not supported by the fused attention kernel")
+        if not return_dict:
+            raise NotImplementedError("return_dict=False is not used by any reference script and is not supported")
+        with ops.device_of(pixel_values):
+            logits, loss, stages, cls_token = self._forward_impl(pixel_values, labels)
         hidden = tuple(_tokens_to_nchw(t, H, W) for (t, H, W) in stages) if output_hidden_states else None
         return SemanticSegmenterOutput(loss=loss, logits=logits, hidden_states=hidden, attentions=None), cls_token

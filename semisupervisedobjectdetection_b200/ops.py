@@ -109,7 +109,22 @@ def _chk(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
         raise L.SfkError(f"{name}: expected a CUDA tensor (libsfk has no CPU path)")
     if t.dtype != dtype:
         raise L.SfkError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if t.device.index != torch.cuda.current_device():
+        # libsfk enqueues on the CURRENT device's stream: a tensor of another GPU would be an illegal (or silently peer-mapped)
+        # access.  The module / wrapper entry points switch devices themselves (device_of); raw op callers must do it.
+        raise L.SfkError(f"{name}: tensor lives on cuda:{t.device.index} but the current device is cuda:"
+                         f"{torch.cuda.current_device()}; wrap the call in `with torch.cuda.device(tensor.device)`")
     return t if t.is_contiguous() else t.contiguous()
+
+
+def device_of(t):
+    """Context manager making the device of tensor / module-device string `t` current (no-op for CPU tensors, so that the
+    usual 'expected a CUDA tensor' error still surfaces from _chk)."""
+    dev = t.device if isinstance(t, torch.Tensor) else torch.device(t)
+    if dev.type != "cuda":
+        import contextlib
+        return contextlib.nullcontext()
+    return torch.cuda.device(dev)
 
 
 def grad_buffer(p: torch.nn.Parameter) -> Optional[torch.Tensor]:

@@ -110,6 +110,13 @@ def ema_teacher_student_step(teacher, student, img_labeled, ground_truth, img_un
     """North-star variant: EMA teacher forward on labeled + unlabeled tiles -> confidence-thresholded pseudo labels ->
     student forward/backward on both -> fused clip+Adam -> rank-local EMA teacher update.
     `grad_sync`: optional callable run between backward and the optimiser step (data-parallel all-reduce)."""
+    with ops.device_of(student.device):
+        return _ema_teacher_student_step(teacher, student, img_labeled, ground_truth, img_unlabeled, supervise_weight,
+                                         ema_decay, grad_sync, overlap_teacher)
+
+
+def _ema_teacher_student_step(teacher, student, img_labeled, ground_truth, img_unlabeled, supervise_weight, ema_decay,
+                              grad_sync, overlap_teacher):
     dev = student.device
     img_l = img_labeled.to(device=dev, dtype=torch.float32)
     img_u = img_unlabeled.to(device=dev, dtype=torch.float32)
@@ -133,13 +140,13 @@ def ema_teacher_student_step(teacher, student, img_labeled, ground_truth, img_un
     t_l = denoise_teacher_probs(t_probs[:nl], gt)
     pseudo_l, _ = pseudo_label_stats(t_l, allow_throw_sample=False)
     pseudo_u, stats_u = pseudo_label_stats(t_probs[nl:].contiguous(), allow_throw_sample=True)
-    keep_u = (stats_u[:, 4] > 0.5)
-    # static shapes: rejected unlabeled tiles stay in the batch with an all-zero target and zero weight
+    keep_u = (stats_u[:, 4] > 0.5).float()
+    # static shapes: rejected unlabeled tiles (TS:43 filters them out) stay in the batch with weight 0, i.e. they add neither
+    # loss nor gradient; every kept tile weighs 1/N_u, like a labeled tile's 1/N_l
     sup = loss_func(s_probs[:nl], gt.to(torch.int64))
     self_l = loss_func(s_probs[:nl], pseudo_l)
-    w_u = keep_u.float().mean()
-    self_u = loss_func(s_probs[nl:], pseudo_u * keep_u.view(-1, 1, 1).to(torch.int64))
-    loss = supervise_weight * sup + (1 - supervise_weight) * (self_l + w_u * self_u) * 0.5
+    self_u = myLoss.weighted_dice_loss(s_probs[nl:], pseudo_u, keep_u)
+    loss = supervise_weight * sup + (1 - supervise_weight) * (self_l + self_u) * 0.5
     student.optimizer.zero_grad()
     loss.backward()
     if grad_sync is not None:

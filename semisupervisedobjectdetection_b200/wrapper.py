@@ -127,6 +127,11 @@ class SegFormerModel(nn.Module):
         return self.loss_argmax_function(probs, target)                    # any other string: hard-thresholded Dice
 
     def predict(self, img, mask=None, isEval=True, use_loss='dice', output_cls_token=False):
+        # the reference accepts any device string (SFM:11); libsfk launches on the current device, so make ours current
+        with ops.device_of(self.device):
+            return self._predict(img, mask, isEval, use_loss, output_cls_token)
+
+    def _predict(self, img, mask, isEval, use_loss, output_cls_token):
         if not isEval:
             self.model.eval()   # SFM:104-105: the flag is inverted in the reference; kept
         img = img.to(self.device)
@@ -152,10 +157,11 @@ class SegFormerModel(nn.Module):
     def train_from_loss(self, loss):
         """SFM:158-162. zero_grad -> backward unless NaN -> clip_grad_value_(1.2) -> Adam, the last two fused in
         FusedClipAdam.step(); a step with no gradient anywhere touches nothing (the reference under torch 2.0.1)."""
-        self.optimizer.zero_grad()
-        if not torch.isnan(loss):
-            loss.backward()
-        self.optimizer.step()
+        with ops.device_of(self.device):
+            self.optimizer.zero_grad()
+            if not torch.isnan(loss):
+                loss.backward()
+            self.optimizer.step()
 
     def scheduler_step(self):
         self.scheduler.step()
@@ -170,10 +176,11 @@ class SegFormerModel(nn.Module):
     # ------------------------------------------------------------------------------------------------ SFM:177-219
     def _autoencode(self, imgs):
         """Autoencoder helpers: post-sigmoid reconstruction vs the image (SFM:192-194, 214-216)."""
-        imgs = imgs.to(self.device)
-        outputs, _ = self._run_model(imgs)
-        recon = self._probabilities(outputs.logits, imgs.shape[2:])
-        return self.mse_loss_function(imgs, recon), recon
+        with ops.device_of(self.device):
+            imgs = imgs.to(self.device)
+            outputs, _ = self._run_model(imgs)
+            recon = self._probabilities(outputs.logits, imgs.shape[2:])
+            return self.mse_loss_function(imgs, recon), recon
 
     def eval_one_epoch_without_mask(self, imgs):
         self.model.eval()

@@ -211,3 +211,43 @@ def test_bench_reference_arm_contract():
     assert d["unit"] == "images/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_variant_names_are_parsed_as_whole_tokens():
+    for name, depths in (("nvidia/mit-b5", [3, 6, 40, 3]), ("b0", [2, 2, 2, 2]), ("nvidia/segformer-b2-finetuned-ade-512-512", [3, 4, 6, 3]),
+                         ("/ckpt/mit-b1/", [2, 2, 2, 2])):
+        assert SegformerConfig.from_variant(name).depths == depths
+    for bad in ("foo", "rgb5", "mit-b7", "b0-b1"):
+        with pytest.raises(ValueError):
+            SegformerConfig.from_variant(bad)
+
+
+def test_from_pretrained_warns_on_random_init_and_loads_local_checkpoints(tmp_path, monkeypatch):
+    """SFM:14-16 starts from the ImageNet-pretrained encoder; offline that is only possible from a local file, and a
+    silent random init would change what the reference mains train."""
+    cls = modeling.SegformerForSemanticSegmentation
+    monkeypatch.delenv("SFK_PRETRAINED_DIR", raising=False)
+    with pytest.warns(RuntimeWarning, match="RANDOM"):
+        net = cls.from_pretrained("nvidia/mit-b0", num_labels=1)
+    sd = {k: torch.full_like(v, 0.5) if v.is_floating_point() else v for k, v in net.state_dict().items()}
+    # (a) the reference wrapper's 'model.'-prefixed state dict, classifier of another width skipped
+    ref_style = {"model." + k: v for k, v in sd.items()}
+    ref_style["model.decode_head.classifier.weight"] = torch.zeros(7, 256, 1, 1)
+    path = tmp_path / "wrapper_style.pth"
+    torch.save(ref_style, path)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        got = cls.from_pretrained(str(path), ignore_mismatched_sizes=True, num_labels=1, variant="b0")
+    assert float(got.segformer.encoder.block[1][0].mlp.dense1.weight.mean()) == 0.5
+    assert float(got.decode_head.classifier.weight.abs().max()) < 0.5   # mismatched shape skipped, init kept
+    # (b) encoder-only dump in a Hugging Face style snapshot directory found through SFK_PRETRAINED_DIR
+    snap = tmp_path / "hub" / "mit-b0"
+    snap.mkdir(parents=True)
+    torch.save({k[len("segformer."):]: v for k, v in sd.items() if k.startswith("segformer.")}, snap / "pytorch_model.bin")
+    monkeypatch.setenv("SFK_PRETRAINED_DIR", str(tmp_path / "hub"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        got = cls.from_pretrained("nvidia/mit-b0", num_labels=1)
+    assert float(got.segformer.encoder.patch_embeddings[0].proj.weight.mean()) == 0.5
+    assert float(got.decode_head.linear_fuse.weight.abs().max()) < 0.5       # head not in the dump: random init kept

@@ -87,27 +87,32 @@ def main():
         allok &= report("epilogue bias+relu bf16", out, torch.relu(a.float() @ b.float().t() + bias))
     elif group == "trace":
         lib = L.load()
-        buf = torch.zeros(8, device=dev, dtype=torch.int64)
-        for name, M, N, K in [("tiny 128x64x64", 128, 64, 64), ("q_s3 16384x320x320", 16384, 320, 320),
-                              ("ffn1_s3 16384x1280x320", 16384, 1280, 320), ("ffn2_s3 16384x320x1280", 16384, 320, 1280),
-                              ("q_s1 262144x64x64", 262144, 64, 64)]:
+        buf = torch.zeros(64, device=dev, dtype=torch.int64)
+        cases = [("q_s3 16384x320x320", 16384, 320, 320, 0), ("ffn1_s3 16384x1280x320", 16384, 1280, 320, 0),
+                 ("ffn1_s3 bn256", 16384, 1280, 320, 256), ("ffn2_s3 16384x320x1280", 16384, 320, 1280, 0),
+                 ("ffn1_s1 262144x256x64", 262144, 256, 64, 0), ("q_s1 262144x64x64", 262144, 64, 64, 0)]
+        for name, M, N, K, bn in cases:
             a = torch.randn(M, K, device=dev).bfloat16()
             b = torch.randn(N, K, device=dev).bfloat16()
+            bias = torch.randn(N, device=dev)
             out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
             for _ in range(3):
-                gemm(a, b, M, N, K, out_bf16=True, out=out)
+                gemm(a, b, M, N, K, out_bf16=True, out=out, bias=bias, block_n=bn)
             torch.cuda.synchronize()
+            buf.zero_()
             lib.sfk_debug_gemm_trace(buf.data_ptr())
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            gemm(a, b, M, N, K, out_bf16=True, out=out)
+            gemm(a, b, M, N, K, out_bf16=True, out=out, bias=bias, block_n=bn)
             e1.record()
             torch.cuda.synchronize()
             lib.sfk_debug_gemm_trace(None)
             t = buf.cpu().tolist()
-            rel = [(x - t[0]) / 1000.0 for x in t]
+            rel = [(x - t[0]) / 1000.0 if x else float("nan") for x in t]
             print(f"TRACE {name}: event {e0.elapsed_time(e1)*1000:.1f} us | us since CTA0 start: setup {rel[1]:.2f} tma0 {rel[2]:.2f} "
                   f"landed {rel[3]:.2f} last-mma {rel[4]:.2f} acc-ready {rel[5]:.2f} tile-stored {rel[6]:.2f} cta-done {rel[7]:.2f}", flush=True)
+            tiles = [(rel[8 + 2 * i], rel[9 + 2 * i]) for i in range(28) if t[8 + 2 * i]]
+            print("      per tile (acc-ready, stored): " + " ".join(f"({a0:.2f},{a1:.2f})" for a0, a1 in tiles), flush=True)
     elif group == "perf":
         shapes = [("q_s3 16384x320x320", 16384, 320, 320), ("kv_s3 4096x640x320", 4096, 640, 320),
                   ("fuse 262144x768x3072", 262144, 768, 3072), ("ffn1_s3 16384x1280x320", 16384, 1280, 320),
