@@ -45,20 +45,22 @@ int sfk_profile_gemm_end(double* total_ms, double* total_flops, long long* launc
 /* After sfk_profile_gemm_end: one CSV line per profiled GEMM launch (M,N,K,flags,microseconds). */
 int sfk_profile_gemm_dump(const char* path);
 
-/* Tuning switches: "gemm_cluster2" = CTA-pair (tcgen05 cta_group::2, 256-row MMA, B split across the pair) GEMM tiles:
+/* Tuning switches: "gemm_epi_tma" (default 1) = staged TMA-store / reduce-add epilogue; "gemm_bstat" (default 1) = weight tile resident
+ * in shared memory for K <= 512 GEMMs; "gemm_dbg" = experiment bits (timing only); "gemm_cluster2" = CTA-pair (tcgen05 cta_group::2, 256-row MMA, B split across the pair) GEMM tiles:
  * 0 never, 1 (default) for large problems (M*N*K >= 1e11, K >= 1024), 2 whenever the shape allows; "gemm_occ2" (default 1) = two co-resident CTAs per SM for K <= 512 GEMMs; "dw_bwd_vec" (2 | 4, default 4)
  * = channels per thread of the depthwise-conv backward kernel; "attn_bwd_persist" (default 1) = persistent evenly split attention backward; "sr_tma_patch" (default 1) = the SR conv's GEMMs read their
  * k == stride patches through a rank-5 TMA view of the activation (implicit im2col) instead of a gathered copy. */
 int sfk_set_option(const char* name, int value);
 
-/* Debug aid: device buffer (>= 8 x uint64) receiving CTA 0's globaltimer (ns) at the phase boundaries of each following
+/* Debug aid: device buffer (>= 256 x uint64; slots 8.. hold per-tile timelines, see tools/check_gemm.py trace) receiving CTA 0's globaltimer (ns) at the phase boundaries of each following
  * GEMM launch: 0 start, 1 setup done, 2 first TMA issued, 3 first operands landed, 4 last MMA issued, 5 accumulator ready,
  * 6 first tile stored, 7 CTA done.  NULL switches it off. */
 int sfk_debug_gemm_trace(void* device_u64x8);
 
 /* Launch plan sfk_gemm_bf16 would use for this shape, without touching the device (host logic, testable on CPU):
- * out8 = {block_n, splits, pipeline stages, grid (CTAs), cta_pair mode, TMEM columns per CTA (256 = two CTAs per SM),
- *         dynamic shared memory bytes, output tiles}.  splits / block_n: 0 = automatic, as in sfk_gemm_bf16. */
+ * out8 = {block_n, splits, pipeline stages, grid (CTAs), mode bits (1 = CTA pair, 2 = B-stationary main loop,
+ *         4 = TMA-store epilogue), TMEM columns per CTA, dynamic shared memory bytes, output tiles}.
+ * splits / block_n: 0 = automatic, as in sfk_gemm_bf16. */
 int sfk_gemm_plan(int M, int N, int K, int a_mn, int b_mn, int out_bf16, int atomic_add, int splits, int block_n, int* out8);
 
 /* ---- dense contractions (tcgen05 + TMA + TMEM) ------------------------------------------------------------

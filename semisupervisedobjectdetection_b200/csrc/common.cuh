@@ -170,6 +170,27 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
       : "memory");
 }
 
+// TMA stores: shared -> global tile writes (bulk async-group completion).  The writing threads must make their generic-proxy
+// shared-memory writes visible to the async proxy first (fence_proxy_async_smem) and the issuing thread must have observed
+// them (__syncwarp / bar.sync) before it issues the store.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tmap), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+// element-wise += into global memory (the tensor map's data type selects the add: f32 here)
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tmap), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// wait until at most N of this thread's committed bulk groups still READ their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
 // tcgen05 ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
@@ -347,6 +368,10 @@ inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
 // 2-D bf16 tensor, inner dimension contiguous. box_inner must be 64 (128 B) for SWIZZLE_128B.
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
                       uint32_t box_inner, uint32_t box_outer);
+// 2-D tensor of 2-byte (elem_bytes == 2, bf16) or 4-byte (f32) elements; box_inner * elem_bytes must equal swizzle_bytes
+// (64 | 128).  Used for the GEMM's TMA-store epilogue and its residual loads.
+int make_tmap_2d_any(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
+                     uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes);
 
 // 3-D bf16 tensor (d0 contiguous). box0 * 2 bytes must equal swizzle_bytes (64 or 128).
 int make_tmap_5d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],

@@ -14,6 +14,8 @@
 // Reference semantics served by this kernel: nn.Linear / 1x1 Conv2d / k==stride Conv2d call sites in
 // segformer_source/models/segformer/modeling_segformer.py:163-165,171-173,236,301,307,713,738 (forward) and their
 // autograd-derived gradients.
+#include <cstring>
+
 #include "common.cuh"
 #include "sfk_internal.h"
 
@@ -24,12 +26,16 @@ static constexpr int BLOCK_K = 64;   // 64 bf16 = 128 B = one swizzle row
 static constexpr int UMMA_K = 16;
 static constexpr int MAX_BLOCK_N = 256;
 static constexpr int TMEM_COLS = 512;  // 2 accumulator buffers x 256 fp32 columns
-static constexpr int GEMM_THREADS = 192;
-static constexpr int MAX_STAGES = 8;
-// behind the barrier block: the current tile's bias slice (MAX_BLOCK_N floats), staged by the epilogue before it waits for
-// the accumulator
-static constexpr uint32_t EPI_BIAS_OFF = 16 * MAX_STAGES + 64;
-static constexpr uint32_t EPI_BIAS_BYTES = 256 * 4;
+static constexpr int GEMM_EPI_WARPS = 8;   // two per TMEM lane quadrant: a lone warp per scheduler cannot hide its own latencies
+static constexpr int GEMM_THREADS = 64 + 32 * GEMM_EPI_WARPS;
+static constexpr int MAX_STAGES = 12;
+// barrier block (behind the operand buffers): full[S], empty[S], tmem_full[2], tmem_empty[2], tmem slot, B-region free,
+// (8 spare barriers); then the current tile's bias slice (MAX_BLOCK_N floats), staged by the epilogue
+// before it waits for the accumulator
+static constexpr uint32_t BAR_MISC_OFF = 16 * MAX_STAGES;
+static constexpr uint32_t EPI_BIAS_OFF = BAR_MISC_OFF + 128;
+static constexpr uint32_t EPI_BIAS_BYTES = 2 * 256 * 4;   // two slots: the next tile's slice is staged while this tile is read
+static constexpr uint32_t EPI_WARP_BUF = 4096;   // one staged chunk of one epilogue warp: 32 rows x 128 B (or 32 x 64 B)
 
 // runtime switch (sfk_set_option("gemm_cluster2", 0|1|2)): CTA pairs (cta_group::2).  Two CTAs of a 2-cluster drive one
 // 256 x N MMA per k-step; each loads its own 128 A rows and HALF of the B tile, so the L2 -> shared-memory stream per
@@ -43,12 +49,30 @@ int g_gemm_cluster2 = 1;
 // overlaps the other's main loop
 int g_gemm_occ2 = 1;
 
+// TMA-store epilogue (sfk_set_option("gemm_epi_tma", 0|1), default 1): each of the 8 epilogue warps stages its 32 rows of a
+// 32-column (f32) or 64-column (bf16) chunk in swizzled shared memory and one lane issues a TMA tile store (reduce-add for
+// split-K); the two warps of a TMEM lane quadrant take alternate chunks.  The legacy epilogue (per-thread row-wise global
+// stores) remains for remapped rows (prompt tokens) and CTA pairs.
+// Measured motivation (profiles/gemm_r2.md): with 4 epilogue warps (one per scheduler, nothing to switch to) a 32-column
+// chunk cost ~1100 cycles of dependent-issue latency and the epilogue, not the MMA, paced every K <= 1280 GEMM (tensor pipe
+// 16-20 %); row-wise fp32 stores made the residual variants ~2x the bf16 ones (24.2 vs 13.5 us at 16384 x 320 x 320).
+int g_gemm_epi_tma = 1;
+// B-stationary main loop (sfk_set_option("gemm_bstat", 0|1), default 1) for K <= 512 without split-K: a CTA owns a contiguous,
+// n-major range of output tiles, keeps the [block_n x K] weight tile resident in shared memory and streams only A.  These
+// GEMMs (M >> N, K) were bound by the L2 -> shared-memory stream, 2/3 of which was the weight tile re-read for every row tile.
+int g_gemm_bstat = 1;
+// experiments (sfk_set_option("gemm_dbg")): bit 0 = skip the TMA stores (wrong results, timing only), bit 1 = skip the proxy
+// fence, bits 4..7 = staging buffers per epilogue warp (0 = default)
+int g_gemm_dbg = 0;
+
 // optional in-kernel timeline (debug): CTA 0 stores globaltimer (ns) at phase boundaries into this device buffer
 unsigned long long* g_gemm_trace = nullptr;
 
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  // SM cycle counter: %globaltimer reads cost ~0.7 us each and distorted the very timeline they were recording.  All
+  // trace slots are written by CTA 0 (one SM), so cycle counts are mutually comparable.
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
   return t;
 }
 #define GEMM_TRACE(slot)                                                     \
@@ -85,6 +109,14 @@ struct GemmKernelParams {
   int a_patch, pa_rows_b, pa_wo, pa_kspan;
   int b_patch, pb_rows_b, pb_wo, pb_span;   // pb_span = sr*C (elements per ky)
   int cluster2;  // CTA-pair mode: launched as 2-CTA clusters, one cta_group::2 MMA per pair (rows 256, B split across the pair)
+  // shared-memory layout (offsets from the 1024-aligned base): [epilogue staging][A/B ring][B region][barriers + bias]
+  uint32_t ring_off, bars_off;
+  int bstat;               // B-stationary: ring holds A only (a_bytes per stage), B tile lives at breg_off (k_blocks x b_kb_bytes)
+  uint32_t breg_off, b_kb_bytes;
+  int epi_tma;             // TMA-store epilogue (kernel template EPI: 1 = f32 chunks of 32 columns, 2 = bf16 chunks of 64 [+ a 32 tail])
+  uint32_t epi_off;        // staging area: 8 warps x 4 KB
+  int do_scale;            // alpha != 1 or per-row scales present
+  int dbg;
 };
 
 __device__ __forceinline__ long long gemm_map_row(long long row, const RowMap& m) {
@@ -98,10 +130,46 @@ __device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, fl
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// Work schedule.  Streaming mode: units (tile, k split) dealt round-robin, column tile fastest.  B-stationary mode: the
+// n-major tile sequence t = n_blk * m_tiles + m_blk is cut into gridDim.x contiguous, equally long ranges, so a CTA changes
+// its weight tile at most a few times.
+struct UnitRange { int begin, end, step; };
+__device__ __forceinline__ UnitRange gemm_units(const GemmKernelParams& p, int pair) {
+  UnitRange r;
+  if (p.bstat) {
+    const long long total = (long long)p.m_tiles * p.n_tiles;
+    r.begin = (int)((total * blockIdx.x) / gridDim.x);
+    r.end = (int)((total * (blockIdx.x + 1)) / gridDim.x);
+    r.step = 1;
+  } else {
+    const int m_groups = pair ? (p.m_tiles + 1) / 2 : p.m_tiles;
+    r.begin = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    r.end = m_groups * p.n_tiles * p.splits;
+    r.step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  }
+  return r;
+}
+__device__ __forceinline__ void gemm_unit_tile(const GemmKernelParams& p, int unit, int pair, uint32_t crank, int& m_blk, int& n_blk,
+                                               int& split) {
+  if (p.bstat) {
+    n_blk = unit / p.m_tiles;
+    m_blk = unit - n_blk * p.m_tiles;
+    split = 0;
+  } else {
+    split = unit % p.splits;
+    const int tile = unit / p.splits;
+    n_blk = tile % p.n_tiles;
+    m_blk = pair ? 2 * (tile / p.n_tiles) + (int)crank : tile / p.n_tiles;
+  }
+}
+
 // PAIR = 1: CTA-pair kernel (must be launched in 2-CTA clusters: it contains cta_group::2 instructions)
-template <int PAIR>
-__global__ void __launch_bounds__(GEMM_THREADS, 2)
+// EPI: 0 = per-thread row-wise epilogue (any output type, row maps), 1 = staged f32 chunks + TMA store / reduce-add,
+//      2 = staged bf16 chunks + TMA store
+template <int PAIR, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_tail,
                          const GemmKernelParams p) {
   pdl_launch_dependents();  // let the next kernel of the stream get scheduled; it waits for our completion itself
   if (threadIdx.x == 0) GEMM_TRACE(0);
@@ -111,14 +179,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
   const uint32_t a_bytes = BLOCK_M * BLOCK_K * 2;
-  const uint32_t bars_off = p.stages * p.stage_bytes;
-  // barrier block: full[S], empty[S], tmem_full[2], tmem_empty[2], tmem_ptr
+  const uint32_t ring = smem_base + p.ring_off;
+  const uint32_t bars_off = p.bars_off;
+  // barrier block: full[S], empty[S], tmem_full[2], tmem_empty[2], tmem_ptr, bfree
   const uint32_t bar_full = smem_base + bars_off;
   const uint32_t bar_empty = bar_full + 8 * MAX_STAGES;
-  const uint32_t bar_tfull = bar_empty + 8 * MAX_STAGES;
+  const uint32_t bar_tfull = bar_full + BAR_MISC_OFF;
   const uint32_t bar_tempty = bar_tfull + 16;
   const uint32_t tmem_slot = bar_tempty + 16;
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + bars_off + 16 * MAX_STAGES + 32);
+  const uint32_t bar_bfree = tmem_slot + 8;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + bars_off + BAR_MISC_OFF + 32);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -126,14 +196,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if (EPI != 0) { tma_prefetch_desc(&tmap_out); tma_prefetch_desc(&tmap_tail); }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, PAIR ? 8 : 4);   // pair: both CTAs' epilogue warps report to the leader
+      mbar_init(bar_tempty + 8 * a, (PAIR ? 2 : 1) * GEMM_EPI_WARPS);   // pair: both CTAs' epilogue warps report to the leader
     }
+    mbar_init(bar_bfree, 1);
     mbar_fence_init();
   }
   // pair kernels take their (pair-collective) TMEM allocation only after the grid dependency has resolved: a dependent
@@ -154,35 +226,42 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const uint32_t tmem_base = *tmem_slot_gen;
   if (threadIdx.x == 0) GEMM_TRACE(1);
 
-  // work units: (row tile | row-tile pair, column tile, k split); in cluster mode the two CTAs of a pair walk the same
-  // unit sequence in lockstep, CTA rank r owning row tile 2*pair + r
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
-  const int m_groups = PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles;
-  const int tiles_mn = m_groups * p.n_tiles;
-  const int total_units = tiles_mn * p.splits;
-  const int unit0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int unit_stride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const UnitRange ur = gemm_units(p, PAIR);
+  const uint32_t ring_stage_bytes = p.bstat ? a_bytes : p.stage_bytes;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int unit = unit0; unit < total_units; unit += unit_stride) {
-        const int split = unit % p.splits;
-        const int tile = unit / p.splits;
-        const int n_blk = tile % p.n_tiles;
-        const int m_blk = PAIR ? 2 * (tile / p.n_tiles) + (int)crank : tile / p.n_tiles;
+      int cur_n = -1;             // B-stationary: column tile currently resident in the B region
+      uint32_t bfree_phase = 0;
+      int ptile = 0;
+      for (int unit = ur.begin; unit < ur.end; unit += ur.step) {
+        int m_blk, n_blk, split;
+        gemm_unit_tile(p, unit, PAIR, crank, m_blk, n_blk, split);
+        if (ptile < 24) GEMM_TRACE(64 + ptile);   // producer starts this tile (debug timeline)
+        ++ptile;
         const int kb0 = (int)(((long long)split * p.k_blocks) / p.splits);
         const int kb1 = (int)(((long long)(split + 1) * p.k_blocks) / p.splits);
+        bool load_b = true;
+        if (p.bstat) {
+          load_b = n_blk != cur_n;
+          if (load_b && cur_n >= 0) {   // every MMA that reads the old weight tile must have retired
+            mbar_wait(bar_bfree, bfree_phase);
+            bfree_phase ^= 1;
+          }
+          cur_n = n_blk;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          const uint32_t sa = smem_base + stage * p.stage_bytes;
-          const uint32_t sb = sa + a_bytes;
+          const uint32_t sa = ring + stage * ring_stage_bytes;
+          const uint32_t sb = p.bstat ? smem_base + p.breg_off + (uint32_t)kb * p.b_kb_bytes : sa + a_bytes;
           if (!PAIR) {
             const uint32_t full = bar_full + 8 * stage;
-            mbar_arrive_expect_tx(full, p.stage_bytes);
-            if (unit == unit0 && kb == kb0) GEMM_TRACE(2);
+            mbar_arrive_expect_tx(full, p.bstat ? a_bytes + (load_b ? p.b_kb_bytes : 0u) : p.stage_bytes);
+            if (unit == ur.begin && kb == kb0) GEMM_TRACE(2);
             if (p.a_patch) {
               // implicit im2col: 128 patch rows = (128 / Wo) ox-rows of one sample; this k-block = 64 of the (kx, c) run of one ky
               const int m0 = m_blk * BLOCK_M;
@@ -195,7 +274,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               tma_load_2d(sa, &tmap_a, full, m_blk * BLOCK_M, kb * BLOCK_K);
               tma_load_2d(sa + 8192, &tmap_a, full, m_blk * BLOCK_M + 64, kb * BLOCK_K);
             }
-            if (p.b_patch) {
+            if (!load_b) {
+              // weight tile already resident
+            } else if (p.b_patch) {
               // MN-major B = patch matrix [K = patch rows, N = (ky, kx, c)]: boxes of [64 n, 64 patch rows]
               const int k0 = kb * BLOCK_K;
               const int bi = k0 / p.pb_rows_b, oy0 = (k0 - bi * p.pb_rows_b) / p.pb_wo;
@@ -214,7 +295,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             // brings its own 128 A rows and its half of the B tile
             const uint32_t full = mapa_shared(bar_full + 8 * stage, 0);
             if (crank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * p.stage_bytes);
-            if (unit == unit0 && kb == kb0) GEMM_TRACE(2);
+            if (unit == ur.begin && kb == kb0) GEMM_TRACE(2);
             if (!p.a_mn) {
               tma_load_2d_pair(sa, &tmap_a, full, kb * BLOCK_K, m_blk * BLOCK_M);
             } else {
@@ -236,84 +317,229 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (pair mode: the leader CTA issues for both) =====================
-    const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, p.block_n, p.a_mn, p.b_mn);
+    // ONE thread runs the whole loop.  Its instruction stream is the pacing resource of short-K GEMMs: the first version
+    // rebuilt both shared-memory descriptors (runtime layout selects, 64-bit packing, R2UR broadcasts under ELECT) for every
+    // tcgen05.mma, ~160 dependent instructions = ~880 cycles per k-block against 320 cycles of tensor work (profiles/
+    // gemm_r2.md).  Now the descriptors of stage 0 / k-step 0 are built once and every MMA's pair is two 64-bit adds.
     const bool issuer = !PAIR || crank == 0;
-    int stage = 0;
-    uint32_t phase = 0;
-    int acc = 0;
-    uint32_t acc_phase[2] = {0, 0};
-    for (int unit = unit0; issuer && unit < total_units; unit += unit_stride) {
-      const int split = unit % p.splits;
-      const int kb0 = (int)(((long long)split * p.k_blocks) / p.splits);
-      const int kb1 = (int)(((long long)(split + 1) * p.k_blocks) / p.splits);
-      // wait for the epilogue to have drained this accumulator buffer
-      mbar_wait(bar_tempty + 8 * acc, acc_phase[acc] ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + acc * (p.tmem_cols >> 1);
-      for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(bar_full + 8 * stage, phase);
+    if (lane == 0 && issuer) {
+      const uint32_t idesc = umma_idesc_bf16(PAIR ? 2 * BLOCK_M : BLOCK_M, p.block_n, p.a_mn, p.b_mn);
+      const uint32_t b_base = p.bstat ? smem_base + p.breg_off : ring + a_bytes;
+      const uint64_t adesc0 = p.a_mn ? umma_smem_desc(ring, 8192, 1024) : umma_smem_desc(ring, 16, 1024);
+      const uint64_t bdesc0 = p.b_mn ? umma_smem_desc(b_base, 8192, 1024) : umma_smem_desc(b_base, 16, 1024);
+      // descriptor address fields count 16-byte units: next k-step = +32 B (K-major) or +2048 B (MN-major)
+      const uint64_t a_kstep = p.a_mn ? 128u : 2u, b_kstep = p.b_mn ? 128u : 2u;
+      const uint64_t a_sstep = ring_stage_bytes >> 4;
+      const uint64_t b_step = p.bstat ? (p.b_kb_bytes >> 4) : (ring_stage_bytes >> 4);   // per k-block (B region) | per stage (ring)
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      int mtile = 0;
+      uint32_t acc_phase[2] = {0, 0};
+      for (int unit = ur.begin; unit < ur.end; unit += ur.step) {
+        int m_blk, n_blk, split;
+        gemm_unit_tile(p, unit, PAIR, crank, m_blk, n_blk, split);
+        const int kb0 = (int)(((long long)split * p.k_blocks) / p.splits);
+        const int kb1 = (int)(((long long)(split + 1) * p.k_blocks) / p.splits);
+        // wait for the epilogue to have drained this accumulator buffer
+        mbar_wait(bar_tempty + 8 * acc, acc_phase[acc] ^ 1);
         tc_fence_after();
-        if (lane == 0 && unit == unit0 && kb == kb0) GEMM_TRACE(3);
-        if (lane == 0) {
-          const uint32_t sa = smem_base + stage * p.stage_bytes;
-          const uint32_t sb = sa + a_bytes;
-#pragma unroll
-          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-            const uint64_t adesc = p.a_mn ? umma_smem_desc(sa + kk * 2048, 8192, 1024)
-                                          : umma_smem_desc(sa + kk * 32, 16, 1024);
-            const uint64_t bdesc = p.b_mn ? umma_smem_desc(sb + kk * 2048, 8192, 1024)
-                                          : umma_smem_desc(sb + kk * 32, 16, 1024);
-            if (PAIR) umma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-            else umma_bf16(tmem_d, adesc, bdesc, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-          }
+        if (mtile < 24) GEMM_TRACE(96 + mtile);    // accumulator buffer free (debug timeline)
+        const uint32_t tmem_d = tmem_base + acc * (p.tmem_cols >> 1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint64_t ad = adesc0 + (uint64_t)stage * a_sstep;
+          const uint64_t bd = bdesc0 + (uint64_t)(p.bstat ? kb : stage) * b_step;
           if (PAIR) {
+            umma_bf16_pair(tmem_d, ad, bd, idesc, kb > kb0 ? 1u : 0u);
+#pragma unroll
+            for (int kk = 1; kk < BLOCK_K / UMMA_K; ++kk) umma_bf16_pair(tmem_d, ad + kk * a_kstep, bd + kk * b_kstep, idesc, 1u);
             umma_commit_pair(bar_empty + 8 * stage, 3);                       // both producers of the pair
             if (kb == kb1 - 1) umma_commit_pair(bar_tfull + 8 * acc, 3);      // both epilogues
           } else {
+            umma_bf16(tmem_d, ad, bd, idesc, kb > kb0 ? 1u : 0u);
+#pragma unroll
+            for (int kk = 1; kk < BLOCK_K / UMMA_K; ++kk) umma_bf16(tmem_d, ad + kk * a_kstep, bd + kk * b_kstep, idesc, 1u);
             umma_commit(bar_empty + 8 * stage);                   // smem slot reusable once these MMAs retire
             if (kb == kb1 - 1) umma_commit(bar_tfull + 8 * acc);  // accumulator complete
           }
-          if (kb == kb1 - 1 && unit == unit0) GEMM_TRACE(4);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (unit == ur.begin) { GEMM_TRACE(3); GEMM_TRACE(4); }
+        if (mtile < 24) GEMM_TRACE(160 + mtile);   // last k-block of the tile issued
+        ++mtile;
+        if (p.bstat && unit + 1 < ur.end && (unit + 1) / p.m_tiles != n_blk)
+          umma_commit(bar_bfree);   // last tile of this column tile: the producer may overwrite the B region once these retire
+        acc_phase[acc] ^= 1;
+        acc ^= 1;
       }
-      acc_phase[acc] ^= 1;
-      acc ^= 1;
     }
+    __syncwarp();
   } else {
-    // ===================== epilogue warps =====================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================== epilogue warps (2..9) =====================
+    const int q = warp & 3;              // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;    // which of the quadrant's two warps: takes every other chunk
     int acc = 0;
     int trace_tile = 0;
     uint32_t acc_phase[2] = {0, 0};
-    for (int unit = unit0; unit < total_units; unit += unit_stride) {
-      const int tile = unit / p.splits;
-      const int n_blk = tile % p.n_tiles;
-      const int m_blk = PAIR ? 2 * (tile / p.n_tiles) + (int)crank : tile / p.n_tiles;
+    const uint32_t stage_buf = smem_base + p.epi_off + (uint32_t)(warp - 2) * EPI_WARP_BUF;
+    const bool has_bias = p.bias != nullptr;
+    const bool has_res = p.residual != nullptr;
+    const bool do_scale = p.do_scale != 0;
+    // bias slices live in two shared-memory slots: while a tile reads one, warp 2 stages the NEXT tile's slice (only when
+    // its column tile differs) into the other; the named barrier at the end of every tile publishes it.  (ncu: bias LDGs
+    // issued after the TMEM load, then a per-tile staging step between two barriers, were the largest epilogue stalls.)
+    uint32_t bias_slot = 0;
+    float* sbias_gen = reinterpret_cast<float*>(smem_gen + bars_off + EPI_BIAS_OFF);
+    if (has_bias && ur.begin < ur.end) {
+      int m_blk, n_blk, split;
+      gemm_unit_tile(p, ur.begin, PAIR, crank, m_blk, n_blk, split);
+      if (warp == 2)
+        for (int j = lane; j < p.block_n; j += 32) sbias_gen[j] = (n_blk * p.block_n + j < p.N) ? __ldg(p.bias + n_blk * p.block_n + j) : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    for (int unit = ur.begin; unit < ur.end; unit += ur.step) {
+      int m_blk, n_blk, split;
+      gemm_unit_tile(p, unit, PAIR, crank, m_blk, n_blk, split);
       const int n0 = n_blk * p.block_n;
-      // ncu: the bias LDGs issued after the TMEM load were the largest stall of the epilogue.  The tile's bias slice goes to
-      // shared memory while the accumulator is still being produced; published by the epilogue-only named barrier below
-      // and released for the next tile by the one at the end of the tile.
-      if (p.bias != nullptr && warp == 2) {
-        float* sbias_gen = reinterpret_cast<float*>(smem_gen + bars_off + EPI_BIAS_OFF);
-        for (int j = lane; j < p.block_n; j += 32) sbias_gen[j] = (n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+      const int row0 = m_blk * BLOCK_M + q * 32;
+      const uint32_t sbias = smem_base + bars_off + EPI_BIAS_OFF + bias_slot * 1024u;
+      // next tile's bias slice: loads issued now (registers), stored to the other slot after this tile's chunks
+      int n_next = n_blk;
+      if (unit + ur.step < ur.end) {
+        int m2, s2;
+        gemm_unit_tile(p, unit + ur.step, PAIR, crank, m2, n_next, s2);
       }
-      const uint32_t sbias = smem_base + bars_off + EPI_BIAS_OFF;
+      const bool bias_reload = has_bias && n_next != n_blk;
+      float bias_next[MAX_BLOCK_N / 32];
+      if (bias_reload && warp == 2) {
+#pragma unroll
+        for (int j = 0; j < MAX_BLOCK_N / 32; ++j) {
+          const int cc = j * 32 + lane;
+          bias_next[j] = (cc < p.block_n && n_next * p.block_n + cc < p.N) ? __ldg(p.bias + n_next * p.block_n + cc) : 0.f;
+        }
+      }
       mbar_wait(bar_tfull + 8 * acc, acc_phase[acc]);
       tc_fence_after();
-      if (p.bias != nullptr) asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (threadIdx.x == 64 && unit == unit0) GEMM_TRACE(5);
+      if (threadIdx.x == 64 && unit == ur.begin) GEMM_TRACE(5);
       if (threadIdx.x == 64 && trace_tile < 28) GEMM_TRACE(8 + 2 * trace_tile);
-      const long long row = (long long)m_blk * BLOCK_M + q * 32 + lane;
+      const long long row = (long long)row0 + lane;
       const bool row_ok = row < p.M;
       float rscale = p.alpha;
       if (p.row_scale != nullptr && row_ok) rscale *= p.row_scale[row / p.rows_per_scale];
+      const p2 rs2 = p2_splat(rscale);
+      const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (p.tmem_cols >> 1);
+      if (EPI != 0) {
+        // ---- staged epilogue: TMEM -> registers -> swizzled shared memory -> TMA store / reduce-add ----
+        constexpr int CW = EPI == 2 ? 64 : 32;               // columns per chunk (a bf16 tile may end in a 32-column chunk)
+        const float* res_row = has_res ? p.residual + row * p.ldr + n0 : nullptr;
+        for (int c0 = (half ^ (trace_tile & 1)) * CW; c0 < p.block_n; c0 += 2 * CW) {
+          const int w = (EPI == 2 && c0 + CW > p.block_n) ? 32 : CW;   // this chunk's width
+          // residual values (first 32 columns of the chunk) first: their latency overlaps the TMEM load and the bias math
+          float4 rr[8];
+          const int col = n0 + c0;
+          const bool res_fast = row_ok && col + w <= p.N;
+          auto load_res = [&](int h) {   // 32 residual values of columns [32 h, 32 h + 32) of this chunk
+            if (res_fast) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) rr[j] = __ldg(reinterpret_cast<const float4*>(res_row + c0 + 32 * h) + j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float t[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int cc = 32 * h + 4 * j + e;
+                  t[e] = (row_ok && cc < w && col + cc < p.N) ? __ldg(res_row + c0 + cc) : 0.f;
+                }
+                rr[j] = make_float4(t[0], t[1], t[2], t[3]);
+              }
+            }
+          };
+          if (has_res) load_res(0);
+          uint32_t r[CW];
+          __syncwarp();
+          tmem_ld_32x32(tmem_acc + c0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+          if (CW == 64 && w == 64) tmem_ld_32x32(tmem_acc + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[CW - 32]));
+          // the TMA store that last read this warp's staging buffer must be done with it
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+          tmem_ld_wait();
+          const uint32_t row_bytes = (EPI == 2 && w == 32) ? 64u : 128u;   // bf16 tail chunk: 64-byte rows (SWIZZLE_64B)
+          const uint32_t xr = row_bytes == 128u ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
+          const uint32_t dst = stage_buf + (uint32_t)lane * row_bytes;
+          // 32 columns at a time: few enough live registers that the 8 bias LDS.128 (and the 8 residual LDG.128) of a step are
+          // issued back to back instead of one round trip per FADD2 (measured: 750 cycles of bias adds per 64-column chunk)
+#pragma unroll
+          for (int h = 0; h < CW / 32; ++h) {
+            if (32 * h < w) {
+              p2 v[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = p2_make_u(r[32 * h + 2 * j], r[32 * h + 2 * j + 1]);
+              if (has_bias) {
+                uint4 b4[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) b4[j] = ld_shared_v4(sbias + (uint32_t)(c0 + 32 * h + 4 * j) * 4);   // broadcast reads
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  v[2 * j] = p2_add(v[2 * j], p2_make_u(b4[j].x, b4[j].y));
+                  v[2 * j + 1] = p2_add(v[2 * j + 1], p2_make_u(b4[j].z, b4[j].w));
+                }
+              }
+              if (do_scale) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = p2_mul(v[j], rs2);
+              }
+              if (has_res) {
+                if (h > 0) load_res(h);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  v[2 * j] = p2_add(v[2 * j], p2_make(rr[j].x, rr[j].y));
+                  v[2 * j + 1] = p2_add(v[2 * j + 1], p2_make(rr[j].z, rr[j].w));
+                }
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  float lo, hi;
+                  p2_split(v[j], lo, hi);
+                  v[j] = p2_make(fmaxf(lo, 0.f), fmaxf(hi, 0.f));
+                }
+              }
+              if (EPI == 2) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  st_shared_v4(dst + (((uint32_t)(4 * h + j) ^ xr) << 4), p2_to_bf16x2(v[4 * j]), p2_to_bf16x2(v[4 * j + 1]),
+                               p2_to_bf16x2(v[4 * j + 2]), p2_to_bf16x2(v[4 * j + 3]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  uint32_t a0, a1, a2, a3;
+                  p2_split_u(v[2 * j], a0, a1);
+                  p2_split_u(v[2 * j + 1], a2, a3);
+                  st_shared_v4(dst + (((uint32_t)j ^ xr) << 4), a0, a1, a2, a3);
+                }
+              }
+            }
+          }
+          if (!(p.dbg & 2)) fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            // boxes reaching past M or N are clipped by the TMA unit
+            if (p.dbg & 1) {}   // experiment: no stores
+            else if (EPI == 1 && p.atomic_add) tma_reduce_add_2d(&tmap_out, stage_buf, n0 + c0, row0);
+            else if (EPI == 2 && w == 32) tma_store_2d(&tmap_tail, stage_buf, n0 + c0, row0);
+            else tma_store_2d(&tmap_out, stage_buf, n0 + c0, row0);
+            tma_store_commit();
+          }
+        }
+      } else {
       const long long orow = gemm_map_row(row, p.out_map);
-      for (int c = 0; c < p.block_n; c += 32) {
+      for (int c = (half ^ (trace_tile & 1)) * 32; c < p.block_n; c += 64) {
         uint32_t r[32];
         __syncwarp();
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * (p.tmem_cols >> 1) + c, r);
+        tmem_ld_32x32(tmem_acc + c, r);
         tmem_ld_wait();
         const int col0 = n0 + c;
         if (!row_ok || col0 >= p.N) continue;
@@ -321,7 +547,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         const bool full_chunk = (col0 + 32 <= p.N);
-        if (p.bias != nullptr) {
+        if (has_bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const uint4 b4 = ld_shared_v4(sbias + (uint32_t)(c + j) * 4);   // broadcast read (zeros past N)
@@ -331,7 +557,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= rscale;
-        if (p.residual != nullptr) {
+        if (has_res) {
           const float* rp = p.residual + gemm_map_row(row, p.res_map) * p.ldr + col0;
           if (full_chunk) {
 #pragma unroll
@@ -385,19 +611,30 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         if (PAIR) mbar_arrive_cluster(mapa_shared(bar_tempty + 8 * acc, 0));   // the leader's MMA issuer waits for both CTAs
         else mbar_arrive(bar_tempty + 8 * acc);
       }
-      if (threadIdx.x == 64 && unit == unit0) GEMM_TRACE(6);
+      if (threadIdx.x == 64 && unit == ur.begin) GEMM_TRACE(6);
       if (threadIdx.x == 64 && trace_tile < 28) GEMM_TRACE(9 + 2 * trace_tile);
       ++trace_tile;
-      if (p.bias != nullptr) asm volatile("bar.sync 1, 128;" ::: "memory");  // everyone is done with this tile's bias slice
+      if (bias_reload) {
+        if (warp == 2) {
+#pragma unroll
+          for (int j = 0; j < MAX_BLOCK_N / 32; ++j)
+            if (j * 32 + lane < p.block_n) sbias_gen[(bias_slot ^ 1u) * 256u + j * 32 + lane] = bias_next[j];
+        }
+        bias_slot ^= 1u;
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // next slice published; (two tiles later) this slot is free again
+      }
       acc_phase[acc] ^= 1;
       acc ^= 1;
     }
+    // staged chunks must have left shared memory before the CTA retires
+    if (EPI != 0 && lane == 0) tma_store_wait_read<0>();
   }
 
   tc_fence_before();
@@ -470,9 +707,36 @@ static int pick_block_n_pair(int N, int b_mn, int M, int atomic_add) {
   return best;
 }
 
-// Host-side launch plan: tile width, residency mode (1 CTA/SM, 2 CTAs/SM, CTA pairs), split-K count, pipeline depth, grid.
-// Pure arithmetic on the problem shape (no device access beyond the cached SM count), so tests can exercise it without a GPU
-// through sfk_gemm_plan().
+// B-stationary tile width: the [bn x K] weight tile must leave room for >= 3 A stages; cost = tiles per CTA x (bn + fixed
+// per-tile overhead) with the contiguous even split (every CTA gets floor or ceil of tiles / CTAs).
+static int pick_block_n_bstat(int N, int b_mn, int M, int k_blocks, int smem_fixed, int* stages_out) {
+  const int cands_k[] = {256, 224, 192, 160, 128, 96, 64, 32};
+  const int cands_mn[] = {256, 192, 128, 64};
+  const int* cands = b_mn ? cands_mn : cands_k;
+  const int nc = b_mn ? 4 : 8;
+  const int m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  const int sms = num_sms();
+  int best = 0, best_stages = 0;
+  double best_cost = 1e30;
+  for (int i = 0; i < nc; ++i) {
+    const int bn = cands[i];
+    const long long b_bytes = (long long)bn * k_blocks * 128;
+    long long stages = (227 * 1024 - smem_fixed - b_bytes) / (BLOCK_M * BLOCK_K * 2);
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 3) continue;
+    const int n_tiles = (N + bn - 1) / bn;
+    const long long tiles = (long long)m_tiles * n_tiles;
+    const long long per_cta = (tiles + sms - 1) / sms;
+    const double cost = (double)per_cta * (bn + 40);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; best_stages = (int)stages; }
+  }
+  *stages_out = best_stages;
+  return best;
+}
+
+// Host-side launch plan: tile width, residency mode (1 CTA/SM, 2 CTAs/SM, CTA pairs, B-stationary), epilogue mode, split-K
+// count, pipeline depth, shared-memory layout, grid.  Pure arithmetic on the problem shape (no device access beyond the
+// cached SM count), so tests can exercise it without a GPU through sfk_gemm_plan().
 static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, size_t& smem_bytes) {
   SFK_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
   SFK_REQUIRE(!(g.atomic_add && g.out_bf16), "gemm: atomic accumulation needs an fp32 output");
@@ -480,6 +744,7 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
   p.a_mn = g.a_mn ? 1 : 0;
   p.b_mn = g.b_mn ? 1 : 0;
   p.k_blocks = (g.K + BLOCK_K - 1) / BLOCK_K;
+  p.m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
   // CTA pairs (cta_group::2) when enabled and the shape allows it
   int pair_bn = 0;
   const bool a_patch = g.a_patch.enabled != 0, b_patch = g.b_patch.enabled != 0;
@@ -503,26 +768,33 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
     }
   }
   p.cluster2 = pair_bn > 0 ? 1 : 0;
-  // latency-bound regime (few k-blocks per tile): prefer two co-resident CTAs per SM over wide tiles
-  const bool occ2 = !p.cluster2 && g_gemm_occ2 && g.block_n <= 0 && !g.atomic_add && p.k_blocks <= 8 && g.N >= 64;
-  p.block_n = pair_bn > 0 ? pair_bn : (g.block_n > 0 ? g.block_n : pick_block_n(g.N, p.b_mn, g.M, g.atomic_add));
-  if (occ2 && p.block_n > 128) {
-    // widest tile <= 128 columns with the least padding
-    const int c_k[] = {128, 96, 64}, c_mn[] = {128, 64};
-    const int* c = p.b_mn ? c_mn : c_k;
-    const int nc2 = p.b_mn ? 2 : 3;
-    int best = c[0];
-    long long best_cols = 1LL << 60;
-    for (int i = 0; i < nc2; ++i) {
-      const long long cols = (long long)((g.N + c[i] - 1) / c[i]) * c[i];
-      if (cols < best_cols) { best_cols = cols; best = c[i]; }
+
+  // epilogue mode: TMA tile stores need identity row maps (prompt-token remaps keep the per-thread path); CTA pairs keep it too
+  const bool maps_identity = g.out_map.period == 0 && g.out_map.offset == 0 && g.res_map.period == 0 && g.res_map.offset == 0;
+  const bool epi_tma = g_gemm_epi_tma && maps_identity && !p.cluster2;
+  const uint32_t stage_bytes_epi = epi_tma ? (uint32_t)GEMM_EPI_WARPS * EPI_WARP_BUF : 0u;
+  const uint32_t bars_bytes = EPI_BIAS_OFF + EPI_BIAS_BYTES;
+
+  // B-stationary main loop: small K, no split-K, plain operands
+  p.bstat = 0;
+  int bstat_bn = 0, bstat_stages = 0;
+  if (g_gemm_bstat && !p.cluster2 && !a_patch && !b_patch && (!g.atomic_add || g.splits == 1) && g.splits <= 1 && p.k_blocks <= 8) {
+    const int fixed = (int)(stage_bytes_epi + bars_bytes + 1024u);
+    if (g.block_n > 0) {
+      const long long b_bytes = (long long)g.block_n * p.k_blocks * 128;
+      long long st = (227 * 1024 - fixed - b_bytes) / (BLOCK_M * BLOCK_K * 2);
+      if (st > MAX_STAGES) st = MAX_STAGES;
+      if (st >= 3 && g.block_n % 32 == 0 && (!p.b_mn || g.block_n % 64 == 0)) { bstat_bn = g.block_n; bstat_stages = (int)st; }
+    } else {
+      bstat_bn = pick_block_n_bstat(g.N, p.b_mn, g.M, p.k_blocks, fixed, &bstat_stages);
     }
-    p.block_n = best;
+    if (bstat_bn > 0) p.bstat = 1;
   }
-  p.tmem_cols = (occ2 && p.block_n <= 128) ? 256 : TMEM_COLS;
+
+  p.block_n = p.bstat ? bstat_bn : pair_bn > 0 ? pair_bn : (g.block_n > 0 ? g.block_n : pick_block_n(g.N, p.b_mn, g.M, g.atomic_add));
+  p.tmem_cols = TMEM_COLS;
   SFK_REQUIRE(p.block_n % 32 == 0 && p.block_n >= 32 && p.block_n <= MAX_BLOCK_N, "gemm: bad block_n %d", p.block_n);
   SFK_REQUIRE(!p.b_mn || p.block_n % 64 == 0, "gemm: MN-major B needs block_n %% 64 == 0");
-  p.m_tiles = (g.M + BLOCK_M - 1) / BLOCK_M;
   p.n_tiles = (g.N + p.block_n - 1) / p.block_n;
   int splits = g.splits;
   if (splits <= 0) {
@@ -550,11 +822,27 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
   if (splits < 1) splits = 1;
   SFK_REQUIRE(splits == 1 || g.atomic_add, "gemm: split-K requires atomic accumulation");
   p.splits = splits;
+
+  // shared-memory layout: [epilogue staging][A/B ring][B region][barriers + bias]
+  p.epi_tma = epi_tma ? 1 : 0;
+  p.epi_off = 0;
+  p.dbg = g_gemm_dbg;
+  p.do_scale = (g.alpha != 1.0f || g.row_scale != nullptr) ? 1 : 0;
+  p.ring_off = stage_bytes_epi;
   p.stage_bytes = BLOCK_M * BLOCK_K * 2 + (p.cluster2 ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;   // per CTA
-  const int smem_budget = (p.tmem_cols == 256 ? 110 * 1024 : 227 * 1024) - 2048 - (int)EPI_BIAS_BYTES;
-  int stages = smem_budget / (int)p.stage_bytes;
-  if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages > p.k_blocks + 1 && p.tmem_cols == 256) stages = p.k_blocks + 1;
+  p.b_kb_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
+  int stages;
+  if (p.bstat) {
+    stages = bstat_stages;
+    p.breg_off = p.ring_off + (uint32_t)stages * BLOCK_M * BLOCK_K * 2;
+    p.bars_off = p.breg_off + (uint32_t)p.k_blocks * p.b_kb_bytes;
+  } else {
+    const int budget = 227 * 1024 - 1024 - (int)bars_bytes - (int)p.ring_off;
+    stages = budget / (int)p.stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    p.breg_off = 0;
+    p.bars_off = p.ring_off + (uint32_t)stages * p.stage_bytes;
+  }
   SFK_REQUIRE(stages >= 2, "gemm: not enough shared memory for 2 stages");
   p.stages = stages;
   p.alpha = g.alpha;
@@ -580,13 +868,14 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
   p.pb_rows_b = b_patch ? g.b_patch.Ho * g.b_patch.Wo : 1;
   p.pb_wo = b_patch ? g.b_patch.Wo : 1;
   p.pb_span = b_patch ? g.b_patch.sr * g.b_patch.C : 1;
-  smem_bytes = (size_t)p.stages * p.stage_bytes + EPI_BIAS_OFF + EPI_BIAS_BYTES + 1024;
+  smem_bytes = (size_t)p.bars_off + bars_bytes + 1024;
+  SFK_REQUIRE(smem_bytes <= (size_t)227 * 1024, "gemm: shared-memory plan of %zu bytes exceeds 227 KB", smem_bytes);
   const long long units = (long long)(p.cluster2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles * p.splits;
   if (p.cluster2) {
     const long long clusters = units < num_sms() / 2 ? units : num_sms() / 2;
     grid = (int)(2 * clusters);
   } else {
-    const long long slots = (long long)num_sms() * (p.tmem_cols == 256 ? 2 : 1);
+    const long long slots = (long long)num_sms();
     grid = (int)(units < slots ? units : slots);
   }
   return 0;
@@ -599,7 +888,7 @@ int gemm_plan(const GemmDesc& g, int out[8]) {
   const int rc = gemm_make_plan(g, p, grid, smem);
   if (rc) return rc;
   out[0] = p.block_n; out[1] = p.splits; out[2] = p.stages; out[3] = grid;
-  out[4] = p.cluster2; out[5] = p.tmem_cols; out[6] = (int)smem; out[7] = p.m_tiles * p.n_tiles;
+  out[4] = p.cluster2 | (p.bstat << 1) | (p.epi_tma << 2); out[5] = p.tmem_cols; out[6] = (int)smem; out[7] = p.m_tiles * p.n_tiles;
   return 0;
 }
 
@@ -646,10 +935,27 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   else         rc = make_tmap_2d_bf16(&tb, g.b, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)g.ldb * 2, 64, BLOCK_K);
   if (rc) return rc;
 
+  CUtensorMap tout, ttail;
+  memset(&tout, 0, sizeof(tout));
+  memset(&ttail, 0, sizeof(ttail));
+  const int epi = !p.epi_tma ? 0 : (g.out_bf16 ? 2 : 1);
+  if (epi == 1) {
+    rc = make_tmap_2d_any(&tout, g.out, 4, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo * 4, 32, 32, 128);
+    if (rc) return rc;
+    ttail = tout;
+  } else if (epi == 2) {
+    rc = make_tmap_2d_any(&tout, g.out, 2, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo * 2, 64, 32, 128);
+    if (rc) return rc;
+    rc = make_tmap_2d_any(&ttail, g.out, 2, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo * 2, 32, 32, 64);
+    if (rc) return rc;
+  }
+
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     SFK_REQUIRE(e == cudaSuccess, "gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -670,9 +976,13 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    (void)cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<1>, ta, tb, p);
+    (void)cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<1, 0>, ta, tb, tout, ttail, p);
+  } else if (epi == 1) {
+    launch_k(gemm_bf16_tcgen05_kernel<0, 1>, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, tout, ttail, p);
+  } else if (epi == 2) {
+    launch_k(gemm_bf16_tcgen05_kernel<0, 2>, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, tout, ttail, p);
   } else {
-    launch_k(gemm_bf16_tcgen05_kernel<0>, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, p);
+    launch_k(gemm_bf16_tcgen05_kernel<0, 0>, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, tout, ttail, p);
   }
   prof_gemm_end(stream);
   return check_launch("gemm_bf16_tcgen05_kernel");

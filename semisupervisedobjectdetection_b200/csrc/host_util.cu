@@ -82,6 +82,29 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t inner, uint64
   return 0;
 }
 
+int make_tmap_2d_any(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
+                     uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+  PFN_encodeTiled enc = get_encode();
+  SFK_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  SFK_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "tensor map: element size %d unsupported", elem_bytes);
+  SFK_REQUIRE((int)box_inner * elem_bytes == swizzle_bytes && (swizzle_bytes == 64 || swizzle_bytes == 128),
+              "tensor map: inner box (%u x %d B) must equal the swizzle span (%d B)", box_inner, elem_bytes, swizzle_bytes);
+  SFK_REQUIRE(box_outer >= 1 && box_outer <= 256, "tensor map: outer box %u out of range", box_outer);
+  SFK_REQUIRE(row_stride_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0,
+              "tensor map: base / row stride must be multiples of 16 bytes");
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstride[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                   const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  SFK_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(2d any) failed with CUresult %d (inner=%llu outer=%llu stride=%llu)",
+              (int)r, (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_stride_bytes);
+  return 0;
+}
+
 // rank-5 tiled map (bf16, SWIZZLE_128B, inner box = 64 elements): used for the k == stride patch view of a channels-last map
 int make_tmap_5d_bf16(CUtensorMap* out, const void* base, const uint64_t dims[5], const uint64_t strides_bytes[4],
                       const uint32_t box[5]) {

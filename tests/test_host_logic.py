@@ -133,13 +133,17 @@ def _plan(M, N, K, a_mn=0, b_mn=0, out_bf16=1, atomic=0, splits=0, block_n=0):
     out = (ctypes.c_int * 8)()
     rc = lib.sfk_gemm_plan(M, N, K, a_mn, b_mn, out_bf16, atomic, splits, block_n, out)
     assert rc == 0, L.last_error()
-    keys = ("block_n", "splits", "stages", "grid", "pair", "tmem_cols", "smem", "tiles")
-    return dict(zip(keys, list(out)))
+    keys = ("block_n", "splits", "stages", "grid", "mode", "tmem_cols", "smem", "tiles")
+    d = dict(zip(keys, list(out)))
+    # mode bits: 1 = CTA pair (cta_group::2), 2 = B-stationary main loop, 4 = TMA-store epilogue
+    d["pair"], d["bstat"], d["epi_tma"] = d["mode"] & 1, (d["mode"] >> 1) & 1, (d["mode"] >> 2) & 1
+    return d
 
 
 def test_gemm_plan_invariants_over_the_mit_shapes():
     """Every forward / dgrad / wgrad shape of MiT-b0..b5 at 512x512 (batch 16): legal tile widths, pipeline depth, grids that
-    fit the machine, shared memory within the 227 KB (113 KB when two CTAs share an SM) budgets."""
+    fit the machine, shared memory within the 227 KB budget; K <= 512 non-split GEMMs keep their weight tile resident with
+    at least 3 A stages; split-K only with atomics."""
     SMS = 148   # num_sms() falls back to the B200 count without a device
     stages_cfg = [(262144, 64, 256), (65536, 128, 512), (16384, 320, 1280), (4096, 512, 2048),     # b1..b5: (tokens, C, 4C)
                   (262144, 32, 128), (65536, 64, 256), (16384, 160, 640), (4096, 256, 1024)]       # b0
@@ -155,13 +159,21 @@ def test_gemm_plan_invariants_over_the_mit_shapes():
         assert p["block_n"] % 32 == 0 and 32 <= p["block_n"] <= 256, (M, N, K, p)
         if b_mn:
             assert p["block_n"] % 64 == 0, (M, N, K, p)
-        assert 2 <= p["stages"] <= 8 and 1 <= p["splits"] <= kb, (M, N, K, p)
+        assert 2 <= p["stages"] <= 12 and 1 <= p["splits"] <= kb, (M, N, K, p)
         assert p["splits"] == 1 or atomic, (M, N, K, p)
-        two_per_sm = p["tmem_cols"] == 256
-        assert p["grid"] <= SMS * (2 if two_per_sm else 1) and p["grid"] >= 1, (M, N, K, p)
-        assert p["smem"] <= (113 if two_per_sm else 227) * 1024, (M, N, K, p)
+        assert p["tmem_cols"] == 512 and 2 * p["block_n"] <= 512, (M, N, K, p)
+        assert 1 <= p["grid"] <= SMS, (M, N, K, p)
+        assert p["smem"] <= 227 * 1024, (M, N, K, p)
         if p["pair"]:
-            assert p["grid"] % 2 == 0 and (not b_mn or p["block_n"] % 128 == 0), (M, N, K, p)
+            assert p["grid"] % 2 == 0 and (not b_mn or p["block_n"] % 128 == 0) and not p["epi_tma"], (M, N, K, p)
+        else:
+            assert p["epi_tma"], (M, N, K, p)
+        if kb <= 8 and not atomic:
+            assert p["bstat"] and p["stages"] >= 3, (M, N, K, p)
+            # resident weight tile + A ring + 32 KB of epilogue staging fit
+            assert p["block_n"] * kb * 128 + p["stages"] * 16384 + 32768 <= p["smem"], (M, N, K, p)
+        else:
+            assert not p["bstat"], (M, N, K, p)
 
 
 def test_gemm_plan_split_k_takes_whole_rounds():
@@ -178,14 +190,16 @@ def test_gemm_plan_split_k_takes_whole_rounds():
 
 
 def test_gemm_plan_modes():
-    """CTA pairs only for the large problems (default option), two CTAs per SM only for K <= 512 non-atomic GEMMs, explicit
-    requests honoured."""
+    """CTA pairs only for the large problems (default option), the B-stationary loop only for K <= 512 non-split GEMMs (with
+    a tile width that covers N without padding where one exists), explicit requests honoured."""
     big = _plan(262144, 768, 3072)
-    assert big["pair"] == 1 and big["block_n"] == 256 and big["tmem_cols"] == 512, big
+    assert big["pair"] == 1 and big["block_n"] == 256 and big["tmem_cols"] == 512 and not big["bstat"], big
     small_k = _plan(16384, 320, 320)
-    assert small_k["pair"] == 0 and small_k["tmem_cols"] == 256 and small_k["block_n"] <= 128, small_k
+    assert small_k["pair"] == 0 and small_k["bstat"] == 1 and small_k["block_n"] == 160 and small_k["epi_tma"] == 1, small_k
+    ffn1 = _plan(16384, 1280, 320)
+    assert ffn1["bstat"] == 1 and 1280 % ffn1["block_n"] == 0, ffn1
     long_k = _plan(16384, 320, 1280)
-    assert long_k["pair"] == 0 and long_k["tmem_cols"] == 512, long_k
+    assert long_k["pair"] == 0 and long_k["bstat"] == 0 and long_k["epi_tma"] == 1, long_k
     forced = _plan(4096, 256, 256, block_n=64, splits=0)
     assert forced["block_n"] == 64, forced
     import ctypes

@@ -39,9 +39,10 @@ def main():
     if os.environ.get("SFK_GEMM_CLUSTER2") is not None:
         L.check(L.load().sfk_set_option(b"gemm_cluster2", 2 * int(os.environ["SFK_GEMM_CLUSTER2"])))  # 1 -> "whenever possible"
         print("gemm_cluster2 =", os.environ["SFK_GEMM_CLUSTER2"], flush=True)
-    if os.environ.get("SFK_GEMM_OCC2") is not None:
-        L.check(L.load().sfk_set_option(b"gemm_occ2", int(os.environ["SFK_GEMM_OCC2"])))
-        print("gemm_occ2 =", os.environ["SFK_GEMM_OCC2"], flush=True)
+    for opt in ("gemm_occ2", "gemm_epi_tma", "gemm_bstat", "gemm_dbg"):
+        if os.environ.get("SFK_" + opt.upper()) is not None:
+            L.check(L.load().sfk_set_option(opt.encode(), int(os.environ["SFK_" + opt.upper()])))
+            print(opt, "=", os.environ["SFK_" + opt.upper()], flush=True)
     torch.manual_seed(0)
     dev = "cuda"
     allok = True
@@ -85,9 +86,43 @@ def main():
         allok &= report("epilogue bias+scale+residual", out, ref)
         out = gemm(a, b, M, N, K, bias=bias, relu=True, out_bf16=True)
         allok &= report("epilogue bias+relu bf16", out, torch.relu(a.float() @ b.float().t() + bias))
+    elif group == "v2":
+        # TMA-store epilogue + B-stationary main loop: every epilogue combination on full, ragged and multi-column-tile shapes
+        shapes = [(512, 320, 320, 0), (16384, 1280, 320, 0), (16384, 320, 320, 0), (1000, 200, 152, 0), (4096, 640, 320, 0),
+                  (2048, 64, 64, 0), (2048, 256, 64, 0), (130, 40, 72, 0), (4096, 320, 1280, 0), (4096, 2048, 512, 0),
+                  (16384, 1280, 320, 128), (16384, 1280, 320, 224), (3000, 96, 512, 32)]
+        for (M, N, K, bn) in shapes:
+            a = torch.randn(M, K, device=dev).bfloat16()
+            b = torch.randn(N, K, device=dev).bfloat16()
+            bias = torch.randn(N, device=dev)
+            res = torch.randn(M, N, device=dev)
+            rs = torch.rand((M + 255) // 256, device=dev) + 0.5
+            base = a.float() @ b.float().t()
+            rsv = rs.repeat_interleave(256)[:M, None]
+            out = gemm(a, b, M, N, K, bias=bias, out_bf16=True, block_n=bn)
+            allok &= report(f"v2 bf16+bias M{M} N{N} K{K} bn{bn}", out, base + bias)
+            out = gemm(a, b, M, N, K, bias=bias, residual=res, row_scale=rs, rows_per_scale=256, block_n=bn)
+            allok &= report(f"v2 f32+bias+scale+res M{M} N{N} K{K} bn{bn}", out, (base + bias) * rsv + res)
+            out = gemm(a, b, M, N, K, residual=res, out_bf16=True, relu=True, block_n=bn)
+            allok &= report(f"v2 bf16+res+relu M{M} N{N} K{K} bn{bn}", out, torch.relu(base + res))
+            out = gemm(a, b, M, N, K, alpha=0.25, block_n=bn)
+            allok &= report(f"v2 f32 alpha M{M} N{N} K{K} bn{bn}", out, 0.25 * base)
+            # dgrad layout (MN-major B) with residual, bf16 out
+            if N % 8 == 0:
+                w = torch.randn(K, N, device=dev).bfloat16()
+                out = gemm(a, w, M, N, K, b_mn=1, residual=res, out_bf16=True)
+                allok &= report(f"v2 dgrad+res M{M} N{N} K{K}", out, a.float() @ w.float() + res)
+        # split-K reduce-add epilogue accumulates into existing contents
+        T, No, Ki = 16384, 320, 1280
+        dy = torch.randn(T, No, device=dev).bfloat16()
+        x = torch.randn(T, Ki, device=dev).bfloat16()
+        out = torch.ones(No, Ki, device=dev)
+        gemm(dy, x, No, Ki, T, a_mn=1, b_mn=1, atomic=True, out=out)
+        gemm(dy, x, No, Ki, T, a_mn=1, b_mn=1, atomic=True, out=out)
+        allok &= report("v2 wgrad reduce-add twice", out, 2 * (dy.float().t() @ x.float()) + 1)
     elif group == "trace":
         lib = L.load()
-        buf = torch.zeros(64, device=dev, dtype=torch.int64)
+        buf = torch.zeros(256, device=dev, dtype=torch.int64)
         cases = [("q_s3 16384x320x320", 16384, 320, 320, 0), ("ffn1_s3 16384x1280x320", 16384, 1280, 320, 0),
                  ("ffn1_s3 bn256", 16384, 1280, 320, 256), ("ffn2_s3 16384x320x1280", 16384, 320, 1280, 0),
                  ("ffn1_s1 262144x256x64", 262144, 256, 64, 0), ("q_s1 262144x64x64", 262144, 64, 64, 0)]
@@ -108,11 +143,13 @@ def main():
             torch.cuda.synchronize()
             lib.sfk_debug_gemm_trace(None)
             t = buf.cpu().tolist()
-            rel = [(x - t[0]) / 1000.0 if x else float("nan") for x in t]
+            rel = [(x - t[0]) / 1965.0 if x else float("nan") for x in t]   # SM cycles at the 1965 MHz boost clock -> us
             print(f"TRACE {name}: event {e0.elapsed_time(e1)*1000:.1f} us | us since CTA0 start: setup {rel[1]:.2f} tma0 {rel[2]:.2f} "
                   f"landed {rel[3]:.2f} last-mma {rel[4]:.2f} acc-ready {rel[5]:.2f} tile-stored {rel[6]:.2f} cta-done {rel[7]:.2f}", flush=True)
             tiles = [(rel[8 + 2 * i], rel[9 + 2 * i]) for i in range(28) if t[8 + 2 * i]]
             print("      per tile (acc-ready, stored): " + " ".join(f"({a0:.2f},{a1:.2f})" for a0, a1 in tiles), flush=True)
+            for label, base in (("producer starts tile", 64), ("accumulator free", 96), ("last k-block issued", 160)):
+                print(f"      {label:22s}: " + " ".join(f"{rel[base + i]:.2f}" for i in range(24) if t[base + i]), flush=True)
     elif group == "perf":
         shapes = [("q_s3 16384x320x320", 16384, 320, 320), ("kv_s3 4096x640x320", 4096, 640, 320),
                   ("fuse 262144x768x3072", 262144, 768, 3072), ("ffn1_s3 16384x1280x320", 16384, 1280, 320),

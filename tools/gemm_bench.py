@@ -56,6 +56,11 @@ def make_case(kind, M, N, K):
         if kind == "fwd_bf16":
             out = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
             return (lambda: gemm(a, w, M, N, K, bias=bias, out_bf16=True, out=out)), (lambda: torch.matmul(a, w.t()))
+        if kind == "fwd_red":   # residual already in the output buffer: scaled accumulator reduce-added in place (split-K style epilogue)
+            out = torch.zeros(M, N, device=DEV, dtype=torch.float32)
+            rs = torch.ones(B, device=DEV)
+            return (lambda: gemm(a, w, M, N, K, bias=bias, row_scale=rs, rows_per_scale=max(1, M // B), atomic=True, splits=1, out=out)), \
+                   (lambda: torch.matmul(a, w.t()))
         res = torch.randn(M, N, device=DEV) if kind == "fwd_res" else None
         rs = torch.ones(B, device=DEV) if kind == "fwd_res" else None
         out = torch.empty(M, N, device=DEV, dtype=torch.float32)
@@ -112,9 +117,10 @@ def main():
     ap.add_argument("--json", default=None)
     ap.add_argument("--filter", default=None)
     ap.add_argument("--no-cublas", action="store_true")
+    ap.add_argument("--as-red", action="store_true", help="time the fwd_res shapes with the in-place reduce-add epilogue instead")
     args = ap.parse_args()
     L.ensure_device()
-    for opt in ("gemm_occ2", "gemm_cluster2", "gemm_wstat"):
+    for opt in ("gemm_occ2", "gemm_cluster2", "gemm_epi_tma", "gemm_bstat", "gemm_dbg"):
         if os.environ.get("SFK_" + opt.upper()) is not None:
             L.check(L.load().sfk_set_option(opt.encode(), int(os.environ["SFK_" + opt.upper()])))
             print(opt, "=", os.environ["SFK_" + opt.upper()], flush=True)
@@ -125,6 +131,8 @@ def main():
             continue
         if args.filter and args.filter not in name:
             continue
+        if args.as_red and kind == "fwd_res":
+            kind = "fwd_red"
         f_sfk, f_cub = make_case(kind, M, N, K)
         us = time_graph(f_sfk)
         us_c = float("nan") if args.no_cublas else time_graph(f_cub)

@@ -90,7 +90,7 @@ def main():
     args = ap.parse_args()
     L.ensure_device()
     lib = L.load()
-    for opt in ("gemm_occ2", "gemm_cluster2", "gemm_wstat", "attn_bwd_persist"):
+    for opt in ("gemm_occ2", "gemm_cluster2", "gemm_epi_tma", "gemm_bstat", "attn_bwd_persist"):
         if os.environ.get("SFK_" + opt.upper()) is not None:
             L.check(lib.sfk_set_option(opt.encode(), int(os.environ["SFK_" + opt.upper()])))
             print(opt, "=", os.environ["SFK_" + opt.upper()], flush=True)
