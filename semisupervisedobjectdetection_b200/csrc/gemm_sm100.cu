@@ -47,7 +47,7 @@ static constexpr uint32_t EPI_WARP_BUF = 4096;   // one staged chunk of one epil
 int g_gemm_cluster2 = 1;
 // small-K GEMMs: 2 resident CTAs per SM (<= 110 KB smem, 256 TMEM columns each) so one CTA's epilogue / pipeline fill
 // overlaps the other's main loop
-int g_gemm_occ2 = 1;
+int g_gemm_occ2 = 0;
 
 // TMA-store epilogue (sfk_set_option("gemm_epi_tma", 0|1), default 1): each of the 8 epilogue warps stages its 32 rows of a
 // 32-column (f32) or 64-column (bf16) chunk in swizzled shared memory and one lane issues a TMA tile store (reduce-add for
@@ -116,6 +116,7 @@ struct GemmKernelParams {
   int epi_tma;             // TMA-store epilogue (kernel template EPI: 1 = f32 chunks of 32 columns, 2 = bf16 chunks of 64 [+ a 32 tail])
   uint32_t epi_off;        // staging area: 8 warps x 4 KB
   int do_scale;            // alpha != 1 or per-row scales present
+  int epi_warps;           // 8 (320-thread CTA, one per SM) | 4 (192-thread CTA: two CTAs per SM, row-wise epilogue)
   int dbg;
 };
 
@@ -203,7 +204,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, (PAIR ? 2 : 1) * GEMM_EPI_WARPS);   // pair: both CTAs' epilogue warps report to the leader
+      mbar_init(bar_tempty + 8 * a, (PAIR ? 2 : 1) * p.epi_warps);   // pair: both CTAs' epilogue warps report to the leader
     }
     mbar_init(bar_bfree, 1);
     mbar_fence_init();
@@ -380,6 +381,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ===================== epilogue warps (2..9) =====================
     const int q = warp & 3;              // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;    // which of the quadrant's two warps: takes every other chunk
+    const int wpq = p.epi_warps >> 2;    // epilogue warps per quadrant (1 | 2)
+    const int epi_threads = 32 * p.epi_warps;
     int acc = 0;
     int trace_tile = 0;
     uint32_t acc_phase[2] = {0, 0};
@@ -397,7 +400,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       gemm_unit_tile(p, ur.begin, PAIR, crank, m_blk, n_blk, split);
       if (warp == 2)
         for (int j = lane; j < p.block_n; j += 32) sbias_gen[j] = (n_blk * p.block_n + j < p.N) ? __ldg(p.bias + n_blk * p.block_n + j) : 0.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
     }
     for (int unit = ur.begin; unit < ur.end; unit += ur.step) {
       int m_blk, n_blk, split;
@@ -434,7 +437,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         // ---- staged epilogue: TMEM -> registers -> swizzled shared memory -> TMA store / reduce-add ----
         constexpr int CW = EPI == 2 ? 64 : 32;               // columns per chunk (a bf16 tile may end in a 32-column chunk)
         const float* res_row = has_res ? p.residual + row * p.ldr + n0 : nullptr;
-        for (int c0 = (half ^ (trace_tile & 1)) * CW; c0 < p.block_n; c0 += 2 * CW) {
+        for (int c0 = (wpq == 2 ? (half ^ (trace_tile & 1)) : 0) * CW; c0 < p.block_n; c0 += wpq * CW) {
           const int w = (EPI == 2 && c0 + CW > p.block_n) ? 32 : CW;   // this chunk's width
           // residual values (first 32 columns of the chunk) first: their latency overlaps the TMEM load and the bias math
           float4 rr[8];
@@ -536,7 +539,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         }
       } else {
       const long long orow = gemm_map_row(row, p.out_map);
-      for (int c = (half ^ (trace_tile & 1)) * 32; c < p.block_n; c += 64) {
+      for (int c = (wpq == 2 ? (half ^ (trace_tile & 1)) : 0) * 32; c < p.block_n; c += wpq * 32) {
         uint32_t r[32];
         __syncwarp();
         tmem_ld_32x32(tmem_acc + c, r);
@@ -628,7 +631,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             if (j * 32 + lane < p.block_n) sbias_gen[(bias_slot ^ 1u) * 256u + j * 32 + lane] = bias_next[j];
         }
         bias_slot ^= 1u;
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // next slice published; (two tiles later) this slot is free again
+        asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");  // next slice published; (two tiles later) this slot is free again
       }
       acc_phase[acc] ^= 1;
       acc ^= 1;
@@ -771,7 +774,7 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
 
   // epilogue mode: TMA tile stores need identity row maps (prompt-token remaps keep the per-thread path); CTA pairs keep it too
   const bool maps_identity = g.out_map.period == 0 && g.out_map.offset == 0 && g.res_map.period == 0 && g.res_map.offset == 0;
-  const bool epi_tma = g_gemm_epi_tma && maps_identity && !p.cluster2;
+  bool epi_tma = g_gemm_epi_tma && maps_identity && !p.cluster2;
   const uint32_t stage_bytes_epi = epi_tma ? (uint32_t)GEMM_EPI_WARPS * EPI_WARP_BUF : 0u;
   const uint32_t bars_bytes = EPI_BIAS_OFF + EPI_BIAS_BYTES;
 
@@ -792,7 +795,23 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
   }
 
   p.block_n = p.bstat ? bstat_bn : pair_bn > 0 ? pair_bn : (g.block_n > 0 ? g.block_n : pick_block_n(g.N, p.b_mn, g.M, g.atomic_add));
-  p.tmem_cols = TMEM_COLS;
+  // "light" CTAs (sfk_set_option("gemm_occ2", 1)): 192 threads, <= 110 KB of shared memory, 256 TMEM columns, row-wise epilogue,
+  // so that two CTAs - of this launch or of a GEMM on another stream - share an SM
+  const bool light = g_gemm_occ2 && !p.bstat && !p.cluster2 && g.block_n <= 0 && !g.atomic_add && p.k_blocks <= 8 && g.N >= 64;
+  if (light && p.block_n > 128) {
+    const int c_k[] = {128, 96, 64}, c_mn[] = {128, 64};
+    const int* c = p.b_mn ? c_mn : c_k;
+    const int nc2 = p.b_mn ? 2 : 3;
+    int best = c[0];
+    long long best_cols = 1LL << 60;
+    for (int i = 0; i < nc2; ++i) {
+      const long long cols = (long long)((g.N + c[i] - 1) / c[i]) * c[i];
+      if (cols < best_cols) { best_cols = cols; best = c[i]; }
+    }
+    p.block_n = best;
+  }
+  p.epi_warps = light ? 4 : GEMM_EPI_WARPS;
+  p.tmem_cols = light ? 256 : TMEM_COLS;
   SFK_REQUIRE(p.block_n % 32 == 0 && p.block_n >= 32 && p.block_n <= MAX_BLOCK_N, "gemm: bad block_n %d", p.block_n);
   SFK_REQUIRE(!p.b_mn || p.block_n % 64 == 0, "gemm: MN-major B needs block_n %% 64 == 0");
   p.n_tiles = (g.N + p.block_n - 1) / p.block_n;
@@ -824,11 +843,12 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
   p.splits = splits;
 
   // shared-memory layout: [epilogue staging][A/B ring][B region][barriers + bias]
+  if (light) epi_tma = false;
   p.epi_tma = epi_tma ? 1 : 0;
   p.epi_off = 0;
   p.dbg = g_gemm_dbg;
   p.do_scale = (g.alpha != 1.0f || g.row_scale != nullptr) ? 1 : 0;
-  p.ring_off = stage_bytes_epi;
+  p.ring_off = epi_tma ? stage_bytes_epi : 0u;
   p.stage_bytes = BLOCK_M * BLOCK_K * 2 + (p.cluster2 ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;   // per CTA
   p.b_kb_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
   int stages;
@@ -837,9 +857,10 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
     p.breg_off = p.ring_off + (uint32_t)stages * BLOCK_M * BLOCK_K * 2;
     p.bars_off = p.breg_off + (uint32_t)p.k_blocks * p.b_kb_bytes;
   } else {
-    const int budget = 227 * 1024 - 1024 - (int)bars_bytes - (int)p.ring_off;
+    const int budget = (light ? 110 : 227) * 1024 - 1024 - (int)bars_bytes - (int)p.ring_off;
     stages = budget / (int)p.stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (light && stages > p.k_blocks + 1) stages = p.k_blocks + 1;
     p.breg_off = 0;
     p.bars_off = p.ring_off + (uint32_t)stages * p.stage_bytes;
   }
@@ -875,7 +896,7 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
     const long long clusters = units < num_sms() / 2 ? units : num_sms() / 2;
     grid = (int)(2 * clusters);
   } else {
-    const long long slots = (long long)num_sms();
+    const long long slots = (long long)num_sms() * (light ? 2 : 1);
     grid = (int)(units < slots ? units : slots);
   }
   return 0;
@@ -982,7 +1003,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   } else if (epi == 2) {
     launch_k(gemm_bf16_tcgen05_kernel<0, 2>, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, tout, ttail, p);
   } else {
-    launch_k(gemm_bf16_tcgen05_kernel<0, 0>, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, tout, ttail, p);
+    launch_k(gemm_bf16_tcgen05_kernel<0, 0>, dim3(grid), dim3(64 + 32 * p.epi_warps), smem, stream, ta, tb, tout, ttail, p);
   }
   prof_gemm_end(stream);
   return check_launch("gemm_bf16_tcgen05_kernel");
