@@ -233,6 +233,26 @@ int sfk_pseudo_label_threshold(const float* p, void* pseudo_i64, float* stats, i
                                sfk_stream_t stream);
 int sfk_denoise_labels(const float* t0, const float* gt, float* out, long long n, sfk_stream_t stream);
 
+/* ---- few-shot / domain-prompt cls-token losses (main_segformer/segFormer_fewshot_learning.py:185-188, 216-226) ---------
+ * out[0] = mean_i cos(a_i, b_i) over n rows of d floats (torch.nn.CosineSimilarity(dim=1), eps 1e-8);
+ * stats f32 [n,3] = {<a,b>, |a|, |b|} is kept for the backward pass; da / db may be NULL. */
+int sfk_cosine_mean_fwd(const float* a, long long lda, const float* b, long long ldb, int n, int d, float* stats, float* out,
+                        sfk_stream_t stream);
+int sfk_cosine_mean_bwd(const float* a, long long lda, const float* b, long long ldb, int n, int d, const float* stats,
+                        const float* dloss, float* da, long long ldda, float* db, long long lddb, sfk_stream_t stream);
+
+/* ---- training input pipeline on the device (config.py:27-38, archaeological_georgia_biostyle_dataloader.py:59-108) --------
+ * src: uint8 tiles, pixel (b, y, x, c) at src + b*batch_stride + y*row_stride + x*pix_stride + c (bytes; c = 0..2 used, so an
+ * RGBA PNG decode is passed as is); params i32 [B,4] = {crop_y0, crop_x0, op, 0}, op: 0 none, 1 HorizontalFlip,
+ * 2 VerticalFlip, 3+k np.rot90(img, k) - the host draws them (albumentations' RandomCrop / OneOf(p=0.75) / RandomRotate90).
+ * out f32 [B,3,OH,OW] = Resize(INTER_LINEAR)(Normalize(mean 0, std 255, max_pixel_value 1)(transformed crop x crop tile)).
+ * mask (optional, may be NULL): uint8, channel 0 used; mask_out f32 [B,OH,OW] = (m - min m) / (max m - min m) of the
+ * INTER_NEAREST-resized transformed crop; minmax: i32 [B,2] workspace. */
+int sfk_tile_augment_u8(const void* src, long long batch_stride, long long row_stride, int pix_stride, int Hs, int Ws,
+                        const int* params, int crop, float* out, int B, int OH, int OW, const void* mask,
+                        long long m_batch_stride, long long m_row_stride, int m_pix_stride, float* mask_out, int* minmax,
+                        sfk_stream_t stream);
+
 /* ---- optimiser (SFM:32-37,158-162) and teacher refresh --------------------------------------------------------- */
 /* clip_grad_value_(clip) then Adam with L2 weight decay over flat f32 buffers; step is 1-based.
  * w_bf16 (optional, same element layout): bf16 shadow of the updated weights written in the same pass. */

@@ -369,3 +369,26 @@ def clip_adam_l2_step(param: Tensor, grad: Tensor, exp_avg: Tensor, exp_avg_sq: 
 
 def ema_update(teacher: Tensor, student: Tensor, decay: float) -> Tensor:
     return decay * teacher + (1 - decay) * student
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# few-shot / domain-prompt cls-token losses (main_segformer/segFormer_fewshot_learning.py, "FS")
+# ---------------------------------------------------------------------------------------------------------------
+def compute_similarity(mat1: Tensor, mat2: Tensor) -> Tensor:
+    """FS:185-188 with similarity_loss = torch.nn.CosineSimilarity(dim=1) (FS:353): mean cosine over the batch."""
+    mat1 = mat1.squeeze(1) if mat1.dim() == 3 else mat1
+    mat2 = mat2.squeeze(1) if mat2.dim() == 3 else mat2
+    return torch.mean(F.cosine_similarity(mat1, mat2, dim=1, eps=1e-8))
+
+
+def fewshot_losses(category_1_loss, category_1_cls_token, category_2_loss, category_2_cls_token):
+    """FS:216-236 -> (summation_loss, intra_loss_1, intra_loss_2, inter_loss)."""
+    batch_size = min(category_1_cls_token.shape[0], category_2_cls_token.shape[0])
+    inter_loss = 0.5 + 0.5 * compute_similarity(category_1_cls_token[:batch_size, :, :], category_2_cls_token[:batch_size, :, :])
+    intra_loss_1 = 0.5 - 0.5 * compute_similarity(category_1_cls_token[:batch_size // 2, :, :],
+                                                  category_1_cls_token[-(batch_size // 2):, :, :])
+    intra_loss_2 = 0.5 - 0.5 * compute_similarity(category_2_cls_token[:batch_size // 2, :, :],
+                                                  category_2_cls_token[-(batch_size // 2):, :, :])
+    category_1_summation_loss = category_1_loss + 100 * inter_loss + 100 * intra_loss_1
+    category_2_summation_loss = category_2_loss + 100 * inter_loss + 100 * intra_loss_2
+    return (category_1_summation_loss + category_2_summation_loss) / 2, intra_loss_1, intra_loss_2, inter_loss

@@ -226,6 +226,21 @@ int sfk_pseudo_label_threshold(const float* p, void* pseudo_i64, float* stats, i
 int sfk_denoise_labels(const float* t0, const float* gt, float* out, long long n, sfk_stream_t stream) {
   return denoise_labels(t0, gt, out, n, ST);
 }
+int sfk_cosine_mean_fwd(const float* a, long long lda, const float* b, long long ldb, int n, int d, float* stats, float* out,
+                        sfk_stream_t stream) {
+  return cosine_mean_fwd(a, lda, b, ldb, n, d, stats, out, ST);
+}
+int sfk_cosine_mean_bwd(const float* a, long long lda, const float* b, long long ldb, int n, int d, const float* stats,
+                        const float* dloss, float* da, long long ldda, float* db, long long lddb, sfk_stream_t stream) {
+  return cosine_mean_bwd(a, lda, b, ldb, n, d, stats, dloss, da, ldda, db, lddb, ST);
+}
+int sfk_tile_augment_u8(const void* src, long long batch_stride, long long row_stride, int pix_stride, int Hs, int Ws,
+                        const int* params, int crop, float* out, int B, int OH, int OW, const void* mask,
+                        long long m_batch_stride, long long m_row_stride, int m_pix_stride, float* mask_out, int* minmax,
+                        sfk_stream_t stream) {
+  return tile_augment_u8(src, batch_stride, row_stride, pix_stride, Hs, Ws, params, crop, out, B, OH, OW, mask, m_batch_stride,
+                         m_row_stride, m_pix_stride, mask_out, minmax, ST);
+}
 int sfk_clip_adam_l2(float* p, const float* g, float* m, float* v, void* w_bf16, long long n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, float clip, int step, sfk_stream_t stream) {
   return clip_adam_l2(p, g, m, v, w_bf16, n, lr, beta1, beta2, eps, weight_decay, clip, step, ST);

@@ -167,6 +167,15 @@ int pseudo_label_threshold(const float* p, long long* pseudo, float* stats, int 
                            float conf_thr, float min_pixels, int allow_throw, float* workspace, cudaStream_t stream);
 int denoise_labels(const float* t0, const float* gt, float* out, long long n, cudaStream_t stream);
 
+// ---- pipeline.cu ----
+int cosine_mean_fwd(const float* a, long long lda, const float* b, long long ldb, int n, int d, float* stats, float* out,
+                    cudaStream_t stream);
+int cosine_mean_bwd(const float* a, long long lda, const float* b, long long ldb, int n, int d, const float* stats,
+                    const float* dloss, float* da, long long ldda, float* db, long long lddb, cudaStream_t stream);
+int tile_augment_u8(const void* src, long long batch_stride, long long row_stride, int pix_stride, int Hs, int Ws, const int* params,
+                    int crop, float* out, int B, int OH, int OW, const void* mask, long long m_batch_stride, long long m_row_stride,
+                    int m_pix_stride, float* mask_out, int* minmax, cudaStream_t stream);
+
 // ---- optim.cu ----
 int clip_adam_l2(float* p, const float* g, float* m, float* v, void* w16, long long n, float lr, float beta1, float beta2,
                  float eps, float wd, float clip, int step, cudaStream_t stream);
