@@ -288,6 +288,33 @@ def run_sfk(args):
     barrier()
     ms_e2e = e0.elapsed_time(e1) / args.steps
     mallocs_e2e = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - mallocs_e2e0
+    # ---- the same end-to-end loop fed the way the reference's data loader is fed: raw uint8 tiles (RGBA PNG decodes with the
+    # 23-row Bing banner, archaeological_georgia_biostyle_dataloader.py:59-108), with RandomCrop / flip / rot90 / 255 / Resize
+    # (config.py:27-38) running in the libsfk input-pipeline kernel instead of albumentations on the host ----
+    from semisupervisedobjectdetection_b200.pipeline import TileAugmenter
+    aug = TileAugmenter(crop=min(500, tile), out_hw=(tile, tile))
+    raw_h, raw_w = aug.crop + 23 + 8, aug.crop + 12
+    gen = torch.Generator().manual_seed(99 + rank)
+    raw_l = torch.randint(0, 256, (N_LABELED, raw_h, raw_w, 4), dtype=torch.uint8, generator=gen).pin_memory()
+    raw_u = torch.randint(0, 256, (N_UNLABELED, raw_h, raw_w, 4), dtype=torch.uint8, generator=gen).pin_memory()
+    raw_m = ((torch.rand(N_LABELED, raw_h, raw_w, generator=gen) > 0.9).to(torch.uint8) * 255).pin_memory()
+    u8_bytes = raw_l.numel() + raw_u.numel() + raw_m.numel() + 2 * 16 * N_LABELED
+
+    def step_u8():
+        p_l = aug.draw_params(N_LABELED, raw_h - 23, raw_w, gen)
+        p_u = aug.draw_params(N_UNLABELED, raw_h - 23, raw_w, gen)
+        img_l, gt_l = aug(raw_l.to(dev, non_blocking=True), p_l, raw_m.to(dev, non_blocking=True), valid_hw=(raw_h - 23, raw_w))
+        img_u, _ = aug(raw_u.to(dev, non_blocking=True), p_u, valid_hw=(raw_h - 23, raw_w))
+        return step(img_l, img_u, gt_l)
+
+    loss_u8 = float(step_u8().detach())
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss_u8 = float(step_u8().detach())
+    e1.record()
+    barrier()
+    ms_e2e_u8 = e0.elapsed_time(e1) / args.steps
     # ---- roofline leg: ONE extra step (outside the timed region) with the side streams off, so that the CUDA events around
     # each GEMM launch time that kernel alone on the GPU instead of a kernel sharing SMs with the teacher / wgrad streams ----
     ops.WGRAD_OVERLAP = False
@@ -339,9 +366,9 @@ def run_sfk(args):
         step(dev_l, dev_u, dev_gt)   # back to the default path before the end-to-end leg
         barrier()
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, ms_literal or 0.0], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, ms_literal or 0.0, ms_e2e_u8], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+        ms, ms_e2e, ms_e2e_u8 = float(t[0]), float(t[1]), float(t[3])
         ms_literal = float(t[2]) if ms_literal is not None else None
     if rank != 0:
         if world > 1:
@@ -377,6 +404,10 @@ def run_sfk(args):
                    "end_to_end_frac_of_sustained_peak": step_tflop / (ms * 1e-3) / pk["tf_sustained"]},
         "e2e": {"value": imgs_per_step / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e, "device_mallocs_in_timed_region": int(mallocs_e2e)},
+        "e2e_u8_input_pipeline": {"value": imgs_per_step / (ms_e2e_u8 * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_u8,
+                                  "h2d_bytes_per_step": int(u8_bytes), "d2h_bytes_per_step": 4,
+                                  "how": "same end-to-end loop fed raw uint8 RGBA tiles + masks from pinned host memory; crop / flip / "
+                                         "rot90 / 255 / bilinear resize (config.py:27-38) run in the libsfk input-pipeline kernel"},
         "literal_decode_head": ({"ms_per_step": ms_literal, "value": imgs_per_step / (ms_literal * 1e-3), "unit": UNIT,
                                  "how": "same step, decode head without the fold, resident inputs"} if ms_literal else None),
         "gpu_launches": int(launches),

@@ -36,18 +36,21 @@ class TileAugmenter:
         op = torch.where(apply, op, torch.zeros_like(op))
         return torch.stack([y0, x0, op, torch.zeros_like(op)], dim=1).to(torch.int32)
 
-    def __call__(self, tiles_u8: torch.Tensor, params: torch.Tensor, masks_u8: Optional[torch.Tensor] = None):
+    def __call__(self, tiles_u8: torch.Tensor, params: torch.Tensor, masks_u8: Optional[torch.Tensor] = None, valid_hw=None):
         """tiles_u8: uint8 [B, H, W, C>=3] on the device (channels 0..2 used); params: int32 [B, 4] (draw_params);
-        masks_u8: optional uint8 [B, H, W] or [B, H, W, C] (channel 0 used).
+        masks_u8: optional uint8 [B, H, W] or [B, H, W, C] (channel 0 used); valid_hw: the (rows, columns) of every tile the
+        crop may touch - DL:64 cuts the 23-row Bing banner off the bottom of the decoded PNG, here the raw decode is passed and
+        valid_hw = (H - 23, W) keeps the crop out of it without a copy.
         Returns (images f32 [B, 3, OH, OW], masks f32 [B, OH, OW] | None)."""
         with ops.device_of(tiles_u8):
             if tiles_u8.dtype != torch.uint8 or tiles_u8.dim() != 4 or tiles_u8.shape[3] < 3:
                 raise ValueError("tiles must be uint8 [B, H, W, C>=3]")
             tiles_u8 = ops._chk(tiles_u8, torch.uint8, "tiles")
             B, H, W, C = tiles_u8.shape
-            params = ops._chk(params.to(tiles_u8.device), torch.int32, "augmentation parameters")
-            if params.shape != (B, 4):
+            if params.shape != (B, 4) or params.dtype != torch.int32:
                 raise ValueError("params must be int32 [B, 4]")
+            host_params = params
+            params = ops._chk(params.to(tiles_u8.device, non_blocking=True), torch.int32, "augmentation parameters")
             OH, OW = self.out_hw
             out = torch.empty(B, 3, OH, OW, device=tiles_u8.device, dtype=torch.float32)
             mask_out = minmax = None
@@ -62,6 +65,13 @@ class TileAugmenter:
                 mask_out = torch.empty(B, OH, OW, device=tiles_u8.device, dtype=torch.float32)
                 minmax = torch.empty(B, 2, device=tiles_u8.device, dtype=torch.int32)
                 m_args = (masks_u8.data_ptr(), H * W * mc, W * mc, mc)
-            ops.call("sfk_tile_augment_u8", tiles_u8.data_ptr(), H * W * C, W * C, C, H, W, params.data_ptr(), self.crop, out.data_ptr(),
+            vh, vw = (H, W) if valid_hw is None else (int(valid_hw[0]), int(valid_hw[1]))
+            if vh > H or vw > W:
+                raise ValueError("valid_hw exceeds the tile")
+            lim = torch.tensor([vh - self.crop, vw - self.crop], dtype=torch.int32)
+            pc = host_params.cpu() if host_params.is_cuda else host_params
+            if bool((pc[:, :2] < 0).any()) or bool((pc[:, :2] > lim).any()) or bool((pc[:, 2] < 0).any()) or bool((pc[:, 2] > 6).any()):
+                raise ValueError("augmentation parameters out of range for this tile size")
+            ops.call("sfk_tile_augment_u8", tiles_u8.data_ptr(), H * W * C, W * C, C, vh, vw, params.data_ptr(), self.crop, out.data_ptr(),
                      B, OH, OW, m_args[0], m_args[1], m_args[2], m_args[3], ops._p(mask_out), ops._p(minmax), ops.stream())
             return out, mask_out
