@@ -42,6 +42,14 @@ __device__ __forceinline__ void red_add_v4_f32_g(float* addr, float a, float b, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// 2^x on the MUFU pipe in one instruction (ex2.approx.ftz: 2 ulp, flushes denormals - the softmax numerators it produces are
+// rounded to bf16 anyway).  exp2f() compiled to ~8 instructions per element here (range scaling for denormal results).
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // write 8 bf16 (one 16-byte chunk) of row r / column chunk j (8 columns each) into a [128 x 64] SWIZZLE_128B tile
 __device__ __forceinline__ void st_swizzled_chunk(uint8_t* tile, int r, int j, uint4 v) {
   *reinterpret_cast<uint4*>(tile + r * 128 + ((j ^ (r & 7)) << 4)) = v;
@@ -138,30 +146,46 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const int valid = min(ATT_BN, p.Tk - c * ATT_BN);
       mbar_wait(b_sfull, ph);
       tc_fence_after();
+      const bool full = valid == ATT_BN;   // only the last chunk of a ragged K/V length needs column masking
       float cmax = -INFINITY;
 #pragma unroll
       for (int cc = 0; cc < ATT_BN; cc += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tS + lane_base + cc, v);
         tmem_ld_wait();
+        if (full) {
+          float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains instead of one of 32
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (cc + j < valid) cmax = fmaxf(cmax, __uint_as_float(v[j]));
+          for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
+          cmax = fmaxf(cmax, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (cc + j < valid) cmax = fmaxf(cmax, __uint_as_float(v[j]));
+        }
       }
       const float m_new = fmaxf(m_run, cmax);
-      const float alpha = exp2f((m_run - m_new) * p.scale_log2);
+      const float alpha = fast_exp2((m_run - m_new) * p.scale_log2);
       const float moff = m_new * p.scale_log2;
-      float sum = 0.f;
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int cc = 0; cc < ATT_BN; cc += 32) {
         uint32_t v[32];
         tmem_ld_32x32(tS + lane_base + cc, v);
         tmem_ld_wait();
         float e[32];
+        if (full) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          e[j] = (cc + j < valid) ? exp2f(fmaf(__uint_as_float(v[j]), p.scale_log2, -moff)) : 0.f;
-          sum += e[j];
+          for (int j = 0; j < 32; ++j) {
+            e[j] = fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -moff));
+            s4[j & 3] += e[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            e[j] = (cc + j < valid) ? fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -moff)) : 0.f;
+            s4[j & 3] += e[j];
+          }
         }
         uint8_t* tile = sP_gen + (cc >> 6) * 16384;
 #pragma unroll
@@ -174,6 +198,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
           st_swizzled_chunk(tile, r, ((cc & 63) >> 3) + j8, o);
         }
       }
+      const float sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
       l_run = l_run * alpha + sum;
       m_run = m_new;
       fence_proxy_async_smem();
@@ -462,7 +487,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         for (int j = 0; j < 32; ++j) {
           const float l2 = stats[buf * 256 + cc + j];
           const float dl = stats[buf * 256 + 128 + cc + j];
-          const float pr = kv_ok ? exp2f(fmaf(__uint_as_float(s[j]), p.scale_log2, -l2)) : 0.f;
+          const float pr = kv_ok ? fast_exp2(fmaf(__uint_as_float(s[j]), p.scale_log2, -l2)) : 0.f;
           pv[j] = pr;
           dsv[j] = pr * (__uint_as_float(dp[j]) - dl) * p.scale;
         }
@@ -728,7 +753,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         for (int j = 0; j < 32; ++j) {
           const float l2 = stats[buf * 256 + cc + j];
           const float dl = stats[buf * 256 + 128 + cc + j];
-          const float pr = kv_ok ? exp2f(fmaf(__uint_as_float(s[j]), p.scale_log2, -l2)) : 0.f;
+          const float pr = kv_ok ? fast_exp2(fmaf(__uint_as_float(s[j]), p.scale_log2, -l2)) : 0.f;
           pv[j] = pr;
           dsv[j] = pr * (__uint_as_float(dp[j]) - dl) * p.scale;
         }
