@@ -1,7 +1,7 @@
 // Low-contention column reductions for kernels whose blocks each hold per-column partial sums (bias / LayerNorm-affine /
 // depthwise-weight gradients).  Plain atomicAdd of every block into one destination serialises ~40 ns per same-address
 // atomic at the L2 (measured: 1171 blocks -> 48 us).  Instead:
-//   1. every block adds its partials into one of NS slot copies   g_slots[slot][v]   (contention / NS),
+//   1. every block adds its partials into one of NS (<= 8) slot copies   g_slots[slot][v]   (contention / NS),
 //   2. the last block to finish (ticket counter per blockIdx.x) sums the NS copies, adds them into the real destinations
 //      with plain read-modify-write, and zeroes the slots + ticket again (self-cleaning static device memory).
 // Invariant the host code keeps: kernels that use the slot area (LayerNorm / depthwise / cast-and-sum BACKWARD kernels and
@@ -23,7 +23,10 @@ static __device__ unsigned int g_colsum_ticket[COLSUM_MAX_GX];
 // host helper: number of slot copies for V virtual columns and `sharers` blocks per column
 inline int colsum_num_slots(long long V, long long sharers) {
   long long ns = COLSUM_SLOT_FLOATS / (V > 0 ? V : 1);
-  if (ns > 64) ns = 64;
+  // 8 copies: ~300-600 blocks per launch leave 40-75 same-address atomics per slot word (spread over the kernel's duration),
+  // while the last block's fold - L2 round trips at the very end of the kernel, nothing left to overlap them - shrinks 8x
+  // against the first version's 64 (measured: stage-3 layer backward 552 -> 500 us, eight slot-using kernels per layer)
+  if (ns > 8) ns = 8;
   if (ns > sharers) ns = sharers;
   if (ns < 1) ns = 1;
   return (int)ns;
@@ -48,13 +51,16 @@ __device__ __forceinline__ void colsum_commit(const float* sh, int v0, int nv, i
   if (!s_last) return;
   __threadfence();
   for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-    float t = 0.f;
-    for (int s = 0; s < ns; ++s) {
-      float* p = g_colsum_slots + (size_t)s * V + v0 + i;
-      t += __ldcg(p);
-      __stcg(p, 0.f);
+    float* p = g_colsum_slots + v0 + i;
+    float part[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains: the loads of a column are all in flight together
+    int s = 0;
+    for (; s + 4 <= ns; s += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) part[u] += __ldcg(p + (size_t)(s + u) * V);
     }
-    write(v0 + i, t);
+    for (; s < ns; ++s) part[0] += __ldcg(p + (size_t)s * V);
+    for (s = 0; s < ns; ++s) __stcg(p + (size_t)s * V, 0.f);
+    write(v0 + i, (part[0] + part[1]) + (part[2] + part[3]));
   }
   if (threadIdx.x == 0) g_colsum_ticket[ticket] = 0u;
 }

@@ -87,6 +87,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--stages", default="1,2,3,4")
     ap.add_argument("--ptl", type=int, default=0)
+    ap.add_argument("--plain", action="store_true", help="no graphs: one forward and three backward calls (for an ncu launch list)")
     args = ap.parse_args()
     L.ensure_device()
     lib = L.load()
@@ -124,6 +125,12 @@ def main():
                                       ops._p(dfront_out), dx.data_ptr(), ops._p(dfront), saved.data_ptr(), sb, scratch.data_ptr(),
                                       scratch.numel(), L.stream_ptr(), None, 0), "layer_bwd")
 
+        if args.plain:
+            fwd()
+            for _ in range(3):
+                bwd()
+            torch.cuda.synchronize()
+            continue
         tf = time_graph(fwd)
         tb = time_graph(bwd)
         est = depth * (2 * tf + tb)
