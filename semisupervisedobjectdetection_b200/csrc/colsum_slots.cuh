@@ -69,7 +69,7 @@ __device__ __forceinline__ void colsum_commit(const float* sh, int v0, int nv, i
 // virtual column v = k * C + channel  (k-th output array)
 template <int VEC, int NV>
 __device__ __forceinline__ void dw_block_commit(float (&acc)[NV][VEC], float* sh, float* out_base, long long out_stride,
-                                                float* out_last, int c0, int C, bool lane_ok, int ns) {
+                                                float* out_last, int c0, int C, bool lane_ok, int ns, int out_cstride = 1) {
   const int lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < NV * 32 * VEC; i += 256) sh[i] = 0.f;
   __syncthreads();
@@ -90,8 +90,10 @@ __device__ __forceinline__ void dw_block_commit(float (&acc)[NV][VEC], float* sh
     const int local = v - v0;
     const int k = local / (32 * VEC), j = local % (32 * VEC);
     if (j < ncol) {
-      float* dst = (k == NV - 1) ? out_last : out_base + (long long)k * out_stride;
-      dst[cbase + j] += sum;
+      // arrays 0..NV-2: element (k, channel) at out_base[k * out_stride + channel * out_cstride] (tap-major [9][C] with
+      // (C, 1), the parameter's own [C, 1, 3, 3] layout with (1, 9)); the last array is a plain [C] vector
+      if (k == NV - 1) out_last[cbase + j] += sum;
+      else out_base[(long long)k * out_stride + (long long)(cbase + j) * out_cstride] += sum;
     }
   });
 }

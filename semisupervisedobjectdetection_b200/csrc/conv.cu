@@ -271,7 +271,7 @@ template <int VEC>
 __global__ void __launch_bounds__(256, VEC == 2 ? 2 : 1)
 dwconv3x3_gelu_bwd_roll_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ wt, const float* __restrict__ bias,
                                const __nv_bfloat16* __restrict__ dg, __nv_bfloat16* __restrict__ dpre, float* __restrict__ dwt,
-                               float* __restrict__ dbias, int B, int H, int W, int C, int ns) {
+                               float* __restrict__ dbias, int B, int H, int W, int C, int ns, int dw_kstride, int dw_cstride) {
   pdl_sync();
   constexpr int SEG = DWR_SEG, NP = VEC / 2;
   typedef DwrVec<VEC> V;
@@ -411,15 +411,17 @@ dwconv3x3_gelu_bwd_roll_kernel(const __nv_bfloat16* __restrict__ x, const float*
   }
   if (dwt != nullptr) {
     __syncthreads();  // everyone is done with the filter taps in sh
-    dw_block_commit<VEC, 10>(acc, sh, dwt, (long long)C, dbias, c0, C, lane_ok, ns);
+    dw_block_commit<VEC, 10>(acc, sh, dwt, (long long)dw_kstride, dbias, c0, C, lane_ok, ns, dw_cstride);
   }
 }
 
 static int g_dw_bwd_vec = 4;  // measured on B200 (tools/check_ops.py dw_perf): 4 is 5-25% faster than 2 on the MiT-b5 shapes
 void set_dw_bwd_vec(int v) { g_dw_bwd_vec = (v == 2) ? 2 : 4; }
 
+// dw_oihw == 0: dwt is a tap-major [9][C] accumulator (public ABI); 1: dwt is the parameter gradient itself, [C, 1, 3, 3]
 int dwconv3x3_gelu_bwd(const void* x, const float* wt, const float* bias, const void* dg, void* dpre, float* dwt,
-                       float* dbias, int B, int H, int W, int C, cudaStream_t stream) {
+                       float* dbias, int B, int H, int W, int C, cudaStream_t stream, int dw_oihw) {
+  const int dw_kstride = dw_oihw ? 1 : C, dw_cstride = dw_oihw ? 9 : 1;
   SFK_REQUIRE(C % 8 == 0, "dwconv3x3_gelu_bwd: C=%d must be a multiple of 8", C);
   SFK_REQUIRE((dwt == nullptr) == (dbias == nullptr), "dwconv3x3_gelu_bwd: pass both or neither of dwt / dbias");
   SFK_REQUIRE((long long)B * H * W * C < (1LL << 31), "dwconv3x3_gelu_bwd: tensor too large for 32-bit offsets");
@@ -428,12 +430,12 @@ int dwconv3x3_gelu_bwd(const void* x, const float* wt, const float* bias, const 
     const dim3 grid = dwr_grid(B, H, W, C, 4, 1);
     launch_k(dwconv3x3_gelu_bwd_roll_kernel<4>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, bias,
              (const __nv_bfloat16*)dg, (__nv_bfloat16*)dpre, dwt, dbias, B, H, W, C,
-             colsum_num_slots((long long)grid.x * 10 * 32 * 4, grid.y));
+             colsum_num_slots((long long)grid.x * 10 * 32 * 4, grid.y), dw_kstride, dw_cstride);
   } else {
     const dim3 grid = dwr_grid(B, H, W, C, 2, 2);
     launch_k(dwconv3x3_gelu_bwd_roll_kernel<2>, dim3(grid), dim3(256), 0, stream, (const __nv_bfloat16*)x, wt, bias,
              (const __nv_bfloat16*)dg, (__nv_bfloat16*)dpre, dwt, dbias, B, H, W, C,
-             colsum_num_slots((long long)grid.x * 10 * 32 * 2, grid.y));
+             colsum_num_slots((long long)grid.x * 10 * 32 * 2, grid.y), dw_kstride, dw_cstride);
   }
   return check_launch("dwconv3x3_gelu_bwd_roll_kernel");
 }

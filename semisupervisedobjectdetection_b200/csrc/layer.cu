@@ -331,7 +331,6 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
   float* delta = sc.take<float>(d.B * d.heads * d.T);
   float* dxn1 = sc.take<float>(rows_all * C);
   __nv_bfloat16* dxn1t = sc.take<__nv_bfloat16>(rows_all * C);
-  float* dw_stage = sc.take<float>(10 * Hd);
   SFK_REQUIRE(sc.off <= scratch_bytes, "layer_backward: scratch arena too small (%zu < %zu)", scratch_bytes, sc.off);
 
   // ---- MixFFN branch ----
@@ -340,15 +339,11 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
   TRY(gemm_bf16(linear_dgrad(dmlp, C, p.w2, Hd, rows_sp, C, Hd, dg, Hd, 1), st));
   if (gr.dw2) TRY(gemm_bf16(linear_wgrad(dmlp, C, s.g, Hd, rows_sp, C, Hd, gr.dw2, Hd), side_fork(st, side)));
   {
+    // depthwise weight / bias gradients accumulate straight into the parameter gradients ([4C, 1, 3, 3] layout and [4C]):
+    // no tap-major staging buffer, memset or layout pass
     const bool want = gr.ddw != nullptr;
-    if (want) {
-      cudaError_t e = cudaMemsetAsync(dw_stage, 0, (size_t)9 * Hd * sizeof(float), st);
-      SFK_REQUIRE(e == cudaSuccess, "layer_backward: memset failed");
-    }
-    // depthwise bias gradient accumulates straight into the parameter gradient; the weight goes through a tap-major stage
-    TRY(dwconv3x3_gelu_bwd(s.h1, p.dw_wt, p.dw_b, dg, dpre, want ? dw_stage : nullptr, want ? gr.ddb : nullptr, (int)d.B,
-                           (int)d.H, (int)d.W, (int)Hd, st));
-    if (want) TRY(dw_wgrad_from_tap(dw_stage, gr.ddw, (int)Hd, st));
+    TRY(dwconv3x3_gelu_bwd(s.h1, p.dw_wt, p.dw_b, dg, dpre, want ? gr.ddw : nullptr, want ? gr.ddb : nullptr, (int)d.B,
+                           (int)d.H, (int)d.W, (int)Hd, st, 1));
   }
   // input gradient of the depthwise conv; the dense1 bias gradient (column sums of dh1) is produced by the same pass
   TRY(dwconv3x3(dpre, p.dw_wt, nullptr, dh1, gr.db1, (int)d.B, (int)d.H, (int)d.W, (int)Hd, 1, st));
@@ -404,8 +399,13 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
   // K | V projections
   if (gr.dwk || gr.dwv) {
     cudaStream_t ws = side_fork(st, side);
-    if (gr.dwk) TRY(gemm_bf16(linear_wgrad(dkv16, 2 * C, s.kvn, C, rows_kv, C, C, gr.dwk, C), ws));
-    if (gr.dwv) TRY(gemm_bf16(linear_wgrad(dkv16 + C, 2 * C, s.kvn, C, rows_kv, C, C, gr.dwv, C), ws));
+    if (gr.dwk && gr.dwv == gr.dwk + C * C) {
+      // key.weight / value.weight gradients adjacent in the flat gradient buffer (FusedClipAdam's layout): one [2C, C] wgrad
+      TRY(gemm_bf16(linear_wgrad(dkv16, 2 * C, s.kvn, C, rows_kv, 2 * C, C, gr.dwk, C), ws));
+    } else {
+      if (gr.dwk) TRY(gemm_bf16(linear_wgrad(dkv16, 2 * C, s.kvn, C, rows_kv, C, C, gr.dwk, C), ws));
+      if (gr.dwv) TRY(gemm_bf16(linear_wgrad(dkv16 + C, 2 * C, s.kvn, C, rows_kv, C, C, gr.dwv, C), ws));
+    }
   }
   if ((gr.dbk == nullptr) != (gr.dbv == nullptr)) {  // only one of the two biases trainable: separate column sums
     if (gr.dbk) TRY(colsum(dkv16, 1, 2 * C, gr.dbk, rows_kv, (int)C, st));
@@ -421,8 +421,15 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
     float* dwsr = sc.take<float>(C * Ksr);
     SFK_REQUIRE(sc.off <= scratch_bytes, "layer_backward: scratch arena too small (%zu < %zu)", scratch_bytes, sc.off);
     TRY(gemm_bf16(linear_dgrad(dkv16, 2 * C, p.wkv, C, rows_kv, 2 * C, C, dkvn, C, 1), st));
-    TRY(layernorm_bwd(dkvn, 1, s.sr_out, 0, id, s.mean_sr, s.rstd_sr, p.lnsr_g, nullptr, id, dsr, 1, id, gr.dlnsr_g, gr.dlnsr_b,
-                      rows_kv, (int)C, st));
+    // without prompt rows the LayerNorm's input gradient IS the SR conv's output gradient: its column sums (the conv's bias
+    // gradient) come out of the same pass
+    const bool fuse_dbsr = d.P == 0 && gr.dbsr != nullptr && gr.dlnsr_g != nullptr;
+    if (fuse_dbsr) {
+      TRY(layernorm_bwd_colsum(dkvn, s.sr_out, s.mean_sr, s.rstd_sr, p.lnsr_g, dsr, 1, gr.dlnsr_g, gr.dlnsr_b, rows_kv, (int)C, gr.dbsr, st));
+    } else {
+      TRY(layernorm_bwd(dkvn, 1, s.sr_out, 0, id, s.mean_sr, s.rstd_sr, p.lnsr_g, nullptr, id, dsr, 1, id, gr.dlnsr_g, gr.dlnsr_b,
+                        rows_kv, (int)C, st));
+    }
     const __nv_bfloat16* dsr_sp = dsr;
     if (d.P > 0) {
       TRY(scale_cast(dsr, 1, kv_spatial_map(d), dsr_c, 1, id, nullptr, 1, rows_red, (int)C, st));
@@ -447,7 +454,7 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
       }
       TRY(conv_wgrad_ohwi_to_oihw(dwsr, gr.dwsr, (int)C, (int)C, (int)d.sr, (int)d.sr, Ksr, ws));
     }
-    if (gr.dbsr) TRY(colsum(dsr_sp, 1, C, gr.dbsr, rows_red, (int)C, st));
+    if (gr.dbsr && !fuse_dbsr) TRY(colsum(dsr_sp, 1, C, gr.dbsr, rows_red, (int)C, st));
   } else {
     TRY(gemm_bf16(linear_dgrad(dkv16, 2 * C, p.wkv, C, rows_kv, 2 * C, C, dxn1, C, 0), st));
   }

@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_ring_kernel(const __nv_bfloat16
         Ld4<TDx>::st(dxr + ci * 4, o);
         if (AUX) {
           o.x *= asc; o.y *= asc; o.z *= asc; o.w *= asc;
-          Ld4<__nv_bfloat16>::st(aux + (size_t)row * C + ci * 4, o);
+          if (aux != nullptr) Ld4<__nv_bfloat16>::st(aux + (size_t)row * C + ci * 4, o);
           cacc[k].x += o.x; cacc[k].y += o.y; cacc[k].z += o.z; cacc[k].w += o.w;
         }
       }
@@ -456,7 +456,8 @@ static int ln_bwd_ring_launch(const void* dy, const void* x, const float* mean, 
   size_t smem = (size_t)8 * (NCH <= 3 ? 3 : 2) * NCH * 1280;
   const size_t red_bytes = (size_t)9 * 2 * C * sizeof(float);
   if (smem < red_bytes) smem = red_bytes;
-  const int ns = colsum_num_slots((aux != nullptr ? 3 : 2) * C, grid);
+  const bool want_aux = aux != nullptr || aux_colsum != nullptr;
+  const int ns = colsum_num_slots((want_aux ? 3 : 2) * C, grid);
 #define LAUNCH_RING(AUXF, RESF)                                                                                               \
   do {                                                                                                                         \
     cudaFuncSetAttribute(ln_bwd_ring_kernel<TDx, NCH, AUXF, RESF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
@@ -464,7 +465,7 @@ static int ln_bwd_ring_launch(const void* dy, const void* x, const float* mean, 
              (const float*)x, mean, rstd, gamma, dres, (TDx*)dx, dgamma, dbeta, (unsigned)rows, (unsigned)C,                   \
              (unsigned)rows_per_block, ns, (__nv_bfloat16*)aux, aux_scale, (unsigned)(aux_rps > 0 ? aux_rps : 1), aux_colsum); \
   } while (0)
-  if (aux != nullptr) { if (dres) LAUNCH_RING(true, true); else LAUNCH_RING(true, false); }
+  if (want_aux) { if (dres) LAUNCH_RING(true, true); else LAUNCH_RING(true, false); }
   else { if (dres) LAUNCH_RING(false, true); else LAUNCH_RING(false, false); }
 #undef LAUNCH_RING
   return check_launch("ln_bwd_ring_kernel");
@@ -476,8 +477,11 @@ static int layernorm_bwd_impl(const void* dy, int dy_bf16, const void* x, int x_
                               int aux_rps, float* aux_colsum, cudaStream_t stream) {
   SFK_REQUIRE(C % 4 == 0 && C <= 4 * 32 * LN_CHUNK_LIMIT, "layernorm_bwd: C=%d unsupported", C);
   if (rows == 0) return 0;
-  if (g_ln_bwd_ring && dy_bf16 && !x_bf16 && map_is_identity(x_map) && map_is_identity(dres_map) && map_is_identity(dx_map) &&
-      C <= 512 && rows * (long long)C < (1LL << 31) && rows >= 256 && (aux == nullptr || (!dx_bf16 && dgamma != nullptr))) {
+  const bool ring_ok = g_ln_bwd_ring && dy_bf16 && !x_bf16 && map_is_identity(x_map) && map_is_identity(dres_map) &&
+                       map_is_identity(dx_map) && C <= 512 && rows * (long long)C < (1LL << 31) && rows >= 256;
+  SFK_REQUIRE(aux != nullptr || aux_colsum == nullptr || (ring_ok && dgamma != nullptr),
+              "layernorm_bwd: column sums of dx without the bf16 copy need the ring kernel (ask layernorm_bwd_colsum)");
+  if (ring_ok && (aux == nullptr || (!dx_bf16 && dgamma != nullptr))) {
 #define RING_N(NCH)                                                                                                           \
   (dx_bf16 ? ln_bwd_ring_launch<__nv_bfloat16, NCH>(dy, x, mean, rstd, gamma, dres, dx, dgamma, dbeta, rows, C, aux, aux_scale, \
                                                     aux_rps, aux_colsum, stream)                                                \
@@ -546,6 +550,21 @@ int layernorm_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, RowMap
 }
 
 // same, also writing aux = bf16(dx * aux_scale[row / aux_rps]) [rows, C] (identity row map) and aux_colsum += column sums
+// LayerNorm backward (bf16 dy, fp32 x) whose dx column sums are wanted as well (a bias gradient upstream): fused into the ring
+// kernel when it applies, else the plain backward followed by the column-sum kernel.
+int layernorm_bwd_colsum(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+                         int dx_bf16, float* dgamma, float* dbeta, long long rows, int C, float* dx_colsum, cudaStream_t stream) {
+  RowMap id;
+  const bool fuse = g_ln_bwd_ring && C <= 512 && rows * (long long)C < (1LL << 31) && rows >= 256 && dgamma != nullptr && dx_colsum != nullptr;
+  if (fuse)
+    return layernorm_bwd_impl(dy, 1, x, 0, id, mean, rstd, gamma, nullptr, id, dx, dx_bf16, id, dgamma, dbeta, rows, C, nullptr, nullptr, 1,
+                              dx_colsum, stream);
+  int rc = layernorm_bwd_impl(dy, 1, x, 0, id, mean, rstd, gamma, nullptr, id, dx, dx_bf16, id, dgamma, dbeta, rows, C, nullptr, nullptr, 1,
+                              nullptr, stream);
+  if (rc || dx_colsum == nullptr) return rc;
+  return colsum(dx, dx_bf16, C, dx_colsum, rows, C, stream);
+}
+
 int layernorm_bwd_aux(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, const float* dres,
                       void* dx, float* dgamma, float* dbeta, long long rows, int C, void* aux, const float* aux_scale, int aux_rps,
                       float* aux_colsum, cudaStream_t stream) {

@@ -90,6 +90,8 @@ int layernorm_fwd(const void* x, int x_bf16, RowMap in_map, const float* gamma, 
 int layernorm_bwd_aux(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, const float* dres,
                       void* dx, float* dgamma, float* dbeta, long long rows, int C, void* aux, const float* aux_scale, int aux_rps,
                       float* aux_colsum, cudaStream_t stream);
+int layernorm_bwd_colsum(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma, void* dx,
+                         int dx_bf16, float* dgamma, float* dbeta, long long rows, int C, float* dx_colsum, cudaStream_t stream);
 int layernorm_bwd(const void* dy, int dy_bf16, const void* x, int x_bf16, RowMap x_map, const float* mean,
                   const float* rstd, const float* gamma, const float* dres, RowMap dres_map, void* dx, int dx_bf16,
                   RowMap dx_map, float* dgamma, float* dbeta, long long rows, int C, cudaStream_t stream);
@@ -106,7 +108,7 @@ int front_grad_sum(const float* g, float* dfront, int B, int P, int T, int C, cu
 int dwconv3x3(const void* x, const float* wt, const float* bias, void* y, float* colsum, int B, int H, int W, int C, int mode,
               cudaStream_t stream);
 int dwconv3x3_gelu_bwd(const void* x, const float* wt, const float* bias, const void* dg, void* dpre, float* dwt,
-                       float* dbias, int B, int H, int W, int C, cudaStream_t stream);
+                       float* dbias, int B, int H, int W, int C, cudaStream_t stream, int dw_oihw = 0);
 int im2col_nhwc(const void* x, void* A, int B, int H, int W, int C, int K, int S, int P, long long tok_stride,
                 long long tok_offset, cudaStream_t stream);
 int im2col_nchw_f32(const float* x, void* A, int B, int Cin, int H, int W, int K, int S, int P, int Kp, cudaStream_t stream);
