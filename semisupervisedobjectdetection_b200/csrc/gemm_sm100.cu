@@ -781,7 +781,11 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
   // B-stationary main loop: small K, no split-K, plain operands
   p.bstat = 0;
   int bstat_bn = 0, bstat_stages = 0;
-  if (g_gemm_bstat && !p.cluster2 && !a_patch && !b_patch && (!g.atomic_add || g.splits == 1) && g.splits <= 1 && p.k_blocks <= 8) {
+  // (measured per MiT-b5 shape, profiles/r2: with K <= 128 the resident tile is small and the A ring deep - the loop wins by
+  // 3-10 %; from K = 320 on the up-front tile load and the one-tile-deep ring lose 5-30 % against streaming wide tiles, so
+  // automatic selection stops at two k-blocks; an explicit block_n still selects it up to K = 512)
+  if (g_gemm_bstat && !p.cluster2 && !a_patch && !b_patch && (!g.atomic_add || g.splits == 1) && g.splits <= 1 &&
+      p.k_blocks <= (g.block_n > 0 ? 8 : 2)) {
     const int fixed = (int)(stage_bytes_epi + bars_bytes + 1024u);
     if (g.block_n > 0) {
       const long long b_bytes = (long long)g.block_n * p.k_blocks * 128;

@@ -168,7 +168,7 @@ def test_gemm_plan_invariants_over_the_mit_shapes():
             assert p["grid"] % 2 == 0 and (not b_mn or p["block_n"] % 128 == 0) and not p["epi_tma"], (M, N, K, p)
         else:
             assert p["epi_tma"], (M, N, K, p)
-        if kb <= 8 and not atomic:
+        if kb <= 2 and not atomic:
             assert p["bstat"] and p["stages"] >= 3, (M, N, K, p)
             # resident weight tile + A ring + 32 KB of epilogue staging fit
             assert p["block_n"] * kb * 128 + p["stages"] * 16384 + 32768 <= p["smem"], (M, N, K, p)
@@ -194,10 +194,12 @@ def test_gemm_plan_modes():
     a tile width that covers N without padding where one exists), explicit requests honoured."""
     big = _plan(262144, 768, 3072)
     assert big["pair"] == 1 and big["block_n"] == 256 and big["tmem_cols"] == 512 and not big["bstat"], big
-    small_k = _plan(16384, 320, 320)
-    assert small_k["pair"] == 0 and small_k["bstat"] == 1 and small_k["block_n"] == 160 and small_k["epi_tma"] == 1, small_k
-    ffn1 = _plan(16384, 1280, 320)
-    assert ffn1["bstat"] == 1 and 1280 % ffn1["block_n"] == 0, ffn1
+    small_k = _plan(262144, 256, 64)
+    assert small_k["pair"] == 0 and small_k["bstat"] == 1 and 256 % small_k["block_n"] == 0 and small_k["epi_tma"] == 1, small_k
+    mid_k = _plan(16384, 1280, 320)
+    assert mid_k["bstat"] == 0 and mid_k["epi_tma"] == 1, mid_k
+    forced_ws = _plan(16384, 320, 320, block_n=160)
+    assert forced_ws["bstat"] == 1 and forced_ws["block_n"] == 160 and forced_ws["stages"] >= 3, forced_ws
     long_k = _plan(16384, 320, 1280)
     assert long_k["pair"] == 0 and long_k["bstat"] == 0 and long_k["epi_tma"] == 1, long_k
     forced = _plan(4096, 256, 256, block_n=64, splits=0)
