@@ -54,6 +54,7 @@ def scratch(nbytes: int, device: torch.device, slot: str = "main") -> torch.Tens
 
 # ---- second stream for weight-gradient GEMMs (off the critical path of backward, see csrc/layer.cu) ----
 WGRAD_OVERLAP = True
+SIDE_STREAM_PRIORITY = 0   # 0 = default; -1 = high (experiment switch, see tools/ab_step.py)
 _wgrad_streams: dict = {}
 _bwd_parity = 0
 
@@ -65,7 +66,7 @@ def wgrad_stream(device=None):
     idx = torch.cuda.current_device() if device is None or device.index is None else device.index
     st = _wgrad_streams.get(idx)
     if st is None:
-        st = torch.cuda.Stream(device=idx)
+        st = torch.cuda.Stream(device=idx, priority=SIDE_STREAM_PRIORITY)
         _wgrad_streams[idx] = st
     return st
 
