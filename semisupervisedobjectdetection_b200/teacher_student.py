@@ -176,3 +176,80 @@ def _ema_teacher_student_step(teacher, student, img_labeled, ground_truth, img_u
     student.optimizer.step()
     ema_update(teacher.optimizer, student.optimizer, ema_decay)
     return loss
+
+
+class PipelinedEmaLoop:
+    """Training loop driver around ema_teacher_student_step for batches that live in (pinned) host memory.
+
+    The reference's loop (TS:80-127, 230-260) does `.to(device)` and reads losses with `.item()` inline, which serialises the
+    host-to-device copy, the step and the read-back.  Here batch i+1 is copied on a copy stream while step i computes, and the
+    loss of step i is read from a pinned buffer after step i+1 has been enqueued, so neither the copy nor the read-back stalls
+    the GPU.  Every batch is still copied from host memory and every loss still comes back to the host - one step later.
+
+        loop = PipelinedEmaLoop(teacher, student)
+        for loss in loop.run(batches):      # batches: iterable of (img_labeled, ground_truth, img_unlabeled) host tensors
+            ...                              # python floats, in batch order
+    """
+
+    def __init__(self, teacher, student, supervise_weight: float = 0.8, ema_decay: float = 0.99, grad_sync=None,
+                 overlap_teacher: bool = True, before_step=None):
+        self.teacher, self.student = teacher, student
+        self.kw = dict(supervise_weight=supervise_weight, ema_decay=ema_decay, grad_sync=grad_sync, overlap_teacher=overlap_teacher)
+        self.before_step = before_step
+        self.dev = torch.device(student.device)
+        self._copy = torch.cuda.Stream(device=self.dev)
+        self._loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+        self._events = [torch.cuda.Event(), torch.cuda.Event()]
+        self._bufs = [None, None]      # double-buffered device copies of a batch
+        self._used = [None, None]      # event recorded on the compute stream after the step that read slot k
+
+    def _upload(self, batch, slot):
+        """Enqueue the host-to-device copies of one batch on the copy stream into the double-buffered device inputs of `slot`
+        (no allocation in steady state); returns (device tensors, ready event)."""
+        bufs = self._bufs[slot]
+        if bufs is None or any(b.shape != t.shape or b.dtype != t.dtype for b, t in zip(bufs, batch)):
+            bufs = tuple(torch.empty(t.shape, dtype=t.dtype, device=self.dev) for t in batch)
+            self._bufs[slot] = bufs
+        if self._used[slot] is not None:
+            self._copy.wait_event(self._used[slot])   # the step that last read these buffers must be done with them
+        with torch.cuda.stream(self._copy):
+            for b, t in zip(bufs, batch):
+                b.copy_(t, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy)
+        return bufs, ev
+
+    def run(self, batches):
+        with ops.device_of(self.dev):
+            it = iter(batches)
+            try:
+                nxt = self._upload(next(it), 0)
+            except StopIteration:
+                return
+            pending = None   # (slot, event) of the loss not yet handed to the caller
+            i = 0
+            main = torch.cuda.current_stream()
+            while nxt is not None:
+                (img_l, gt, img_u), ready = nxt
+                try:
+                    nxt = self._upload(next(it), (i + 1) & 1)       # overlaps with the step enqueued below
+                except StopIteration:
+                    nxt = None
+                main.wait_event(ready)
+                if self.before_step is not None:
+                    self.before_step()
+                loss = ema_teacher_student_step(self.teacher, self.student, img_l, gt, img_u, **self.kw)
+                slot = i & 1
+                self._loss_host[slot:slot + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+                self._events[slot].record(main)
+                self._used[slot] = self._events[slot]
+                if pending is not None:
+                    pslot, pev = pending
+                    pev.synchronize()
+                    yield float(self._loss_host[pslot])
+                pending = (slot, self._events[slot])
+                i += 1
+            if pending is not None:
+                pslot, pev = pending
+                pev.synchronize()
+                yield float(self._loss_host[pslot])

@@ -158,3 +158,38 @@ def test_raw_ops_reject_tensors_of_another_device():
     x = torch.randn(64, 32, device="cuda:1")
     with pytest.raises(_lib.SfkError):
         ops.layernorm_fwd(ops._chk(x, torch.float32, "x"), torch.ones(32, device="cuda:1"), torch.zeros(32, device="cuda:1"))
+
+
+def test_pipelined_loop_matches_the_sequential_steps():
+    """PipelinedEmaLoop (uploads on a copy stream, losses read one step late) gives the same losses and weights as calling
+    ema_teacher_student_step on device tensors one batch at a time (eval-mode statistics: no RNG in the step)."""
+    from semisupervisedobjectdetection_b200 import teacher_student as TS
+    from tests.test_gpu_model import _b0_wrapper
+
+    def make_pair():
+        s, _, _ = _b0_wrapper(lr=1e-3)
+        t, _, _ = _b0_wrapper(lr=1e-3)
+        for p in t.model.parameters():
+            p.requires_grad_(False)
+        s.model.eval(), t.model.eval()
+        return t, s
+
+    batches = []
+    for i in range(4):
+        batches.append((synth.uniform01(f"pipe{i}/l", (2, 3, 64, 64)).pin_memory(),
+                        (synth.uniform01(f"pipe{i}/gt", (2, 64, 64)) > 0.7).float().pin_memory(),
+                        synth.uniform01(f"pipe{i}/u", (2, 3, 64, 64)).pin_memory()))
+    t1, s1 = make_pair()
+    seq = [float(TS.ema_teacher_student_step(t1, s1, b[0].cuda(), b[1].cuda(), b[2].cuda())) for b in batches]
+    t2, s2 = make_pair()
+    loop = TS.PipelinedEmaLoop(t2, s2)
+    piped = list(loop.run(batches))
+    assert len(piped) == len(seq)
+    for a, b in zip(seq, piped):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(a)), (seq, piped)
+    # split-K weight gradients are summed with L2 atomics (run-to-run order differs) and Adam turns a sign flip of a ~0 gradient
+    # into a full +-lr step, so the weights are compared in the mean, not bit for bit
+    for a, b in ((s1, s2), (t1, t2)):
+        diff = (a.optimizer.flat_p - b.optimizer.flat_p).abs()
+        assert float(diff.mean()) < 1e-6 and float((diff > 1e-4).float().mean()) < 1e-3
+    assert list(loop.run([])) == []
