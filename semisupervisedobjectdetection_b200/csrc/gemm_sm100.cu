@@ -52,17 +52,20 @@ int g_gemm_occ2 = 0;
 // TMA-store epilogue (sfk_set_option("gemm_epi_tma", 0|1), default 1): each of the 8 epilogue warps stages its 32 rows of a
 // 32-column (f32) or 64-column (bf16) chunk in swizzled shared memory and one lane issues a TMA tile store (reduce-add for
 // split-K); the two warps of a TMEM lane quadrant take alternate chunks.  The legacy epilogue (per-thread row-wise global
-// stores) remains for remapped rows (prompt tokens) and CTA pairs.
+// stores) remains for remapped rows (prompt tokens).
 // Measured motivation (profiles/gemm_r2.md): with 4 epilogue warps (one per scheduler, nothing to switch to) a 32-column
 // chunk cost ~1100 cycles of dependent-issue latency and the epilogue, not the MMA, paced every K <= 1280 GEMM (tensor pipe
 // 16-20 %); row-wise fp32 stores made the residual variants ~2x the bf16 ones (24.2 vs 13.5 us at 16384 x 320 x 320).
 int g_gemm_epi_tma = 1;
+// staging buffers per epilogue warp (sfk_set_option("gemm_epi_bufs", 1|2), default 2; falls back to 1 where the operand ring
+// would otherwise drop below three stages)
+int g_gemm_epi_bufs = 2;
 // B-stationary main loop (sfk_set_option("gemm_bstat", 0|1), default 1) for K <= 512 without split-K: a CTA owns a contiguous,
 // n-major range of output tiles, keeps the [block_n x K] weight tile resident in shared memory and streams only A.  These
 // GEMMs (M >> N, K) were bound by the L2 -> shared-memory stream, 2/3 of which was the weight tile re-read for every row tile.
 int g_gemm_bstat = 1;
-// experiments (sfk_set_option("gemm_dbg")): bit 0 = skip the TMA stores (wrong results, timing only), bit 1 = skip the proxy
-// fence, bits 4..7 = staging buffers per epilogue warp (0 = default)
+// experiments (sfk_set_option("gemm_dbg"), wrong results, timing only): bit 0 = skip the TMA stores, bit 1 = skip the proxy
+// fence, bit 2 = no operand loads, bit 3 = no MMAs
 int g_gemm_dbg = 0;
 
 // optional in-kernel timeline (debug): CTA 0 stores globaltimer (ns) at phase boundaries into this device buffer
@@ -87,6 +90,8 @@ struct GemmKernelParams {
   int splits;
   int k_blocks;  // ceil(K / BLOCK_K)
   int m_tiles, n_tiles;
+  int units;                  // streaming mode: (row tiles | row-tile pairs) x column tiles x splits
+  int step_s, step_n, step_m; // mixed-radix digits of the per-CTA unit stride (grid | grid / 2) over (splits, n_tiles)
   int stages;
   uint32_t stage_bytes;  // A + B bytes per stage
   // epilogue
@@ -114,7 +119,8 @@ struct GemmKernelParams {
   int bstat;               // B-stationary: ring holds A only (a_bytes per stage), B tile lives at breg_off (k_blocks x b_kb_bytes)
   uint32_t breg_off, b_kb_bytes;
   int epi_tma;             // TMA-store epilogue (kernel template EPI: 1 = f32 chunks of 32 columns, 2 = bf16 chunks of 64 [+ a 32 tail])
-  uint32_t epi_off;        // staging area: 8 warps x 4 KB
+  uint32_t epi_off;        // staging area: 8 warps x epi_bufs x 4 KB
+  int epi_bufs;            // staging buffers per epilogue warp (1 | 2)
   int do_scale;            // alpha != 1 or per-row scales present
   int epi_warps;           // 8 (320-thread CTA, one per SM) | 4 (192-thread CTA: two CTAs per SM, row-wise epilogue)
   int dbg;
@@ -134,34 +140,50 @@ __device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, fl
 // Work schedule.  Streaming mode: units (tile, k split) dealt round-robin, column tile fastest.  B-stationary mode: the
 // n-major tile sequence t = n_blk * m_tiles + m_blk is cut into gridDim.x contiguous, equally long ranges, so a CTA changes
 // its weight tile at most a few times.
-struct UnitRange { int begin, end, step; };
-__device__ __forceinline__ UnitRange gemm_units(const GemmKernelParams& p, int pair) {
-  UnitRange r;
+// The walk is division-free per tile: the producer, the MMA issuer and the epilogue warps each run this iterator in a single
+// thread's (or warp's) instruction stream, and with 5-k-block tiles the ~10 integer divisions (two of them 64-bit) of the
+// first version cost 0.65 us between two tiles of the issuer and 0.8 us before the first TMA (in-kernel timeline, profiles/r2).
+// The host splits the stride of the round-robin deal into its mixed-radix digits (step_s, step_n, step_m).
+struct TileIter {
+  int m_grp, n_blk, split;   // current unit: row tile (row-tile PAIR in pair mode), column tile, k split
+  int left;                  // units left including the current one
+};
+__device__ __forceinline__ TileIter tile_iter_begin(const GemmKernelParams& p, int pair) {
+  TileIter it;
   if (p.bstat) {
-    const long long total = (long long)p.m_tiles * p.n_tiles;
-    r.begin = (int)((total * blockIdx.x) / gridDim.x);
-    r.end = (int)((total * (blockIdx.x + 1)) / gridDim.x);
-    r.step = 1;
+    const unsigned total = (unsigned)p.m_tiles * (unsigned)p.n_tiles;   // host guarantees total * gridDim.x < 2^32
+    const unsigned begin = total * blockIdx.x / gridDim.x, end = total * (blockIdx.x + 1u) / gridDim.x;
+    it.n_blk = (int)(begin / (unsigned)p.m_tiles);
+    it.m_grp = (int)(begin - (unsigned)it.n_blk * (unsigned)p.m_tiles);
+    it.split = 0;
+    it.left = (int)(end - begin);
   } else {
-    const int m_groups = pair ? (p.m_tiles + 1) / 2 : p.m_tiles;
-    r.begin = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    r.end = m_groups * p.n_tiles * p.splits;
-    r.step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int unit0 = pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int step = pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    it.split = unit0 % p.splits;
+    const int tile = unit0 / p.splits;
+    it.n_blk = tile % p.n_tiles;
+    it.m_grp = tile / p.n_tiles;
+    it.left = unit0 < p.units ? (p.units - 1 - unit0) / step + 1 : 0;
   }
-  return r;
+  return it;
 }
-__device__ __forceinline__ void gemm_unit_tile(const GemmKernelParams& p, int unit, int pair, uint32_t crank, int& m_blk, int& n_blk,
-                                               int& split) {
+__device__ __forceinline__ void tile_iter_next(const GemmKernelParams& p, TileIter& it) {
+  --it.left;
   if (p.bstat) {
-    n_blk = unit / p.m_tiles;
-    m_blk = unit - n_blk * p.m_tiles;
-    split = 0;
+    if (++it.m_grp == p.m_tiles) { it.m_grp = 0; ++it.n_blk; }
   } else {
-    split = unit % p.splits;
-    const int tile = unit / p.splits;
-    n_blk = tile % p.n_tiles;
-    m_blk = pair ? 2 * (tile / p.n_tiles) + (int)crank : tile / p.n_tiles;
+    it.split += p.step_s;
+    if (it.split >= p.splits) { it.split -= p.splits; ++it.n_blk; }
+    it.n_blk += p.step_n;
+    if (it.n_blk >= p.n_tiles) { it.n_blk -= p.n_tiles; ++it.m_grp; }
+    it.m_grp += p.step_m;
   }
+}
+__device__ __forceinline__ void tile_k_range(const GemmKernelParams& p, const TileIter& it, int& kb0, int& kb1) {
+  if (p.splits == 1) { kb0 = 0; kb1 = p.k_blocks; return; }
+  kb0 = (int)((unsigned)it.split * (unsigned)p.k_blocks / (unsigned)p.splits);
+  kb1 = (int)((unsigned)(it.split + 1) * (unsigned)p.k_blocks / (unsigned)p.splits);
 }
 
 // PAIR = 1: CTA-pair kernel (must be launched in 2-CTA clusters: it contains cta_group::2 instructions)
@@ -194,19 +216,22 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
-    if (EPI != 0) { tma_prefetch_desc(&tmap_out); tma_prefetch_desc(&tmap_tail); }
-    for (int s = 0; s < p.stages; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
-    }
-    for (int a = 0; a < 2; ++a) {
+  if (warp == 0) {
+    // one lane per barrier pair / descriptor instead of one thread walking all of them
+    if (lane < p.stages) {
+      mbar_init(bar_full + 8 * lane, 1);
+      mbar_init(bar_empty + 8 * lane, 1);
+    } else if (lane < p.stages + 2) {
+      const int a = lane - p.stages;
       mbar_init(bar_tfull + 8 * a, 1);
       mbar_init(bar_tempty + 8 * a, (PAIR ? 2 : 1) * p.epi_warps);   // pair: both CTAs' epilogue warps report to the leader
+    } else if (lane == p.stages + 2) {
+      mbar_init(bar_bfree, 1);
+    } else if (lane == 31) {
+      tma_prefetch_desc(&tmap_a);
+      tma_prefetch_desc(&tmap_b);
+      if (EPI != 0) { tma_prefetch_desc(&tmap_out); tma_prefetch_desc(&tmap_tail); }
     }
-    mbar_init(bar_bfree, 1);
     mbar_fence_init();
   }
   // pair kernels take their (pair-collective) TMEM allocation only after the grid dependency has resolved: a dependent
@@ -228,7 +253,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (threadIdx.x == 0) GEMM_TRACE(1);
 
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
-  const UnitRange ur = gemm_units(p, PAIR);
+  const TileIter it0 = tile_iter_begin(p, PAIR);
   const uint32_t ring_stage_bytes = p.bstat ? a_bytes : p.stage_bytes;
 
   if (warp == 0) {
@@ -239,13 +264,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       int cur_n = -1;             // B-stationary: column tile currently resident in the B region
       uint32_t bfree_phase = 0;
       int ptile = 0;
-      for (int unit = ur.begin; unit < ur.end; unit += ur.step) {
-        int m_blk, n_blk, split;
-        gemm_unit_tile(p, unit, PAIR, crank, m_blk, n_blk, split);
+      for (TileIter it = it0; it.left > 0; tile_iter_next(p, it)) {
+        const int m_blk = PAIR ? 2 * it.m_grp + (int)crank : it.m_grp, n_blk = it.n_blk;
         if (ptile < 24) GEMM_TRACE(64 + ptile);   // producer starts this tile (debug timeline)
         ++ptile;
-        const int kb0 = (int)(((long long)split * p.k_blocks) / p.splits);
-        const int kb1 = (int)(((long long)(split + 1) * p.k_blocks) / p.splits);
+        int kb0, kb1;
+        tile_k_range(p, it, kb0, kb1);
         bool load_b = true;
         if (p.bstat) {
           load_b = n_blk != cur_n;
@@ -259,10 +283,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sa = ring + stage * ring_stage_bytes;
           const uint32_t sb = p.bstat ? smem_base + p.breg_off + (uint32_t)kb * p.b_kb_bytes : sa + a_bytes;
-          if (!PAIR) {
+          if (p.dbg & 4) {   // experiment: no operand loads (timing of the MMA / epilogue side alone; wrong results)
+            if (!PAIR || crank == 0) mbar_arrive(bar_full + 8 * stage);
+          } else if (!PAIR) {
             const uint32_t full = bar_full + 8 * stage;
             mbar_arrive_expect_tx(full, p.bstat ? a_bytes + (load_b ? p.b_kb_bytes : 0u) : p.stage_bytes);
-            if (unit == ur.begin && kb == kb0) GEMM_TRACE(2);
+            if (ptile == 1 && kb == kb0) GEMM_TRACE(2);
             if (p.a_patch) {
               // implicit im2col: 128 patch rows = (128 / Wo) ox-rows of one sample; this k-block = 64 of the (kx, c) run of one ky
               const int m0 = m_blk * BLOCK_M;
@@ -296,7 +322,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             // brings its own 128 A rows and its half of the B tile
             const uint32_t full = mapa_shared(bar_full + 8 * stage, 0);
             if (crank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * p.stage_bytes);
-            if (unit == ur.begin && kb == kb0) GEMM_TRACE(2);
+            if (ptile == 1 && kb == kb0) GEMM_TRACE(2);
             if (!p.a_mn) {
               tma_load_2d_pair(sa, &tmap_a, full, kb * BLOCK_K, m_blk * BLOCK_M);
             } else {
@@ -336,14 +362,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       uint32_t phase = 0;
       int acc = 0;
       int mtile = 0;
-      uint32_t acc_phase[2] = {0, 0};
-      for (int unit = ur.begin; unit < ur.end; unit += ur.step) {
-        int m_blk, n_blk, split;
-        gemm_unit_tile(p, unit, PAIR, crank, m_blk, n_blk, split);
-        const int kb0 = (int)(((long long)split * p.k_blocks) / p.splits);
-        const int kb1 = (int)(((long long)(split + 1) * p.k_blocks) / p.splits);
+      uint32_t acc_phase = 0;   // bit a = phase of accumulator buffer a (a register, not an indexed local array)
+      for (TileIter it = it0; it.left > 0; tile_iter_next(p, it)) {
+        int kb0, kb1;
+        tile_k_range(p, it, kb0, kb1);
         // wait for the epilogue to have drained this accumulator buffer
-        mbar_wait(bar_tempty + 8 * acc, acc_phase[acc] ^ 1);
+        mbar_wait(bar_tempty + 8 * acc, ((acc_phase >> acc) & 1u) ^ 1u);
         tc_fence_after();
         if (mtile < 24) GEMM_TRACE(96 + mtile);    // accumulator buffer free (debug timeline)
         const uint32_t tmem_d = tmem_base + acc * (p.tmem_cols >> 1);
@@ -352,7 +376,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           tc_fence_after();
           const uint64_t ad = adesc0 + (uint64_t)stage * a_sstep;
           const uint64_t bd = bdesc0 + (uint64_t)(p.bstat ? kb : stage) * b_step;
-          if (PAIR) {
+          if (p.dbg & 8) {   // experiment: no MMAs (timing of the operand stream alone; wrong results)
+            if (PAIR) { umma_commit_pair(bar_empty + 8 * stage, 3); if (kb == kb1 - 1) umma_commit_pair(bar_tfull + 8 * acc, 3); }
+            else { umma_commit(bar_empty + 8 * stage); if (kb == kb1 - 1) umma_commit(bar_tfull + 8 * acc); }
+          } else if (PAIR) {
             umma_bf16_pair(tmem_d, ad, bd, idesc, kb > kb0 ? 1u : 0u);
 #pragma unroll
             for (int kk = 1; kk < BLOCK_K / UMMA_K; ++kk) umma_bf16_pair(tmem_d, ad + kk * a_kstep, bd + kk * b_kstep, idesc, 1u);
@@ -367,12 +394,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        if (unit == ur.begin) { GEMM_TRACE(3); GEMM_TRACE(4); }
+        if (mtile == 0) { GEMM_TRACE(3); GEMM_TRACE(4); }
         if (mtile < 24) GEMM_TRACE(160 + mtile);   // last k-block of the tile issued
         ++mtile;
-        if (p.bstat && unit + 1 < ur.end && (unit + 1) / p.m_tiles != n_blk)
+        if (p.bstat && it.left > 1 && it.m_grp + 1 == p.m_tiles)
           umma_commit(bar_bfree);   // last tile of this column tile: the producer may overwrite the B region once these retire
-        acc_phase[acc] ^= 1;
+        acc_phase ^= 1u << acc;
         acc ^= 1;
       }
     }
@@ -385,8 +412,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int epi_threads = 32 * p.epi_warps;
     int acc = 0;
     int trace_tile = 0;
-    uint32_t acc_phase[2] = {0, 0};
-    const uint32_t stage_buf = smem_base + p.epi_off + (uint32_t)(warp - 2) * EPI_WARP_BUF;
+    uint32_t acc_phase = 0;   // bit a = phase of accumulator buffer a
+    // staging buffers of this warp (1 or 2 x 4 KB): with two, the TMA store of a chunk reads its buffer while the next chunk
+    // is converted into the other one (ncu, profiles/r2: the wait for the previous store's shared-memory read was the
+    // largest single stall of the epilogue warps)
+    const uint32_t stage_buf0 = smem_base + p.epi_off + (uint32_t)(warp - 2) * (uint32_t)p.epi_bufs * EPI_WARP_BUF;
+    uint32_t stage_sel = 0;
     const bool has_bias = p.bias != nullptr;
     const bool has_res = p.residual != nullptr;
     const bool do_scale = p.do_scale != 0;
@@ -395,24 +426,23 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // issued after the TMEM load, then a per-tile staging step between two barriers, were the largest epilogue stalls.)
     uint32_t bias_slot = 0;
     float* sbias_gen = reinterpret_cast<float*>(smem_gen + bars_off + EPI_BIAS_OFF);
-    if (has_bias && ur.begin < ur.end) {
-      int m_blk, n_blk, split;
-      gemm_unit_tile(p, ur.begin, PAIR, crank, m_blk, n_blk, split);
+    if (has_bias && it0.left > 0) {
+      const int n_blk = it0.n_blk;
       if (warp == 2)
         for (int j = lane; j < p.block_n; j += 32) sbias_gen[j] = (n_blk * p.block_n + j < p.N) ? __ldg(p.bias + n_blk * p.block_n + j) : 0.f;
       asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");
     }
-    for (int unit = ur.begin; unit < ur.end; unit += ur.step) {
-      int m_blk, n_blk, split;
-      gemm_unit_tile(p, unit, PAIR, crank, m_blk, n_blk, split);
+    for (TileIter it = it0; it.left > 0; tile_iter_next(p, it)) {
+      const int m_blk = PAIR ? 2 * it.m_grp + (int)crank : it.m_grp, n_blk = it.n_blk;
       const int n0 = n_blk * p.block_n;
       const int row0 = m_blk * BLOCK_M + q * 32;
       const uint32_t sbias = smem_base + bars_off + EPI_BIAS_OFF + bias_slot * 1024u;
       // next tile's bias slice: loads issued now (registers), stored to the other slot after this tile's chunks
       int n_next = n_blk;
-      if (unit + ur.step < ur.end) {
-        int m2, s2;
-        gemm_unit_tile(p, unit + ur.step, PAIR, crank, m2, n_next, s2);
+      if (it.left > 1) {
+        TileIter nx = it;
+        tile_iter_next(p, nx);
+        n_next = nx.n_blk;
       }
       const bool bias_reload = has_bias && n_next != n_blk;
       float bias_next[MAX_BLOCK_N / 32];
@@ -423,9 +453,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           bias_next[j] = (cc < p.block_n && n_next * p.block_n + cc < p.N) ? __ldg(p.bias + n_next * p.block_n + cc) : 0.f;
         }
       }
-      mbar_wait(bar_tfull + 8 * acc, acc_phase[acc]);
+      mbar_wait(bar_tfull + 8 * acc, (acc_phase >> acc) & 1u);
       tc_fence_after();
-      if (threadIdx.x == 64 && unit == ur.begin) GEMM_TRACE(5);
+      if (threadIdx.x == 64 && trace_tile == 0) GEMM_TRACE(5);
       if (threadIdx.x == 64 && trace_tile < 28) GEMM_TRACE(8 + 2 * trace_tile);
       const long long row = (long long)row0 + lane;
       const bool row_ok = row < p.M;
@@ -442,22 +472,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           // residual values (first 32 columns of the chunk) first: their latency overlaps the TMEM load and the bias math
           float4 rr[8];
           const int col = n0 + c0;
-          const bool res_fast = row_ok && col + w <= p.N;
-          auto load_res = [&](int h) {   // 32 residual values of columns [32 h, 32 h + 32) of this chunk
-            if (res_fast) {
+          // 32 residual values of columns [32 h, 32 h + 32) of this chunk, one predicated 16-byte load per 4 columns: a group
+          // that straddles N still lies inside the row pitch (ldr % 4 == 0, checked by the host); its surplus columns are
+          // clipped by the TMA store
+          auto load_res = [&](int h) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) rr[j] = __ldg(reinterpret_cast<const float4*>(res_row + c0 + 32 * h) + j);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float t[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int cc = 32 * h + 4 * j + e;
-                  t[e] = (row_ok && cc < w && col + cc < p.N) ? __ldg(res_row + c0 + cc) : 0.f;
-                }
-                rr[j] = make_float4(t[0], t[1], t[2], t[3]);
-              }
+            for (int j = 0; j < 8; ++j) {
+              const int cc = 32 * h + 4 * j;
+              rr[j] = (row_ok && cc < w && col + cc < p.N) ? __ldg(reinterpret_cast<const float4*>(res_row + c0 + cc))
+                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
             }
           };
           if (has_res) load_res(0);
@@ -465,10 +488,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           __syncwarp();
           tmem_ld_32x32(tmem_acc + c0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
           if (CW == 64 && w == 64) tmem_ld_32x32(tmem_acc + c0 + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[CW - 32]));
-          // the TMA store that last read this warp's staging buffer must be done with it
-          if (lane == 0) tma_store_wait_read<0>();
+          // the TMA store that last read the staging buffer about to be overwritten must be done with it
+          if (lane == 0) {
+            if (p.epi_bufs == 2) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
+          }
           __syncwarp();
           tmem_ld_wait();
+          const uint32_t stage_buf = stage_buf0 + stage_sel * EPI_WARP_BUF;
+          stage_sel ^= (uint32_t)(p.epi_bufs - 1);
           const uint32_t row_bytes = (EPI == 2 && w == 32) ? 64u : 128u;   // bf16 tail chunk: 64-byte rows (SWIZZLE_64B)
           const uint32_t xr = row_bytes == 128u ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
           const uint32_t dst = stage_buf + (uint32_t)lane * row_bytes;
@@ -621,7 +649,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         if (PAIR) mbar_arrive_cluster(mapa_shared(bar_tempty + 8 * acc, 0));   // the leader's MMA issuer waits for both CTAs
         else mbar_arrive(bar_tempty + 8 * acc);
       }
-      if (threadIdx.x == 64 && unit == ur.begin) GEMM_TRACE(6);
+      if (threadIdx.x == 64 && trace_tile == 0) GEMM_TRACE(6);
       if (threadIdx.x == 64 && trace_tile < 28) GEMM_TRACE(9 + 2 * trace_tile);
       ++trace_tile;
       if (bias_reload) {
@@ -633,7 +661,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         bias_slot ^= 1u;
         asm volatile("bar.sync 1, %0;" ::"r"(epi_threads) : "memory");  // next slice published; (two tiles later) this slot is free again
       }
-      acc_phase[acc] ^= 1;
+      acc_phase ^= 1u << acc;
       acc ^= 1;
     }
     // staged chunks must have left shared memory before the CTA retires
@@ -772,10 +800,11 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
   }
   p.cluster2 = pair_bn > 0 ? 1 : 0;
 
-  // epilogue mode: TMA tile stores need identity row maps (prompt-token remaps keep the per-thread path); CTA pairs keep it too
+  // epilogue mode: TMA tile stores need identity row maps (prompt-token remaps keep the per-thread path)
   const bool maps_identity = g.out_map.period == 0 && g.out_map.offset == 0 && g.res_map.period == 0 && g.res_map.offset == 0;
-  bool epi_tma = g_gemm_epi_tma && maps_identity && !p.cluster2;
-  const uint32_t stage_bytes_epi = epi_tma ? (uint32_t)GEMM_EPI_WARPS * EPI_WARP_BUF : 0u;
+  bool epi_tma = g_gemm_epi_tma && maps_identity;
+  int epi_bufs = epi_tma ? (g_gemm_epi_bufs >= 2 ? 2 : 1) : 1;
+  uint32_t stage_bytes_epi = epi_tma ? (uint32_t)GEMM_EPI_WARPS * (uint32_t)epi_bufs * EPI_WARP_BUF : 0u;
   const uint32_t bars_bytes = EPI_BIAS_OFF + EPI_BIAS_BYTES;
 
   // B-stationary main loop: small K, no split-K, plain operands
@@ -785,7 +814,7 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
   // 3-10 %; from K = 320 on the up-front tile load and the one-tile-deep ring lose 5-30 % against streaming wide tiles, so
   // automatic selection stops at two k-blocks; an explicit block_n still selects it up to K = 512)
   if (g_gemm_bstat && !p.cluster2 && !a_patch && !b_patch && (!g.atomic_add || g.splits == 1) && g.splits <= 1 &&
-      p.k_blocks <= (g.block_n > 0 ? 8 : 2)) {
+      p.k_blocks <= (g.block_n > 0 ? 8 : 2) && (long long)p.m_tiles * ((g.N + 31) / 32) * num_sms() < (1LL << 32)) {
     const int fixed = (int)(stage_bytes_epi + bars_bytes + 1024u);
     if (g.block_n > 0) {
       const long long b_bytes = (long long)g.block_n * p.k_blocks * 128;
@@ -847,13 +876,19 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
   p.splits = splits;
 
   // shared-memory layout: [epilogue staging][A/B ring][B region][barriers + bias]
-  if (light) epi_tma = false;
+  if (light) { epi_tma = false; epi_bufs = 1; stage_bytes_epi = 0; }
+  p.stage_bytes = BLOCK_M * BLOCK_K * 2 + (p.cluster2 ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;   // per CTA
+  if (epi_tma && epi_bufs == 2 && !p.bstat &&
+      (227 * 1024 - 1024 - (int)bars_bytes - (int)stage_bytes_epi) / (int)p.stage_bytes < 3) {
+    epi_bufs = 1;   // keep the operand ring at least three deep
+    stage_bytes_epi = (uint32_t)GEMM_EPI_WARPS * EPI_WARP_BUF;
+  }
   p.epi_tma = epi_tma ? 1 : 0;
+  p.epi_bufs = epi_bufs;
   p.epi_off = 0;
   p.dbg = g_gemm_dbg;
   p.do_scale = (g.alpha != 1.0f || g.row_scale != nullptr) ? 1 : 0;
   p.ring_off = epi_tma ? stage_bytes_epi : 0u;
-  p.stage_bytes = BLOCK_M * BLOCK_K * 2 + (p.cluster2 ? p.block_n / 2 : p.block_n) * BLOCK_K * 2;   // per CTA
   p.b_kb_bytes = (uint32_t)p.block_n * BLOCK_K * 2;
   int stages;
   if (p.bstat) {
@@ -896,12 +931,22 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
   smem_bytes = (size_t)p.bars_off + bars_bytes + 1024;
   SFK_REQUIRE(smem_bytes <= (size_t)227 * 1024, "gemm: shared-memory plan of %zu bytes exceeds 227 KB", smem_bytes);
   const long long units = (long long)(p.cluster2 ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles * p.splits;
+  SFK_REQUIRE(units < (1LL << 30), "gemm: %lld work units exceed the scheduler's range", units);
   if (p.cluster2) {
     const long long clusters = units < num_sms() / 2 ? units : num_sms() / 2;
     grid = (int)(2 * clusters);
   } else {
     const long long slots = (long long)num_sms() * (light ? 2 : 1);
     grid = (int)(units < slots ? units : slots);
+  }
+  // per-CTA unit stride of the round-robin deal, in mixed-radix digits over (splits, n_tiles): TileIter adds them with carries
+  p.units = (int)units;
+  {
+    const int step = p.cluster2 ? grid / 2 : grid;
+    p.step_s = step % p.splits;
+    const int t = step / p.splits;
+    p.step_n = t % p.n_tiles;
+    p.step_m = t / p.n_tiles;
   }
   return 0;
 }
@@ -981,6 +1026,8 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     SFK_REQUIRE(e == cudaSuccess, "gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -1001,7 +1048,9 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    (void)cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<1, 0>, ta, tb, tout, ttail, p);
+    if (epi == 1) (void)cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<1, 1>, ta, tb, tout, ttail, p);
+    else if (epi == 2) (void)cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<1, 2>, ta, tb, tout, ttail, p);
+    else (void)cudaLaunchKernelEx(&cfg, gemm_bf16_tcgen05_kernel<1, 0>, ta, tb, tout, ttail, p);
   } else if (epi == 1) {
     launch_k(gemm_bf16_tcgen05_kernel<0, 1>, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, tout, ttail, p);
   } else if (epi == 2) {
