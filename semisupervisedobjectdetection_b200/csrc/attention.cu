@@ -237,6 +237,204 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Forward fast path for Tk <= 256 (every stage of the 512x512 path without prompt tokens: the spatial reduction always
+// leaves 16 x 16 = 256 key/value rows).  The whole score row fits tensor memory, so there is no online rescaling:
+//   S[128 x 256] = Q K^T in ONE accumulator (256 TMEM columns), 256 softmax threads (two per query row, 128 columns each;
+//   row maximum and row sum exchanged through shared memory), P[128 x 256] (bf16, four swizzled 64-column tiles) written
+//   over the Q and K tiles (dead once S is complete), O = P V with K = 256 into the first D columns of the same TMEM
+//   allocation, 256 threads convert and store O.
+// 97 KB of shared memory and 256 TMEM columns per CTA: two CTAs per SM, one's softmax under the other's loads and MMAs.
+// Measured motivation (profiles/r2): the chunked kernel above ran one thread per row through two dependent 128-column
+// chunks (S MMA -> softmax -> P V MMA -> rescale, twice) and took 25-30 us for the 640 tiles of a stage-3 layer, ~15 % of
+// either roofline.
+// ------------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(288, 2)
+attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                   const __grid_constant__ CUtensorMap tmap_v, const AttFwdParams p) {
+  pdl_launch_dependents();
+  using Cfg = AttCfg<D>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (base - smem_u32(smem_raw));
+  // [P: 64 KB, overlaying Q (TILE) and K (2 TILE)] [V: 2 TILE] [barriers, exchange buffers]
+  const uint32_t sP = base, sQ = base, sK = base + Cfg::TILE, sV = base + 65536;
+  uint8_t* sP_gen = gen;
+  const uint32_t bars = sV + 2 * Cfg::TILE;
+  const uint32_t b_qk = bars, b_v = bars + 8, b_sfull = bars + 16, b_pready = bars + 24, b_ofull = bars + 32, tmem_slot = bars + 40;
+  uint8_t* bars_gen = gen + 65536 + 2 * Cfg::TILE;
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(bars_gen + 40);
+  float* xmax = reinterpret_cast<float*>(bars_gen + 64);          // [2][128] row maxima of the two column halves
+  float* xsum = xmax + 256;                                       // [2][128] row sums
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BM, head = blockIdx.y, batch = blockIdx.z;
+
+  if (threadIdx.x == 256) {
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
+    mbar_init(b_qk, 1); mbar_init(b_v, 1); mbar_init(b_sfull, 1); mbar_init(b_pready, 256); mbar_init(b_ofull, 1);
+    mbar_fence_init();
+  }
+  if (warp == 8) { tmem_alloc(tmem_slot, 256); tmem_relinquish(); }
+  pdl_wait();  // setup above overlaps the previous kernel's tail
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot_gen;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      // ---------------- control thread: TMA + MMA issue ----------------
+      mbar_arrive_expect_tx(b_qk, 3 * Cfg::TILE);
+      tma_load_3d(sQ, &tmap_q, b_qk, head * D, q0, batch);
+      tma_load_3d(sK, &tmap_k, b_qk, head * D, 0, batch);        // box = 256 rows; rows >= Tk arrive as zeros
+      mbar_arrive_expect_tx(b_v, 2 * Cfg::TILE);
+      tma_load_3d(sV, &tmap_v, b_v, head * D, 0, batch);
+      const uint32_t idesc_s = umma_idesc_bf16(128, 256, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(128, D, 0, 1);
+      mbar_wait(b_qk, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < Cfg::KSTEPS; ++kk)
+        umma_bf16(tmem, umma_smem_desc_lt(sQ + kk * 32, 16, 8 * Cfg::RB, Cfg::LT),
+                  umma_smem_desc_lt(sK + kk * 32, 16, 8 * Cfg::RB, Cfg::LT), idesc_s, kk > 0 ? 1u : 0u);
+      umma_commit(b_sfull);
+      mbar_wait(b_pready, 0);     // all 256 threads have read S and written P (over Q / K)
+      mbar_wait(b_v, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 16; ++ks)
+        umma_bf16(tmem, umma_smem_desc_lt(sP + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, 2u),
+                  umma_smem_desc_lt(sV + ks * 16 * Cfg::RB, 128 * Cfg::RB, 8 * Cfg::RB, Cfg::LT), idesc_o, ks > 0 ? 1u : 0u);
+      umma_commit(b_ofull);
+    }
+  } else {
+    // ---------------- softmax threads: query row r, column half h ----------------
+    const int qd = warp & 3, h = warp >> 2;
+    const int r = qd * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+    const int valid = min(128, max(0, p.Tk - h * 128));   // valid key columns of this half
+    const bool full = valid == 128;
+    mbar_wait(b_sfull, 0);
+    tc_fence_after();
+    float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+    for (int cc = 0; cc < 128; cc += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem + lane_base + h * 128 + cc, v);
+      tmem_ld_wait();
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (cc + j < valid) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
+      }
+    }
+    const float m_half = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+    xmax[h * 128 + r] = m_half;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float m_row = fmaxf(m_half, xmax[(h ^ 1) * 128 + r]);
+    const float moff = m_row * p.scale_log2;
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int cc = 0; cc < 128; cc += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem + lane_base + h * 128 + cc, v);
+      tmem_ld_wait();
+      float e[32];
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          e[j] = fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -moff));
+          s4[j & 3] += e[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          e[j] = (cc + j < valid) ? fast_exp2(fmaf(__uint_as_float(v[j]), p.scale_log2, -moff)) : 0.f;
+          s4[j & 3] += e[j];
+        }
+      }
+      uint8_t* tile = sP_gen + (h * 2 + (cc >> 6)) * 16384;
+#pragma unroll
+      for (int j8 = 0; j8 < 4; ++j8) {
+        uint4 o;
+        o.x = pack_bf16x2(e[j8 * 8 + 0], e[j8 * 8 + 1]);
+        o.y = pack_bf16x2(e[j8 * 8 + 2], e[j8 * 8 + 3]);
+        o.z = pack_bf16x2(e[j8 * 8 + 4], e[j8 * 8 + 5]);
+        o.w = pack_bf16x2(e[j8 * 8 + 6], e[j8 * 8 + 7]);
+        st_swizzled_chunk(tile, r, ((cc & 63) >> 3) + j8, o);
+      }
+    }
+    xsum[h * 128 + r] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    mbar_arrive(b_pready);
+    mbar_wait(b_ofull, 0);
+    tc_fence_after();
+    // every thread arrived on b_pready before the P V MMAs were issued, so both halves' sums are visible here
+    const float l_row = xsum[r] + xsum[128 + r];
+    const float inv = 1.f / l_row;
+    constexpr int OC = D / 2;   // output columns per thread
+    uint32_t v[OC];
+    if (OC == 32) tmem_ld_32x32(tmem + lane_base + h * OC, *reinterpret_cast<uint32_t(*)[32]>(&v[0]));
+    else tmem_ld_32x16(tmem + lane_base + h * OC, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+    tmem_ld_wait();
+    const int t = q0 + r;
+    if (t < p.T) {
+      __nv_bfloat16* op = p.o + batch * p.o_batch_stride + (long long)t * p.ldo + head * D + h * OC;
+#pragma unroll
+      for (int j = 0; j < OC; j += 8) {
+        uint4 o;
+        o.x = pack_bf16x2(__uint_as_float(v[j]) * inv, __uint_as_float(v[j + 1]) * inv);
+        o.y = pack_bf16x2(__uint_as_float(v[j + 2]) * inv, __uint_as_float(v[j + 3]) * inv);
+        o.z = pack_bf16x2(__uint_as_float(v[j + 4]) * inv, __uint_as_float(v[j + 5]) * inv);
+        o.w = pack_bf16x2(__uint_as_float(v[j + 6]) * inv, __uint_as_float(v[j + 7]) * inv);
+        *reinterpret_cast<uint4*>(op + j) = o;
+      }
+      if (p.lse && h == 0) p.lse[((long long)batch * p.heads + head) * p.T + t] = moff + log2f(l_row);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+// sfk_set_option("attn_fwd256", 0|1): single-pass forward kernel for Tk <= 256 (default 1)
+int g_attn_fwd256 = 1;
+
+template <int D>
+static int attn_fwd256_launch(const AttentionDesc& a, cudaStream_t stream) {
+  using Cfg = AttCfg<D>;
+  CUtensorMap tq, tk, tv;
+  int rc = make_tmap_3d_bf16(&tq, a.q, (uint64_t)a.heads * D, (uint64_t)a.T, (uint64_t)a.B, (uint64_t)a.ldq * 2,
+                             (uint64_t)a.q_batch_stride * 2, D, ATT_BM, 1, Cfg::RB);
+  if (rc) return rc;
+  rc = make_tmap_3d_bf16(&tk, a.k, (uint64_t)a.heads * D, (uint64_t)a.Tk, (uint64_t)a.B, (uint64_t)a.ldkv * 2,
+                         (uint64_t)a.kv_batch_stride * 2, D, 256, 1, Cfg::RB);
+  if (rc) return rc;
+  rc = make_tmap_3d_bf16(&tv, a.v, (uint64_t)a.heads * D, (uint64_t)a.Tk, (uint64_t)a.B, (uint64_t)a.ldkv * 2,
+                         (uint64_t)a.kv_batch_stride * 2, D, 256, 1, Cfg::RB);
+  if (rc) return rc;
+  AttFwdParams p;
+  p.T = a.T; p.Tk = a.Tk; p.heads = a.heads;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.o = (__nv_bfloat16*)a.o; p.ldo = a.ldo; p.o_batch_stride = a.o_batch_stride; p.lse = a.lse;
+  const size_t smem = 65536 + 2 * Cfg::TILE + 64 + 2048 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd256_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    SFK_REQUIRE(e == cudaSuccess, "attention_fwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  dim3 grid((a.T + ATT_BM - 1) / ATT_BM, a.heads, a.B);
+  launch_k(attn_fwd256_kernel<D>, dim3(grid), dim3(288), smem, stream, tq, tk, tv, p);
+  return check_launch("attn_fwd256_kernel");
+}
+
 template <int D>
 static int attn_fwd_launch(const AttentionDesc& a, cudaStream_t stream) {
   using Cfg = AttCfg<D>;
@@ -271,6 +469,7 @@ int attention_fwd(const AttentionDesc& a, cudaStream_t stream) {
   SFK_REQUIRE(a.T > 0 && a.Tk > 0 && a.B > 0 && a.heads > 0, "attention: empty problem");
   SFK_REQUIRE(a.B <= 65535 && a.heads <= 65535, "attention: batch/heads exceed grid limits");
   SFK_REQUIRE(a.ldo % 8 == 0 && (reinterpret_cast<uintptr_t>(a.o) & 15) == 0, "attention: output must be 16-byte aligned");
+  if (g_attn_fwd256 && a.Tk <= 256) return a.D == 64 ? attn_fwd256_launch<64>(a, stream) : attn_fwd256_launch<32>(a, stream);
   return a.D == 64 ? attn_fwd_launch<64>(a, stream) : attn_fwd_launch<32>(a, stream);
 }
 

@@ -65,7 +65,7 @@ int g_gemm_epi_bufs = 2;
 // GEMMs (M >> N, K) were bound by the L2 -> shared-memory stream, 2/3 of which was the weight tile re-read for every row tile.
 int g_gemm_bstat = 1;
 // experiments (sfk_set_option("gemm_dbg"), wrong results, timing only): bit 0 = skip the TMA stores, bit 1 = skip the proxy
-// fence, bit 2 = no operand loads, bit 3 = no MMAs
+// fence, bit 2 = no operand loads, bit 3 = no MMAs, bit 4 = no tiles at all
 int g_gemm_dbg = 0;
 
 // optional in-kernel timeline (debug): CTA 0 stores globaltimer (ns) at phase boundaries into this device buffer
@@ -121,6 +121,7 @@ struct GemmKernelParams {
   int epi_tma;             // TMA-store epilogue (kernel template EPI: 1 = f32 chunks of 32 columns, 2 = bf16 chunks of 64 [+ a 32 tail])
   uint32_t epi_off;        // staging area: 8 warps x epi_bufs x 4 KB
   int epi_bufs;            // staging buffers per epilogue warp (1 | 2)
+  uint32_t res_off;        // residual transpose buffers: 8 warps x 4 KB (behind the staging area; only with a residual)
   int do_scale;            // alpha != 1 or per-row scales present
   int epi_warps;           // 8 (320-thread CTA, one per SM) | 4 (192-thread CTA: two CTAs per SM, row-wise epilogue)
   int dbg;
@@ -253,7 +254,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (threadIdx.x == 0) GEMM_TRACE(1);
 
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
-  const TileIter it0 = tile_iter_begin(p, PAIR);
+  TileIter it0 = tile_iter_begin(p, PAIR);
+  if (p.dbg & 16) it0.left = 0;   // experiment: no work at all (launch + prologue + teardown floor)
   const uint32_t ring_stage_bytes = p.bstat ? a_bytes : p.stage_bytes;
 
   if (warp == 0) {
@@ -417,6 +419,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // is converted into the other one (ncu, profiles/r2: the wait for the previous store's shared-memory read was the
     // largest single stall of the epilogue warps)
     const uint32_t stage_buf0 = smem_base + p.epi_off + (uint32_t)(warp - 2) * (uint32_t)p.epi_bufs * EPI_WARP_BUF;
+    const uint32_t res_buf = smem_base + p.res_off + (uint32_t)(warp - 2) * EPI_WARP_BUF;   // residual transpose buffer
     uint32_t stage_sel = 0;
     const bool has_bias = p.bias != nullptr;
     const bool has_res = p.residual != nullptr;
@@ -453,6 +456,25 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           bias_next[j] = (cc < p.block_n && n_next * p.block_n + cc < p.N) ? __ldg(p.bias + n_next * p.block_n + cc) : 0.f;
         }
       }
+      // residual tile: read with COALESCED 16-byte loads (8 lanes per row, 4 rows per instruction), transposed to the
+      // thread-per-row TMEM layout through a swizzled 4 KB buffer per warp, and fetched one 32-column half ahead of its use.
+      // (The first version let each thread read its own row: 32 cache lines per load instruction, 2560 L1 tag cycles per
+      // 128 x 160 tile - the epilogue of the residual GEMMs alone took 6.6 us more than the bf16 ones, profiles/r2.)
+      constexpr int CWR = EPI == 2 ? 64 : 32;
+      float4 rr[8];
+      const int res_r = lane >> 3, res_p = lane & 7;   // row within a 4-row group / 16-byte piece of the 128-byte row segment
+      auto res_fetch = [&](int c0f, int hf) {
+        const int wf = (EPI == 2 && c0f + CWR > p.block_n) ? 32 : CWR;
+        const int cc = 32 * hf + 4 * res_p;
+        const bool cok = cc < wf && n0 + c0f + cc < p.N;
+        const float* base = p.residual + (long long)(row0 + res_r) * p.ldr + n0 + c0f + cc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          rr[j] = (cok && row0 + res_r + 4 * j < p.M) ? __ldg(reinterpret_cast<const float4*>(base + (long long)(4 * j) * p.ldr))
+                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      const int c0_first = (wpq == 2 ? (half ^ (trace_tile & 1)) : 0) * CWR;
+      if (EPI != 0 && has_res && c0_first < p.block_n) res_fetch(c0_first, 0);
       mbar_wait(bar_tfull + 8 * acc, (acc_phase >> acc) & 1u);
       tc_fence_after();
       if (threadIdx.x == 64 && trace_tile == 0) GEMM_TRACE(5);
@@ -466,24 +488,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       if (EPI != 0) {
         // ---- staged epilogue: TMEM -> registers -> swizzled shared memory -> TMA store / reduce-add ----
         constexpr int CW = EPI == 2 ? 64 : 32;               // columns per chunk (a bf16 tile may end in a 32-column chunk)
-        const float* res_row = has_res ? p.residual + row * p.ldr + n0 : nullptr;
         for (int c0 = (wpq == 2 ? (half ^ (trace_tile & 1)) : 0) * CW; c0 < p.block_n; c0 += wpq * CW) {
           const int w = (EPI == 2 && c0 + CW > p.block_n) ? 32 : CW;   // this chunk's width
-          // residual values (first 32 columns of the chunk) first: their latency overlaps the TMEM load and the bias math
-          float4 rr[8];
-          const int col = n0 + c0;
-          // 32 residual values of columns [32 h, 32 h + 32) of this chunk, one predicated 16-byte load per 4 columns: a group
-          // that straddles N still lies inside the row pitch (ldr % 4 == 0, checked by the host); its surplus columns are
-          // clipped by the TMA store
-          auto load_res = [&](int h) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int cc = 32 * h + 4 * j;
-              rr[j] = (row_ok && cc < w && col + cc < p.N) ? __ldg(reinterpret_cast<const float4*>(res_row + c0 + cc))
-                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          };
-          if (has_res) load_res(0);
           uint32_t r[CW];
           __syncwarp();
           tmem_ld_32x32(tmem_acc + c0, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
@@ -523,11 +529,24 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 for (int j = 0; j < 16; ++j) v[j] = p2_mul(v[j], rs2);
               }
               if (has_res) {
-                if (h > 0) load_res(h);
+                __syncwarp();   // the previous half's reads of the transpose buffer are done
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                  v[2 * j] = p2_add(v[2 * j], p2_make(rr[j].x, rr[j].y));
-                  v[2 * j + 1] = p2_add(v[2 * j + 1], p2_make(rr[j].z, rr[j].w));
+                  const uint32_t rw = (uint32_t)(4 * j + res_r);
+                  st_shared_v4(res_buf + rw * 128u + ((((uint32_t)res_p) ^ (rw & 7u)) << 4), __float_as_uint(rr[j].x),
+                               __float_as_uint(rr[j].y), __float_as_uint(rr[j].z), __float_as_uint(rr[j].w));
+                }
+                __syncwarp();
+                // fetch the next half of this tile (this chunk's second half, or the warp's next chunk)
+                if (h + 1 < CW / 32 && 32 * (h + 1) < w) res_fetch(c0, h + 1);
+                else if (c0 + wpq * CW < p.block_n) res_fetch(c0 + wpq * CW, 0);
+                uint4 r4[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) r4[j] = ld_shared_v4(res_buf + (uint32_t)lane * 128u + ((((uint32_t)j) ^ ((uint32_t)lane & 7u)) << 4));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  v[2 * j] = p2_add(v[2 * j], p2_make_u(r4[j].x, r4[j].y));
+                  v[2 * j + 1] = p2_add(v[2 * j + 1], p2_make_u(r4[j].z, r4[j].w));
                 }
               }
               if (p.relu) {
@@ -804,7 +823,8 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
   const bool maps_identity = g.out_map.period == 0 && g.out_map.offset == 0 && g.res_map.period == 0 && g.res_map.offset == 0;
   bool epi_tma = g_gemm_epi_tma && maps_identity;
   int epi_bufs = epi_tma ? (g_gemm_epi_bufs >= 2 ? 2 : 1) : 1;
-  uint32_t stage_bytes_epi = epi_tma ? (uint32_t)GEMM_EPI_WARPS * (uint32_t)epi_bufs * EPI_WARP_BUF : 0u;
+  const uint32_t res_bytes = (epi_tma && g.residual != nullptr) ? (uint32_t)GEMM_EPI_WARPS * EPI_WARP_BUF : 0u;
+  uint32_t stage_bytes_epi = epi_tma ? (uint32_t)GEMM_EPI_WARPS * (uint32_t)epi_bufs * EPI_WARP_BUF + res_bytes : 0u;
   const uint32_t bars_bytes = EPI_BIAS_OFF + EPI_BIAS_BYTES;
 
   // B-stationary main loop: small K, no split-K, plain operands
@@ -881,11 +901,12 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
   if (epi_tma && epi_bufs == 2 && !p.bstat &&
       (227 * 1024 - 1024 - (int)bars_bytes - (int)stage_bytes_epi) / (int)p.stage_bytes < 3) {
     epi_bufs = 1;   // keep the operand ring at least three deep
-    stage_bytes_epi = (uint32_t)GEMM_EPI_WARPS * EPI_WARP_BUF;
+    stage_bytes_epi = (uint32_t)GEMM_EPI_WARPS * EPI_WARP_BUF + res_bytes;
   }
   p.epi_tma = epi_tma ? 1 : 0;
   p.epi_bufs = epi_bufs;
   p.epi_off = 0;
+  p.res_off = (uint32_t)GEMM_EPI_WARPS * (uint32_t)epi_bufs * EPI_WARP_BUF;
   p.dbg = g_gemm_dbg;
   p.do_scale = (g.alpha != 1.0f || g.row_scale != nullptr) ? 1 : 0;
   p.ring_off = epi_tma ? stage_bytes_epi : 0u;
