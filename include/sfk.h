@@ -145,12 +145,18 @@ typedef struct {
   const float *ln1_g, *ln1_b, *ln2_g, *ln2_b, *lnsr_g, *lnsr_b;
   const float *dw_wt, *dw_b;                   /* depthwise weight tap-major [9][4C], bias [4C] */
   const float *drop_scale_attn, *drop_scale_mlp; /* per-sample drop-path multipliers mask/keep (MS:95-102) or NULL */
+  const void *dmlp_in;                         /* backward only, optional: bf16 [B*H*W, C] = dout * drop_scale_mlp already produced (with db2
+                                                  accumulated) by the following layer's backward through next_dmlp below */
 } sfk_layer_params;
 typedef struct {
   float *dwq, *dwk, *dwv, *dwo, *dwsr, *dw1, *dw2;   /* same shapes as the nn.Parameters (sr: OIHW) */
   float *dbq, *dbk, *dbv, *dbo, *dbsr, *db1, *db2;
   float *dln1_g, *dln1_b, *dln2_g, *dln2_b, *dlnsr_g, *dlnsr_b;
   float *ddw, *ddb;                                  /* depthwise [4C,1,3,3], [4C] */
+  /* optional (ptl == 0): the LayerNorm-1 backward that writes dx also writes the PRECEDING layer's MixFFN input gradient
+   * next_dmlp = bf16(dx * next_drop_scale[sample]) and accumulates its column sums into next_db2 (that layer's dense2 bias
+   * gradient), so the preceding layer's backward can take it through sfk_layer_params.dmlp_in instead of re-reading dx */
+  void *next_dmlp; const float *next_drop_scale; float *next_db2;
 } sfk_layer_grads;
 size_t sfk_layer_saved_bytes(const sfk_layer_dims* dims);
 size_t sfk_layer_scratch_bytes(const sfk_layer_dims* dims);

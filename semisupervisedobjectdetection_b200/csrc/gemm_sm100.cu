@@ -60,6 +60,10 @@ int g_gemm_epi_tma = 1;
 // staging buffers per epilogue warp (sfk_set_option("gemm_epi_bufs", 1|2), default 2; falls back to 1 where the operand ring
 // would otherwise drop below three stages)
 int g_gemm_epi_bufs = 2;
+// experiment: cap on the operand ring depth (sfk_set_option("gemm_max_stages", n); 0 = no cap)
+int g_gemm_max_stages = 0;
+// per-CTA rotated k-block order (sfk_set_option("gemm_krot", 0|1))
+int g_gemm_krot = 0;   // measured on the MiT-b5 shapes: no effect (19.51 vs 19.52 ms per step), so off
 // B-stationary main loop (sfk_set_option("gemm_bstat", 0|1), default 1) for K <= 512 without split-K: a CTA owns a contiguous,
 // n-major range of output tiles, keeps the [block_n x K] weight tile resident in shared memory and streams only A.  These
 // GEMMs (M >> N, K) were bound by the L2 -> shared-memory stream, 2/3 of which was the weight tile re-read for every row tile.
@@ -121,6 +125,7 @@ struct GemmKernelParams {
   int epi_tma;             // TMA-store epilogue (kernel template EPI: 1 = f32 chunks of 32 columns, 2 = bf16 chunks of 64 [+ a 32 tail])
   uint32_t epi_off;        // staging area: 8 warps x epi_bufs x 4 KB
   int epi_bufs;            // staging buffers per epilogue warp (1 | 2)
+  int krot;                // rotate each CTA's k-block order (streaming mode)
   uint32_t res_off;        // residual transpose buffers: 8 warps x 4 KB (behind the staging area; only with a residual)
   int do_scale;            // alpha != 1 or per-row scales present
   int epi_warps;           // 8 (320-thread CTA, one per SM) | 4 (192-thread CTA: two CTAs per SM, row-wise epilogue)
@@ -281,7 +286,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
           cur_n = n_blk;
         }
-        for (int kb = kb0; kb < kb1; ++kb) {
+        // k-blocks are walked from a per-CTA rotated start (the sum does not care about the order): CTAs that share a
+        // weight tile and start together would otherwise all request the same few L2 lines at the same moment
+        const int krot = p.krot ? (int)((PAIR ? blockIdx.x >> 1 : blockIdx.x) % (unsigned)(kb1 - kb0)) : 0;
+        for (int ki = kb0; ki < kb1; ++ki) {
+          int kb = ki + krot;
+          if (kb >= kb1) kb -= kb1 - kb0;
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sa = ring + stage * ring_stage_bytes;
           const uint32_t sb = p.bstat ? smem_base + p.breg_off + (uint32_t)kb * p.b_kb_bytes : sa + a_bytes;
@@ -290,7 +300,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           } else if (!PAIR) {
             const uint32_t full = bar_full + 8 * stage;
             mbar_arrive_expect_tx(full, p.bstat ? a_bytes + (load_b ? p.b_kb_bytes : 0u) : p.stage_bytes);
-            if (ptile == 1 && kb == kb0) GEMM_TRACE(2);
+            if (ptile == 1 && ki == kb0) GEMM_TRACE(2);
             if (p.a_patch) {
               // implicit im2col: 128 patch rows = (128 / Wo) ox-rows of one sample; this k-block = 64 of the (kx, c) run of one ky
               const int m0 = m_blk * BLOCK_M;
@@ -324,7 +334,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             // brings its own 128 A rows and its half of the B tile
             const uint32_t full = mapa_shared(bar_full + 8 * stage, 0);
             if (crank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * p.stage_bytes);
-            if (ptile == 1 && kb == kb0) GEMM_TRACE(2);
+            if (ptile == 1 && ki == kb0) GEMM_TRACE(2);
             if (!p.a_mn) {
               tma_load_2d_pair(sa, &tmap_a, full, kb * BLOCK_K, m_blk * BLOCK_M);
             } else {
@@ -905,6 +915,7 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
   }
   p.epi_tma = epi_tma ? 1 : 0;
   p.epi_bufs = epi_bufs;
+  p.krot = (g_gemm_krot && !p.bstat) ? 1 : 0;
   p.epi_off = 0;
   p.res_off = (uint32_t)GEMM_EPI_WARPS * (uint32_t)epi_bufs * EPI_WARP_BUF;
   p.dbg = g_gemm_dbg;
@@ -923,6 +934,11 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
     if (light && stages > p.k_blocks + 1) stages = p.k_blocks + 1;
     p.breg_off = 0;
     p.bars_off = p.ring_off + (uint32_t)stages * p.stage_bytes;
+  }
+  if (g_gemm_max_stages >= 2 && stages > g_gemm_max_stages) {
+    stages = g_gemm_max_stages;
+    if (p.bstat) { p.breg_off = p.ring_off + (uint32_t)stages * BLOCK_M * BLOCK_K * 2; p.bars_off = p.breg_off + (uint32_t)p.k_blocks * p.b_kb_bytes; }
+    else p.bars_off = p.ring_off + (uint32_t)stages * p.stage_bytes;
   }
   SFK_REQUIRE(stages >= 2, "gemm: not enough shared memory for 2 stages");
   p.stages = stages;

@@ -335,7 +335,9 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
 
   // ---- MixFFN branch ----
   // drop-path backward + bf16 cast, fused with the dense2 bias gradient (column sums of dmlp)
-  TRY(scale_cast_sum(dout, 0, id, dmlp, 1, id, p.drop_scale_mlp, (int)d.N, rows_sp, (int)C, gr.db2, nullptr, 0, st));
+  // (the following layer's LayerNorm-1 backward may already have produced both: dmlp_in)
+  if (p.dmlp_in != nullptr) dmlp = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(p.dmlp_in));
+  else TRY(scale_cast_sum(dout, 0, id, dmlp, 1, id, p.drop_scale_mlp, (int)d.N, rows_sp, (int)C, gr.db2, nullptr, 0, st));
   TRY(gemm_bf16(linear_dgrad(dmlp, C, p.w2, Hd, rows_sp, C, Hd, dg, Hd, 1), st));
   if (gr.dw2) TRY(gemm_bf16(linear_wgrad(dmlp, C, s.g, Hd, rows_sp, C, Hd, gr.dw2, Hd), side_fork(st, side)));
   {
@@ -466,10 +468,16 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
   }
   if (gr.dwq) TRY(gemm_bf16(linear_wgrad(dq16, C, s.xn1, C, rows_all, C, C, gr.dwq, C), side_fork(st, side)));
   // LN1 backward + residual gradient
-  if (d.P == 0) {
+  if (d.P == 0 && gr.next_dmlp != nullptr && gr.dln1_g != nullptr && gr.dln1_b != nullptr) {
+    // dx is the preceding layer's output gradient: the same pass emits its drop-path-scaled bf16 copy and dense2 bias gradient
+    TRY(layernorm_bwd_aux(dxn1t, xcat, s.mean1, s.rstd1, p.ln1_g, dx1, dx, gr.dln1_g, gr.dln1_b, rows_all, (int)C, gr.next_dmlp,
+                          gr.next_drop_scale, (int)d.N, gr.next_db2, st));
+  } else if (d.P == 0) {
+    SFK_REQUIRE(gr.next_dmlp == nullptr, "layer_backward: next_dmlp needs trainable LayerNorm-1 parameters");
     TRY(layernorm_bwd(dxn1t, 1, xcat, 0, id, s.mean1, s.rstd1, p.ln1_g, dx1, id, dx, 0, id, gr.dln1_g, gr.dln1_b, rows_all, (int)C,
                       st));
   } else {
+    SFK_REQUIRE(gr.next_dmlp == nullptr, "layer_backward: next_dmlp is only available without prompt / cls rows");
     float* dxcat = sc.take<float>(rows_all * C);
     SFK_REQUIRE(sc.off <= scratch_bytes, "layer_backward: scratch arena too small (%zu < %zu)", scratch_bytes, sc.off);
     TRY(layernorm_bwd(dxn1t, 1, xcat, 0, id, s.mean1, s.rstd1, p.ln1_g, dx1, id, dxcat, 0, id, gr.dln1_g, gr.dln1_b, rows_all,

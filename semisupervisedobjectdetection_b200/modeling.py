@@ -324,9 +324,23 @@ class SegformerMixFFN(nn.Module):
 # ---------------------------------------------------------------------------------------------------------------
 # one encoder layer (MS:320-363) -> one libsfk call per direction
 # ---------------------------------------------------------------------------------------------------------------
+class _BwdLink:
+    """Hand-over between the backward passes of two consecutive layers of a stage (no prompt / cls rows).  The LayerNorm-1
+    backward of layer i+1 writes dx = the output gradient of layer i; in the same pass it can emit what layer i's backward
+    would otherwise start with: the drop-path-scaled bf16 copy of that gradient and its column sums (dense2 bias gradient).
+    Layer i+1 fills `dmlp` / `dx_ptr`; layer i takes the copy only if autograd hands it exactly that dx tensor."""
+    __slots__ = ("layer", "drop_mlp", "dmlp", "dx_ptr")
+
+    def __init__(self, layer, drop_mlp):
+        self.layer, self.drop_mlp, self.dmlp, self.dx_ptr = layer, drop_mlp, None, None
+
+
+LAYER_LINK = os.environ.get("SFK_LAYER_LINK", "1") != "0"
+
+
 class _LayerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, front, anchor, layer, H, W, drop_attn, drop_mlp):
+    def forward(ctx, x, front, anchor, layer, H, W, drop_attn, drop_mlp, link_in=None, link_out=None):
         x = ops._chk(x, torch.float32, "hidden_states")
         B, N, C = x.shape
         ptl = 0 if front is None else front.shape[1]
@@ -348,6 +362,7 @@ class _LayerFn(torch.autograd.Function):
                  ops._p(front_out), saved.data_ptr(), saved_bytes, scratch.data_ptr(), scratch.numel(), ops.stream())
         if need_grad:
             ctx.layer, ctx.dims, ctx.saved, ctx.keep, ctx.ptl = layer, dims, saved, (params, keep, drop_attn, drop_mlp), ptl
+            ctx.link_in, ctx.link_out = link_in, link_out
             ctx.save_for_backward(x)
         if front_out is None:
             return out, None
@@ -361,6 +376,15 @@ class _LayerFn(torch.autograd.Function):
         B, N, C = x.shape
         if dout is None:
             dout = torch.zeros_like(x)
+        link_in, link_out = ctx.link_in, ctx.link_out
+        dmlp_in = None
+        if link_out is not None and link_out.dmlp is not None:
+            # the following layer already produced this layer's MixFFN input gradient (and its dense2 bias gradient)
+            if link_out.dx_ptr != dout.data_ptr():
+                raise RuntimeError("SegformerLayer backward: the output gradient is not the tensor the following layer produced "
+                                   "(a second consumer of an intermediate layer output?); set SFK_LAYER_LINK=0 to disable the "
+                                   "cross-layer backward fusion")
+            dmlp_in, link_out.dmlp = link_out.dmlp, None
         dout = ops._chk(dout, torch.float32, "layer grad")
         if dfront_out is not None:
             dfront_out = ops._chk(dfront_out, torch.float32, "front grad")
@@ -373,13 +397,27 @@ class _LayerFn(torch.autograd.Function):
         grads, gkeep = layer._grad_struct()
         dx = torch.empty_like(x)
         dfront = torch.empty(B, ptl, C, device=x.device, dtype=torch.float32) if ptl else None
+        if dmlp_in is not None:
+            params.dmlp_in = dmlp_in.data_ptr()
+        dmlp_next = None
+        if link_in is not None and ptl == 0 and grads.dln1_g and grads.dln1_b:
+            dmlp_next = torch.empty(B * N, C, device=x.device, dtype=torch.bfloat16)
+            db2_prev = ops.grad_buffer(link_in.layer.mlp.dense2.bias)
+            gkeep.append(db2_prev)
+            grads.next_dmlp, grads.next_drop_scale = dmlp_next.data_ptr(), ops._p(link_in.drop_mlp)
+            grads.next_db2 = None if db2_prev is None else db2_prev.data_ptr()
         ops.call("sfk_layer_bwd", ctypes.byref(dims), ctypes.byref(params), ctypes.byref(grads), x.data_ptr(), dout.data_ptr(),
                  ops._p(dfront_out), dx.data_ptr(), ops._p(dfront), ctx.saved.data_ptr(), ctx.saved.numel(), scratch.data_ptr(),
                  scratch.numel(), ops.stream(), None if ws is None else ws.cuda_stream, parity)
+        params.dmlp_in = None
+        if dmlp_next is not None:
+            link_in.dmlp, link_in.dx_ptr = dmlp_next, dx.data_ptr()
         if ws is not None:
             ops.defer_free(ctx.saved)  # the saved activations are still being read by the side-stream wgrad GEMMs
+            if dmlp_in is not None:
+                ops.defer_free(dmlp_in)  # ... and so is the handed-over gradient copy (dense2 wgrad operand)
         ctx.saved = None
-        return dx, dfront, None, None, None, None, None, None
+        return dx, dfront, None, None, None, None, None, None, None, None
 
 
 class SegformerLayer(nn.Module):
@@ -398,6 +436,7 @@ class SegformerLayer(nn.Module):
         self.mlp = SegformerMixFFN(config, in_features=hidden_size, hidden_features=mlp_hidden_size)
         self._anchor = _GradAnchor()
         self._sh, self._sh_key, self._plist = None, None, None
+        self._link_out = None
 
     # -- bf16 shadow weights in GEMM layouts (refreshed when the fp32 masters change) --
     def _params(self):
@@ -510,7 +549,7 @@ class SegformerLayer(nn.Module):
     def drop_prob(self) -> float:
         return self.drop_path.drop_prob if isinstance(self.drop_path, SegformerDropPath) else 0.0
 
-    def _forward_split(self, spatial, front, height, width, scales=None):
+    def _forward_split(self, spatial, front, height, width, scales=None, link_in=None):
         B = spatial.shape[0]
         if scales is None and self.training and self.drop_prob() > 0.0:
             # the same DropPath module is applied twice with independent draws (MS:350,358)
@@ -518,7 +557,10 @@ class SegformerLayer(nn.Module):
         s_attn = scales[0] if scales is not None else None
         s_mlp = scales[1] if scales is not None else None
         anchor = self._anchor.get(self._params(), spatial.device)
-        return _LayerFn.apply(spatial.float(), None if front is None else front.float(), anchor, self, height, width, s_attn, s_mlp)
+        link_out = _BwdLink(self, s_mlp) if (LAYER_LINK and front is None and torch.is_grad_enabled()) else None
+        self._link_out = link_out   # picked up by the encoder loop right after this call
+        return _LayerFn.apply(spatial.float(), None if front is None else front.float(), anchor, self, height, width, s_attn, s_mlp,
+                              link_in if front is None else None, link_out)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -601,6 +643,7 @@ class SegformerEncoder(nn.Module):
                 hidden.register_hook(lambda g, b=bucketer, o=off: b.notify(o))
             block_cls.append(None)
             running_cls = None
+            link = None   # cross-layer backward hand-over (see _BwdLink); restarts at every stage
             pt = self.prompt_tokens[idx]
             ct = self.cls_token[idx]
             for i, layer in enumerate(blk):
@@ -613,7 +656,8 @@ class SegformerEncoder(nn.Module):
                     rows = pt[i] if pt.dim() == 3 else pt
                     front_parts.append(rows.to(hidden.device).float().unsqueeze(0).expand(B, -1, -1))
                 front = torch.cat(front_parts, dim=1).contiguous() if front_parts else None
-                hidden, front_out = layer._forward_split(hidden, front, H, W, dp_scales[layer_no])
+                hidden, front_out = layer._forward_split(hidden, front, H, W, dp_scales[layer_no], link)
+                link = layer._link_out
                 layer_no += 1
                 if ct is not None:
                     running_cls = front_out[:, 0:1, :]  # MS:463-465

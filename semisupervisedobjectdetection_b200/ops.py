@@ -213,9 +213,9 @@ class LayerDims(ctypes.Structure):
 
 
 _PARAM_FIELDS = ("wq", "wkv", "wo", "wsr", "w1", "w2", "bq", "bkv", "bo", "bsr", "b1", "b2", "ln1_g", "ln1_b", "ln2_g", "ln2_b",
-                 "lnsr_g", "lnsr_b", "dw_wt", "dw_b", "drop_scale_attn", "drop_scale_mlp")
+                 "lnsr_g", "lnsr_b", "dw_wt", "dw_b", "drop_scale_attn", "drop_scale_mlp", "dmlp_in")
 _GRAD_FIELDS = ("dwq", "dwk", "dwv", "dwo", "dwsr", "dw1", "dw2", "dbq", "dbk", "dbv", "dbo", "dbsr", "db1", "db2", "dln1_g",
-                "dln1_b", "dln2_g", "dln2_b", "dlnsr_g", "dlnsr_b", "ddw", "ddb")
+                "dln1_b", "dln2_g", "dln2_b", "dlnsr_g", "dlnsr_b", "ddw", "ddb", "next_dmlp", "next_drop_scale", "next_db2")
 
 
 class LayerParams(ctypes.Structure):

@@ -39,7 +39,7 @@ def main():
     if os.environ.get("SFK_GEMM_CLUSTER2") is not None:
         L.check(L.load().sfk_set_option(b"gemm_cluster2", 2 * int(os.environ["SFK_GEMM_CLUSTER2"])))  # 1 -> "whenever possible"
         print("gemm_cluster2 =", os.environ["SFK_GEMM_CLUSTER2"], flush=True)
-    for opt in ("gemm_occ2", "gemm_epi_tma", "gemm_bstat", "gemm_dbg", "gemm_epi_bufs"):
+    for opt in ("gemm_occ2", "gemm_epi_tma", "gemm_bstat", "gemm_dbg", "gemm_epi_bufs", "gemm_krot"):
         if os.environ.get("SFK_" + opt.upper()) is not None:
             L.check(L.load().sfk_set_option(opt.encode(), int(os.environ["SFK_" + opt.upper()])))
             print(opt, "=", os.environ["SFK_" + opt.upper()], flush=True)

@@ -120,7 +120,7 @@ def main():
     ap.add_argument("--as-red", action="store_true", help="time the fwd_res shapes with the in-place reduce-add epilogue instead")
     args = ap.parse_args()
     L.ensure_device()
-    for opt in ("gemm_occ2", "gemm_cluster2", "gemm_epi_tma", "gemm_bstat", "gemm_dbg", "gemm_epi_bufs"):
+    for opt in ("gemm_occ2", "gemm_cluster2", "gemm_epi_tma", "gemm_bstat", "gemm_dbg", "gemm_epi_bufs", "gemm_krot"):
         if os.environ.get("SFK_" + opt.upper()) is not None:
             L.check(L.load().sfk_set_option(opt.encode(), int(os.environ["SFK_" + opt.upper()])))
             print(opt, "=", os.environ["SFK_" + opt.upper()], flush=True)
