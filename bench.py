@@ -243,7 +243,8 @@ def run_sfk(args):
         torch.cuda.synchronize()
 
     lib = L.load()
-    for opt in ("gemm_occ2", "gemm_cluster2", "gemm_bstat", "gemm_epi_tma", "dw_bwd_vec", "sr_tma_patch"):
+    for opt in ("gemm_occ2", "gemm_cluster2", "gemm_bstat", "gemm_epi_tma", "gemm_epi_bufs", "dw_bwd_vec", "sr_tma_patch",
+                "sr_patch_store", "attn_fwd256", "attn_bwd_persist"):
         if os.environ.get("SFK_" + opt.upper()) is not None:
             lib.sfk_set_option(opt.encode(), int(os.environ["SFK_" + opt.upper()]))
     imgs_per_step = (N_LABELED + N_UNLABELED) * world

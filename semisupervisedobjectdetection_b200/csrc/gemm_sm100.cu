@@ -126,6 +126,8 @@ struct GemmKernelParams {
   uint32_t epi_off;        // staging area: 8 warps x epi_bufs x 4 KB
   int epi_bufs;            // staging buffers per epilogue warp (1 | 2)
   int krot;                // rotate each CTA's k-block order (streaming mode)
+  int res_bf16;            // residual rows are bf16 (EPI == 2 only): one 128-byte fetch covers a whole 64-column chunk
+  int out_patch, po_rows_b, po_wo, po_span;   // patch-view store (EPI == 2): patches per sample, ox-row length, sr*C
   uint32_t res_off;        // residual transpose buffers: 8 warps x 4 KB (behind the staging area; only with a residual)
   int do_scale;            // alpha != 1 or per-row scales present
   int epi_warps;           // 8 (320-thread CTA, one per SM) | 4 (192-thread CTA: two CTAs per SM, row-wise epilogue)
@@ -473,14 +475,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       constexpr int CWR = EPI == 2 ? 64 : 32;
       float4 rr[8];
       const int res_r = lane >> 3, res_p = lane & 7;   // row within a 4-row group / 16-byte piece of the 128-byte row segment
+      const bool res16 = EPI == 2 && p.res_bf16 != 0;   // bf16 residual: a 128-byte row segment is a whole 64-column chunk
       auto res_fetch = [&](int c0f, int hf) {
         const int wf = (EPI == 2 && c0f + CWR > p.block_n) ? 32 : CWR;
-        const int cc = 32 * hf + 4 * res_p;
+        const int cc = res16 ? 8 * res_p : 32 * hf + 4 * res_p;
         const bool cok = cc < wf && n0 + c0f + cc < p.N;
-        const float* base = p.residual + (long long)(row0 + res_r) * p.ldr + n0 + c0f + cc;
+        const long long off = (long long)(row0 + res_r) * p.ldr + n0 + c0f + cc;
+        const char* base = reinterpret_cast<const char*>(p.residual) + off * (res16 ? 2 : 4);
+        const long long rstep = 4 * p.ldr * (res16 ? 2 : 4);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          rr[j] = (cok && row0 + res_r + 4 * j < p.M) ? __ldg(reinterpret_cast<const float4*>(base + (long long)(4 * j) * p.ldr))
+          rr[j] = (cok && row0 + res_r + 4 * j < p.M) ? __ldg(reinterpret_cast<const float4*>(base + j * rstep))
                                                       : make_float4(0.f, 0.f, 0.f, 0.f);
       };
       const int c0_first = (wpq == 2 ? (half ^ (trace_tile & 1)) : 0) * CWR;
@@ -539,24 +544,40 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 for (int j = 0; j < 16; ++j) v[j] = p2_mul(v[j], rs2);
               }
               if (has_res) {
-                __syncwarp();   // the previous half's reads of the transpose buffer are done
+                if (!res16 || h == 0) {
+                  __syncwarp();   // the previous reads of the transpose buffer are done
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const uint32_t rw = (uint32_t)(4 * j + res_r);
-                  st_shared_v4(res_buf + rw * 128u + ((((uint32_t)res_p) ^ (rw & 7u)) << 4), __float_as_uint(rr[j].x),
-                               __float_as_uint(rr[j].y), __float_as_uint(rr[j].z), __float_as_uint(rr[j].w));
+                  for (int j = 0; j < 8; ++j) {
+                    const uint32_t rw = (uint32_t)(4 * j + res_r);
+                    st_shared_v4(res_buf + rw * 128u + ((((uint32_t)res_p) ^ (rw & 7u)) << 4), __float_as_uint(rr[j].x),
+                                 __float_as_uint(rr[j].y), __float_as_uint(rr[j].z), __float_as_uint(rr[j].w));
+                  }
+                  __syncwarp();
+                  // fetch the next 128-byte row segments of this tile (this chunk's second half, or the warp's next chunk)
+                  if (!res16 && h + 1 < CW / 32 && 32 * (h + 1) < w) res_fetch(c0, h + 1);
+                  else if (c0 + wpq * CW < p.block_n) res_fetch(c0 + wpq * CW, 0);
                 }
-                __syncwarp();
-                // fetch the next half of this tile (this chunk's second half, or the warp's next chunk)
-                if (h + 1 < CW / 32 && 32 * (h + 1) < w) res_fetch(c0, h + 1);
-                else if (c0 + wpq * CW < p.block_n) res_fetch(c0 + wpq * CW, 0);
-                uint4 r4[8];
+                if (res16) {
+                  uint4 r4[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) r4[j] = ld_shared_v4(res_buf + (uint32_t)lane * 128u + ((((uint32_t)j) ^ ((uint32_t)lane & 7u)) << 4));
+                  for (int j = 0; j < 4; ++j)
+                    r4[j] = ld_shared_v4(res_buf + (uint32_t)lane * 128u + ((((uint32_t)(4 * h + j)) ^ ((uint32_t)lane & 7u)) << 4));
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  v[2 * j] = p2_add(v[2 * j], p2_make_u(r4[j].x, r4[j].y));
-                  v[2 * j + 1] = p2_add(v[2 * j + 1], p2_make_u(r4[j].z, r4[j].w));
+                  for (int j = 0; j < 4; ++j) {
+                    v[4 * j] = p2_add(v[4 * j], p2_from_bf16x2(r4[j].x));
+                    v[4 * j + 1] = p2_add(v[4 * j + 1], p2_from_bf16x2(r4[j].y));
+                    v[4 * j + 2] = p2_add(v[4 * j + 2], p2_from_bf16x2(r4[j].z));
+                    v[4 * j + 3] = p2_add(v[4 * j + 3], p2_from_bf16x2(r4[j].w));
+                  }
+                } else {
+                  uint4 r4[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) r4[j] = ld_shared_v4(res_buf + (uint32_t)lane * 128u + ((((uint32_t)j) ^ ((uint32_t)lane & 7u)) << 4));
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    v[2 * j] = p2_add(v[2 * j], p2_make_u(r4[j].x, r4[j].y));
+                    v[2 * j + 1] = p2_add(v[2 * j + 1], p2_make_u(r4[j].z, r4[j].w));
+                  }
                 }
               }
               if (p.relu) {
@@ -589,6 +610,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             // boxes reaching past M or N are clipped by the TMA unit
             if (p.dbg & 1) {}   // experiment: no stores
             else if (EPI == 1 && p.atomic_add) tma_reduce_add_2d(&tmap_out, stage_buf, n0 + c0, row0);
+            else if (EPI == 2 && p.out_patch) {
+              // scatter through the patch view: these 32 patch rows are (32 / Wo) ox-rows of one sample, the 64 columns one
+              // (kx, c) run of a single ky
+              const int n = n0 + c0;
+              const int bi = row0 / p.po_rows_b, oy0 = (row0 - bi * p.po_rows_b) / p.po_wo;
+              tma_store_5d(&tmap_out, stage_buf, n % p.po_span, n / p.po_span, 0, oy0, bi);
+            }
             else if (EPI == 2 && w == 32) tma_store_2d(&tmap_tail, stage_buf, n0 + c0, row0);
             else tma_store_2d(&tmap_out, stage_buf, n0 + c0, row0);
             tma_store_commit();
@@ -818,6 +846,13 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
     SFK_REQUIRE(g.N == g.b_patch.sr * g.b_patch.sr * g.b_patch.C && g.K == g.b_patch.B * g.b_patch.Ho * g.b_patch.Wo,
                 "gemm: B patch view does not match N=%d K=%d", g.N, g.K);
   }
+  const bool out_patch = g.out_patch.enabled != 0;
+  if (out_patch) {
+    SFK_REQUIRE(g.out_bf16 && !g.atomic_add && patch_view_ok(g.out_patch, 32), "gemm: output patch view needs a bf16 output and whole ox-rows per 32 patches (Wo=%d Ho=%d)",
+                g.out_patch.Wo, g.out_patch.Ho);
+    SFK_REQUIRE(g.N == g.out_patch.sr * g.out_patch.sr * g.out_patch.C && g.M == g.out_patch.B * g.out_patch.Ho * g.out_patch.Wo,
+                "gemm: output patch view does not match M=%d N=%d", g.M, g.N);
+  }
   const bool pair_wanted = !a_patch && !b_patch &&
                            (g_gemm_cluster2 == 2 || (g_gemm_cluster2 == 1 && (double)g.M * g.N * g.K >= 1.0e11 && g.K >= 1024));
   if (pair_wanted && g.M > BLOCK_M && (num_sms() % 2 == 0)) {
@@ -916,6 +951,13 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
   p.epi_tma = epi_tma ? 1 : 0;
   p.epi_bufs = epi_bufs;
   p.krot = (g_gemm_krot && !p.bstat) ? 1 : 0;
+  p.res_bf16 = g.res_bf16 ? 1 : 0;
+  SFK_REQUIRE(!g.res_bf16 || g.residual == nullptr || (epi_tma && g.out_bf16), "gemm: a bf16 residual needs the staged bf16-output epilogue");
+  p.out_patch = out_patch ? 1 : 0;
+  p.po_rows_b = out_patch ? g.out_patch.Ho * g.out_patch.Wo : 1;
+  p.po_wo = out_patch ? g.out_patch.Wo : 1;
+  p.po_span = out_patch ? g.out_patch.sr * g.out_patch.C : 1;
+  SFK_REQUIRE(!out_patch || (epi_tma && p.block_n % 64 == 0), "gemm: output patch view needs the staged epilogue and 64-column chunks (block_n=%d)", p.block_n);
   p.epi_off = 0;
   p.res_off = (uint32_t)GEMM_EPI_WARPS * (uint32_t)epi_bufs * EPI_WARP_BUF;
   p.dbg = g_gemm_dbg;
@@ -1010,7 +1052,7 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   SFK_REQUIRE((reinterpret_cast<uintptr_t>(g.out) & 15) == 0 && ((g.ldo * esz) % 16) == 0,
               "gemm: output must be 16-byte aligned with a 16-byte multiple row pitch");
   SFK_REQUIRE(!(g.atomic_add && g.out_bf16), "gemm: atomic accumulation needs an fp32 output");
-  if (g.residual) SFK_REQUIRE((reinterpret_cast<uintptr_t>(g.residual) & 15) == 0 && (g.ldr % 4) == 0,
+  if (g.residual) SFK_REQUIRE((reinterpret_cast<uintptr_t>(g.residual) & 15) == 0 && (g.ldr % (g.res_bf16 ? 8 : 4)) == 0,
                               "gemm: residual must be 16-byte aligned");
   if (g.bias) SFK_REQUIRE((reinterpret_cast<uintptr_t>(g.bias) & 15) == 0, "gemm: bias must be 16-byte aligned");
 
@@ -1048,6 +1090,16 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   const int epi = !p.epi_tma ? 0 : (g.out_bf16 ? 2 : 1);
   if (epi == 1) {
     rc = make_tmap_2d_any(&tout, g.out, 4, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo * 4, 32, 32, 128);
+    if (rc) return rc;
+    ttail = tout;
+  } else if (epi == 2 && p.out_patch) {
+    const PatchView& v = g.out_patch;
+    const long long W = (long long)v.Wo * v.sr;
+    const uint64_t dims[5] = {(uint64_t)v.sr * v.C, (uint64_t)v.sr, (uint64_t)v.Wo, (uint64_t)v.Ho, (uint64_t)v.B};
+    const uint64_t strides[4] = {(uint64_t)W * v.C * 2, (uint64_t)v.sr * v.C * 2, (uint64_t)v.sr * W * v.C * 2,
+                                 (uint64_t)v.batch_stride * 2};
+    const uint32_t box[5] = {64, 1, (uint32_t)v.Wo, (uint32_t)(32 / v.Wo), 1};
+    rc = make_tmap_5d_bf16(&tout, g.out, dims, strides, box);
     if (rc) return rc;
     ttail = tout;
   } else if (epi == 2) {

@@ -14,6 +14,9 @@ namespace sfk {
 
 // sfk_set_option("sr_tma_patch", 0|1): read the SR conv's patches through a rank-5 TMA view (default) or gather them first
 int g_sr_tma_patch = 1;
+// sfk_set_option("sr_patch_store", 0|1): the SR conv's input-gradient GEMM stores through the patch view (default) or writes the
+// patch-matrix gradient and runs col2im
+int g_sr_patch_store = 1;
 
 namespace {
 
@@ -212,7 +215,7 @@ size_t layer_scratch_bytes(const sfk_layer_dims& dd) {
   size_t b = 0;
   b += sp * d.hidden * 2 * 3;                 // dg, dpre, dh1
   b += sp * d.C * 2 * 2;                      // dmlp, dxn2
-  b += tok * d.C * (4 + 2 + 2 + 4 + 2 + 4 + 2 + 4);  // dx1, da, dctx, dq(f32), dq(bf16), dxn1(f32), dxn1 total(bf16), dxcat
+  b += tok * d.C * (4 + 2 + 2 + 4 + 2 + 4 + 2 + 4 + 2);  // dx1, da, dctx, dq(f32), dq(bf16), dxn1(f32), dxn1 total(bf16), dxcat, dxn1 SR part (bf16)
   b += kv * 2 * d.C * (4 + 2);                // dkv f32 + bf16
   b += kv * d.C * (4 + 2 + 2 + 2);            // dkvn, dsr, dsr compact
   b += (size_t)d.B * d.heads * d.T * 4;       // delta
@@ -398,6 +401,7 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
     else
       TRY(scale_cast(dkv32, 0, id, dkv16, 1, id, nullptr, 1, rows_kv, (int)(2 * C), st));
   }
+  __nv_bfloat16* dxn1_16 = nullptr;   // SR path's contribution to LN1's output gradient when the dgrad GEMM scatters it itself
   // K | V projections
   if (gr.dwk || gr.dwv) {
     cudaStream_t ws = side_fork(st, side);
@@ -439,8 +443,19 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
       // prompt rows feed LN1's output gradient directly
       TRY(scale_cast(dsr, 1, front_map(d.P, d.Nkv), dxn1, 0, front_map(d.P, d.N), nullptr, 1, d.B * d.P, (int)C, st));
     }
-    TRY(gemm_bf16(linear_dgrad(dsr_sp, C, p.wsr, Ksr, rows_red, C, Ksr, dA, Ksr, 1), st));
-    TRY(col2im_nhwc(dA, dxn1, (int)d.B, (int)d.H, (int)d.W, (int)C, (int)d.sr, (int)d.sr, 0, d.T, d.P, 0, st));
+    const PatchView pv_out = sr_patch_view(d);
+    if (d.P == 0 && g_sr_patch_store && patch_view_ok(pv_out, 32) && (Ksr % 64) == 0) {
+      // k == stride: the conv's input gradient is a permutation of dA, so the GEMM's TMA stores scatter it straight into the
+      // [B, H, W, C] gradient (bf16) - no dA buffer, no col2im pass; the Q-projection dgrad below adds it as a bf16 residual
+      dxn1_16 = sc.take<__nv_bfloat16>(rows_all * C);
+      SFK_REQUIRE(sc.off <= scratch_bytes, "layer_backward: scratch arena too small (%zu < %zu)", scratch_bytes, sc.off);
+      GemmDesc g = linear_dgrad(dsr_sp, C, p.wsr, Ksr, rows_red, C, Ksr, dxn1_16, Ksr, 1);
+      g.out_patch = pv_out;
+      TRY(gemm_bf16(g, st));
+    } else {
+      TRY(gemm_bf16(linear_dgrad(dsr_sp, C, p.wsr, Ksr, rows_red, C, Ksr, dA, Ksr, 1), st));
+      TRY(col2im_nhwc(dA, dxn1, (int)d.B, (int)d.H, (int)d.W, (int)C, (int)d.sr, (int)d.sr, 0, d.T, d.P, 0, st));
+    }
     if (gr.dwsr) {
       cudaStream_t ws = side_fork(st, side);  // dsr_sp is final here; patch gather + wgrad + layout fix all run off-path
       cudaError_t e = cudaMemsetAsync(dwsr, 0, (size_t)C * Ksr * sizeof(float), ws);
@@ -463,7 +478,9 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
   // Q projection: dxn1_total = dq · Wq + dxn1
   {
     GemmDesc g = linear_dgrad(dq16, C, p.wq, C, rows_all, C, C, dxn1t, C, 1);
-    g.residual = dxn1; g.ldr = C;
+    if (dxn1_16 != nullptr) { g.residual = reinterpret_cast<const float*>(dxn1_16); g.res_bf16 = 1; }
+    else g.residual = dxn1;
+    g.ldr = C;
     TRY(gemm_bf16(g, st));
   }
   if (gr.dwq) TRY(gemm_bf16(linear_wgrad(dq16, C, s.xn1, C, rows_all, C, C, gr.dwq, C), side_fork(st, side)));

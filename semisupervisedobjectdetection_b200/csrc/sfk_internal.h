@@ -53,6 +53,9 @@ struct GemmDesc {
   int block_n = 0;  // 0 = auto
   PatchView a_patch;   // A (K-major, M = B*Ho*Wo rows, K = sr*sr*C) read through the patch view of `a`
   PatchView b_patch;   // B (MN-major: [K = B*Ho*Wo rows, N = sr*sr*C]) read through the patch view of `b`  (wgrad)
+  PatchView out_patch; // bf16 output [M = B*Ho*Wo patches, N = sr*sr*C] scattered through the patch view of `out` (col2im of a
+                       // k == stride conv's input gradient as part of the store: `out` is the [B, H, W, C] activation gradient)
+  int res_bf16 = 0;    // `residual` points to bf16 [M, ldr] instead of fp32 (bf16 output only)
 };
 
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream);
