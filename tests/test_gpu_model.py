@@ -29,7 +29,9 @@ def test_model_matches_reference_goldens(decode_fold):
 
 
 def test_sr_conv_tma_patch_view_matches_gather():
-    """The implicit-im2col (rank-5 TMA) SR conv operands against the gathered copy on the same inputs (b0, 512x512)."""
+    """Every fused path against the plainer kernel sequence it replaced, one switch at a time (b0, 512x512): the implicit-im2col
+    (rank-5 TMA) SR conv operands vs the gathered copy, the patch-view TMA store of the SR conv's input gradient vs col2im, the
+    cross-layer LayerNorm-1 backward hand-over vs the separate cast pass, the single-pass attention forward vs the chunked one."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "check_model.py"), "patch"], cwd=ROOT, capture_output=True,
                        text=True, timeout=600)
     tail = "\n".join((r.stdout + r.stderr).splitlines()[-20:])
