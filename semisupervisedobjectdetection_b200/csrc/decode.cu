@@ -162,15 +162,19 @@ __global__ void __launch_bounds__(256) upsample_add4_kernel(const __nv_bfloat16*
 // Shared-memory pixel layout: [8 chunks x floats 0..3][8 chunks x floats 4..7], so the 8 threads of a pixel read 128
 // contiguous bytes per LDS.128.
 static constexpr int UPS_CS = 64;
+// sfk_set_option("upsample_sep", 0|1): separable shared-memory upsample-add / transposed upsampling (default) or the direct kernels
+int g_upsample_sep = 1;
 __global__ void __launch_bounds__(256) upsample_add4_sep_kernel(const __nv_bfloat16* __restrict__ z0, UpLevel l1, UpLevel l2, UpLevel l3,
                                                                 const float* __restrict__ bias, __nv_bfloat16* __restrict__ out, int B,
                                                                 int H, int W, int C) {
   pdl_sync();
   extern __shared__ __align__(16) float vrow[];
   constexpr int CS = UPS_CS, K8 = CS / 8;
-  const int y = blockIdx.x % H;
-  const int b = blockIdx.x / H;
-  const int cb = blockIdx.y * CS;
+  // grid = (channel slabs, rows): consecutive blocks are the slabs of ONE row, so the row's 128-byte pieces are requested
+  // together (with rows fastest every block touched one line per 1.5 KB and the kernel sat at 2.5 TB/s of scattered lines)
+  const int y = blockIdx.y % H;
+  const int b = blockIdx.y / H;
+  const int cb = blockIdx.x * CS;
   const int off1 = l1.w, off2 = l1.w + l2.w, wtot = l1.w + l2.w + l3.w;
   constexpr int PX = 256 / K8;
   const int c8 = threadIdx.x % K8;
@@ -243,8 +247,6 @@ __global__ void __launch_bounds__(256) upsample_add4_sep_kernel(const __nv_bfloa
   }
 }
 
-// sfk_set_option("upsample_sep", 0|1): separable shared-memory upsample-add (default) or the direct four-tap kernel
-int g_upsample_sep = 1;
 
 int upsample_add4(const void* z0, const void* z1, int h1, int w1, const void* z2, int h2, int w2, const void* z3, int h3, int w3,
                   const float* bias, void* out, int B, int H, int W, int C, cudaStream_t stream) {
@@ -253,14 +255,14 @@ int upsample_add4(const void* z0, const void* z1, int h1, int w1, const void* z2
   if ((long long)B * H * W == 0) return 0;
   UpLevel l1{(const __nv_bfloat16*)z1, h1, w1}, l2{(const __nv_bfloat16*)z2, h2, w2}, l3{(const __nv_bfloat16*)z3, h3, w3};
   const size_t sep_smem = (size_t)(w1 + w2 + w3) * UPS_CS * sizeof(float);
-  if (g_upsample_sep && sep_smem <= 200 * 1024 && (long long)B * H <= 0x7fffffffLL) {
+  if (g_upsample_sep && sep_smem <= 200 * 1024 && (long long)B * H <= 65535) {
     static size_t attr_bytes = 48 * 1024;
     if (sep_smem > attr_bytes) {
       cudaError_t e = cudaFuncSetAttribute(upsample_add4_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sep_smem);
       SFK_REQUIRE(e == cudaSuccess, "upsample_add4: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
       attr_bytes = sep_smem;
     }
-    launch_k(upsample_add4_sep_kernel, dim3((unsigned)(B * H), (unsigned)((C + UPS_CS - 1) / UPS_CS)), dim3(256), sep_smem, stream,
+    launch_k(upsample_add4_sep_kernel, dim3((unsigned)((C + UPS_CS - 1) / UPS_CS), (unsigned)(B * H)), dim3(256), sep_smem, stream,
              (const __nv_bfloat16*)z0, l1, l2, l3, bias, (__nv_bfloat16*)out, B, H, W, C);
     return check_launch("upsample_add4_sep_kernel");
   }
@@ -347,12 +349,128 @@ __global__ void __launch_bounds__(256) upsample_concat_bwd_kernel(const __nv_bfl
   }
 }
 
+// Separable version of the transposed bilinear gather (default for real down-scaling): a block owns one low-res row (b, yi)
+// and a 64-channel slab.  Phase 1 reduces the contributing hi-res rows VERTICALLY (thread = (hi-res pixel, 8-channel chunk),
+// fp32 registers, four independent 16-byte loads per row step), phase 2 reduces HORIZONTALLY out of shared memory.  The direct
+// kernel above walks the whole (2f x 2f) window per output: (2f)^2 16-byte loads and weight products per 8 outputs - 258 /
+// 285 / 330 us for the three levels of the 16 x 128 x 128 x 768 batch (1.2-1.6 TB/s).
+__global__ void __launch_bounds__(256) upsample_bwd_sep_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ din,
+                                                               int B, int h, int w, int C, int H, int W, long long ld_out, int ch_off) {
+  pdl_sync();
+  extern __shared__ __align__(16) float tmp[];   // [W][CS]: per pixel [8 chunks x floats 0..3][8 chunks x floats 4..7]
+  __shared__ int s_rows[64];
+  __shared__ float s_wy[64];
+  __shared__ int s_nrows;
+  constexpr int CS = UPS_CS, K8 = CS / 8, PX = 256 / K8;
+  const int yi = blockIdx.y % h;
+  const int b = blockIdx.y / h;
+  const int cb = blockIdx.x * CS;
+  if (threadIdx.x == 0) {
+    int n = 0;
+    const float sy = (float)h / (float)H, fy = (float)H / (float)h;
+    int ylo = (int)floorf((yi - 1 + 0.5f) * fy - 0.5f) - 1, yhi = (int)ceilf((yi + 1 + 0.5f) * fy - 0.5f) + 1;
+    if (ylo < 0) ylo = 0;
+    if (yhi > H - 1) yhi = H - 1;
+    for (int y = ylo; y <= yhi && n < 64; ++y) {
+      int y0, y1;
+      float ly;
+      bilinear_src(y, sy, h, y0, y1, ly);
+      float wy = 0.f;
+      if (y0 == yi) wy += 1.f - ly;
+      if (y1 == yi) wy += ly;
+      if (wy != 0.f) { s_rows[n] = y; s_wy[n] = wy; ++n; }
+    }
+    s_nrows = n;
+  }
+  __syncthreads();
+  const int nrows = s_nrows;
+  const int c8 = threadIdx.x % K8;
+  const bool c_ok = cb + c8 * 8 < C;
+  // ---- phase 1: tmp[x][c] = sum_rows wy * dout[row][x][c] ----
+  for (int xb = threadIdx.x / K8; xb < W; xb += 4 * PX) {
+    float acc[4][8];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[u][k] = 0.f;
+    const __nv_bfloat16* base = dout + ((size_t)b * H * W + xb) * ld_out + ch_off + cb + c8 * 8;
+    for (int r = 0; r < nrows; ++r) {
+      const float wy = s_wy[r];
+      const __nv_bfloat16* rowp = base + (size_t)s_rows[r] * W * ld_out;
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        v[u] = (c_ok && xb + u * PX < W) ? *reinterpret_cast<const uint4*>(rowp + (size_t)(u * PX) * ld_out) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t* vp = reinterpret_cast<const uint32_t*>(&v[u]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = unpack_bf16x2(vp[k]);
+          acc[u][2 * k] = fmaf(wy, f.x, acc[u][2 * k]);
+          acc[u][2 * k + 1] = fmaf(wy, f.y, acc[u][2 * k + 1]);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int x = xb + u * PX;
+      if (x < W) {
+        float* dst = tmp + (size_t)x * CS + c8 * 4;
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+        *reinterpret_cast<float4*>(dst + CS / 2) = make_float4(acc[u][4], acc[u][5], acc[u][6], acc[u][7]);
+      }
+    }
+  }
+  __syncthreads();
+  if (!c_ok) return;
+  // ---- phase 2: din[xi][c] = sum_x wx * tmp[x][c] ----
+  const float sx = (float)w / (float)W, fx = (float)W / (float)w;
+  for (int xi = threadIdx.x / K8; xi < w; xi += PX) {
+    int xlo = (int)floorf((xi - 1 + 0.5f) * fx - 0.5f) - 1, xhi = (int)ceilf((xi + 1 + 0.5f) * fx - 0.5f) + 1;
+    if (xlo < 0) xlo = 0;
+    if (xhi > W - 1) xhi = W - 1;
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int x = xlo; x <= xhi; ++x) {
+      int x0, x1;
+      float lx;
+      bilinear_src(x, sx, w, x0, x1, lx);
+      float wx = 0.f;
+      if (x0 == xi) wx += 1.f - lx;
+      if (x1 == xi) wx += lx;
+      if (wx == 0.f) continue;
+      const float* t = tmp + (size_t)x * CS + c8 * 4;
+      const float4 p0 = *reinterpret_cast<const float4*>(t), p1 = *reinterpret_cast<const float4*>(t + CS / 2);
+      acc[0] = fmaf(wx, p0.x, acc[0]); acc[1] = fmaf(wx, p0.y, acc[1]); acc[2] = fmaf(wx, p0.z, acc[2]); acc[3] = fmaf(wx, p0.w, acc[3]);
+      acc[4] = fmaf(wx, p1.x, acc[4]); acc[5] = fmaf(wx, p1.y, acc[5]); acc[6] = fmaf(wx, p1.z, acc[6]); acc[7] = fmaf(wx, p1.w, acc[7]);
+    }
+    uint4 o;
+    o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]);
+    o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+    *reinterpret_cast<uint4*>(din + (((size_t)b * h + yi) * w + xi) * C + cb + c8 * 8) = o;
+  }
+}
+
 int upsample_concat_bwd(const void* dout, void* din, int B, int h, int w, int C, int H, int W, long long ld_out, int ch_off,
                         cudaStream_t stream) {
   SFK_REQUIRE(C % 8 == 0 && ld_out % 8 == 0 && ch_off % 8 == 0, "upsample_concat_bwd: channel counts must be multiples of 8");
   const long long total = (long long)B * h * w * (C / 8);
   if (total == 0) return 0;
   SFK_REQUIRE(H <= 16 * h + 32 || h == H, "upsample_concat_bwd: scale factor too large");
+  const size_t sep_smem = (size_t)W * UPS_CS * sizeof(float);
+  if (g_upsample_sep && !(h == H && w == W) && sep_smem <= 200 * 1024 && (long long)B * h <= 65535) {
+    static size_t attr_bytes = 48 * 1024;
+    if (sep_smem > attr_bytes) {
+      cudaError_t e = cudaFuncSetAttribute(upsample_bwd_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sep_smem);
+      SFK_REQUIRE(e == cudaSuccess, "upsample_concat_bwd: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      attr_bytes = sep_smem;
+    }
+    launch_k(upsample_bwd_sep_kernel, dim3((unsigned)((C + UPS_CS - 1) / UPS_CS), (unsigned)(B * h)), dim3(256), sep_smem, stream,
+             (const __nv_bfloat16*)dout, (__nv_bfloat16*)din, B, h, w, C, H, W, ld_out, ch_off);
+    return check_launch("upsample_bwd_sep_kernel");
+  }
   launch_k(upsample_concat_bwd_kernel, dim3((unsigned)(B * h)), dim3(256), 0, stream, (const __nv_bfloat16*)dout, (__nv_bfloat16*)din, B, h, w,
            C, H, W, ld_out, ch_off);
   return check_launch("upsample_concat_bwd_kernel");
@@ -403,17 +521,28 @@ __global__ void __launch_bounds__(128) bn_partial_kernel(const __nv_bfloat16* __
 }
 
 // mean / rstd (biased variance) + running-stat update with the unbiased variance (nn.BatchNorm2d train mode)
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int nblocks, long long M, int C, float eps, float momentum,
-                                   float* __restrict__ mean, float* __restrict__ rstd, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var) {
+// Block = 32 channels x 8 row lanes: each lane adds every 8th partial row in fp64, the lanes are combined through shared memory.
+// (One thread per channel walking all ~400 partial rows with dependent fp64 adds took 66 us per launch.)
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float* __restrict__ partial, int nblocks, long long M, int C, float eps,
+                                                          float momentum, float* __restrict__ mean, float* __restrict__ rstd,
+                                                          float* __restrict__ running_mean, float* __restrict__ running_var) {
   pdl_sync();
-  const int c = blockIdx.x * 128 + threadIdx.x;
-  if (c >= C) return;
+  __shared__ double sh_s[8][32], sh_q[8][32];
+  const int lc = threadIdx.x & 31, lr = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lc;
   double s = 0.0, q = 0.0;
-  for (int b = 0; b < nblocks; ++b) {
-    s += (double)partial[(long long)b * 2 * C + c];
-    q += (double)partial[(long long)b * 2 * C + C + c];
+  if (c < C) {
+    for (int b = lr; b < nblocks; b += 8) {
+      s += (double)partial[(long long)b * 2 * C + c];
+      q += (double)partial[(long long)b * 2 * C + C + c];
+    }
   }
+  sh_s[lr][lc] = s;
+  sh_q[lr][lc] = q;
+  __syncthreads();
+  if (lr != 0 || c >= C) return;
+#pragma unroll
+  for (int j = 1; j < 8; ++j) { s += sh_s[j][lc]; q += sh_q[j][lc]; }
   const double mu = s / (double)M;
   double var = q / (double)M - mu * mu;
   if (var < 0.0) var = 0.0;
@@ -447,7 +576,7 @@ int bn_batch_stats(const void* x, long long M, int C, float eps, float momentum,
   launch_k(bn_partial_kernel, dim3(dim3(gx, (unsigned)gy)), dim3(128), 0, stream, (const __nv_bfloat16*)x, workspace, M, C, rpb);
   int rc = check_launch("bn_partial_kernel");
   if (rc) return rc;
-  launch_k(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, stream, workspace, (int)gy, M, C, eps, momentum, mean, rstd, running_mean,
+  launch_k(bn_finalize_kernel, dim3((C + 31) / 32), dim3(256), 0, stream, workspace, (int)gy, M, C, eps, momentum, mean, rstd, running_mean,
                                                           running_var);
   return check_launch("bn_finalize_kernel");
 }

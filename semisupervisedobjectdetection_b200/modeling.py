@@ -50,13 +50,30 @@ class BaseModelOutput(_Output):
     _fields = ("last_hidden_state", "hidden_states", "attentions")
 
 
-@dataclass
 class SemanticSegmenterOutput(_Output):
-    loss: Optional[torch.Tensor] = None
-    logits: Optional[torch.Tensor] = None
-    hidden_states: Optional[Tuple[torch.Tensor, ...]] = None
-    attentions: Optional[Tuple[torch.Tensor, ...]] = None
+    """loss / logits / hidden_states / attentions.  `hidden_states` may be given as a zero-argument callable: the NCHW fp32
+    stage maps are then built on first access.  The reference wrapper switches config.output_hidden_states on (SFM:17) but no
+    project script ever reads the maps, and building them eagerly cost 16 layout-copy launches and ~0.9 GB of
+    HBM traffic per teacher-student step."""
     _fields = ("loss", "logits", "hidden_states", "attentions")
+
+    def __init__(self, loss=None, logits=None, hidden_states=None, attentions=None):
+        self.loss, self.logits, self.attentions = loss, logits, attentions
+        self._hidden, self._hidden_grad_mode = hidden_states, torch.is_grad_enabled()
+
+    @property
+    def hidden_states(self):
+        if callable(self._hidden):
+            with torch.set_grad_enabled(self._hidden_grad_mode):   # as if built inside the forward call
+                self._hidden = self._hidden()
+        return self._hidden
+
+    @hidden_states.setter
+    def hidden_states(self, value):
+        self._hidden = value
+
+    def __repr__(self):
+        return f"SemanticSegmenterOutput(loss={self.loss!r}, logits={self.logits!r}, hidden_states=<{'lazy' if callable(self._hidden) else type(self._hidden).__name__}>)"
 
 
 def _versions(params) -> tuple:
@@ -1183,5 +1200,5 @@ class SegformerForSemanticSegmentation(SegformerPreTrainedModel):
             raise NotImplementedError("return_dict=False is not used by any reference script and is not supported")
         with ops.device_of(pixel_values):
             logits, loss, stages, cls_token = self._forward_impl(pixel_values, labels)
-        hidden = tuple(_tokens_to_nchw(t, H, W) for (t, H, W) in stages) if output_hidden_states else None
+        hidden = (lambda: tuple(_tokens_to_nchw(t, H, W) for (t, H, W) in stages)) if output_hidden_states else None
         return SemanticSegmenterOutput(loss=loss, logits=logits, hidden_states=hidden, attentions=None), cls_token
