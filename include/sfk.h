@@ -56,6 +56,9 @@ int sfk_set_option(const char* name, int value);
  * GEMM launch: 0 start, 1 setup done, 2 first TMA issued, 3 first operands landed, 4 last MMA issued, 5 accumulator ready,
  * 6 first tile stored, 7 CTA done.  NULL switches it off. */
 int sfk_debug_gemm_trace(void* device_u64x8);
+/* Debug: after a forward attention launch with sfk_set_option("attn_dbg", 2): SM cycle counts of CTA (0,0,0) at its phase
+ * boundaries (start, setup done, Q/K landed, S ready, row maxima exchanged, P written, O ready, end), copied to 16 host int64. */
+int sfk_debug_attn_trace(long long* host_i64x16);
 
 /* Launch plan sfk_gemm_bf16 would use for this shape, without touching the device (host logic, testable on CPU):
  * out8 = {block_n, splits, pipeline stages, grid (CTAs), mode bits (1 = CTA pair, 2 = B-stationary main loop,

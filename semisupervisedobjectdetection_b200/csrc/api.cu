@@ -6,7 +6,7 @@
 
 using namespace sfk;
 
-namespace sfk { extern int g_gemm_cluster2; extern int g_gemm_occ2; extern int g_gemm_epi_tma; extern int g_gemm_bstat; extern int g_gemm_epi_bufs; extern int g_gemm_max_stages; extern int g_gemm_krot; extern int g_gemm_dbg; extern int g_ln_bwd_ring; extern unsigned long long* g_gemm_trace; void set_dw_bwd_vec(int v); extern int g_sr_tma_patch; extern int g_sr_patch_store; extern int g_upsample_sep; extern int g_attn_bwd_persist; extern int g_attn_fwd256; }
+namespace sfk { extern int g_gemm_cluster2; extern int g_gemm_occ2; extern int g_gemm_epi_tma; extern int g_gemm_bstat; extern int g_gemm_epi_bufs; extern int g_gemm_max_stages; extern int g_gemm_krot; extern int g_gemm_dbg; extern int g_ln_bwd_ring; extern unsigned long long* g_gemm_trace; void set_dw_bwd_vec(int v); extern int g_sr_tma_patch; extern int g_sr_patch_store; extern int g_upsample_sep; extern int g_attn_bwd_persist; extern int g_attn_fwd256; int set_attn_dbg(int v); int get_attn_trace(long long* out16); }
 
 extern "C" {
 
@@ -19,6 +19,7 @@ int sfk_set_option(const char* name, int value) {
   if (name != nullptr && std::string(name) == "sr_patch_store") { sfk::g_sr_patch_store = value ? 1 : 0; return 0; }
   if (name != nullptr && std::string(name) == "gemm_krot") { sfk::g_gemm_krot = value ? 1 : 0; return 0; }
   if (name != nullptr && std::string(name) == "gemm_max_stages") { sfk::g_gemm_max_stages = value; return 0; }
+  if (name != nullptr && std::string(name) == "attn_dbg") return sfk::set_attn_dbg(value);
   if (name != nullptr && std::string(name) == "attn_fwd256") { sfk::g_attn_fwd256 = value ? 1 : 0; return 0; }
   if (name != nullptr && std::string(name) == "gemm_epi_bufs") { sfk::g_gemm_epi_bufs = value >= 2 ? 2 : 1; return 0; }
   if (name != nullptr && std::string(name) == "gemm_dbg") { sfk::g_gemm_dbg = value; return 0; }
@@ -31,6 +32,7 @@ int sfk_set_option(const char* name, int value) {
 }
 
 /* debug: device buffer of >= 8 u64 receiving CTA 0's globaltimer at phase boundaries of every following GEMM (NULL = off) */
+int sfk_debug_attn_trace(long long* host_i64x16) { return sfk::get_attn_trace(host_i64x16); }
 int sfk_debug_gemm_trace(void* device_u64x8) {
   sfk::g_gemm_trace = static_cast<unsigned long long*>(device_u64x8);
   return 0;

@@ -249,11 +249,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 // chunks (S MMA -> softmax -> P V MMA -> rescale, twice) and took 25-30 us for the 640 tiles of a stage-3 layer, ~15 % of
 // either roofline.
 // ------------------------------------------------------------------------------------------------
+__device__ int g_attn_dbg_dev = 0;   // timing experiments only (sfk_set_option("attn_dbg"))
+__device__ long long g_attn_trace[16];   // bit 1 of attn_dbg: CTA (0,0,0) stores clock64 at its phase boundaries
+#define ATT_TRACE(slot)                                                                                   \
+  do {                                                                                                    \
+    if ((g_attn_dbg_dev & 2) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) g_attn_trace[slot] = clock64(); \
+  } while (0)
 template <int D>
 __global__ void __launch_bounds__(288, 2)
 attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                    const __grid_constant__ CUtensorMap tmap_v, const AttFwdParams p) {
   pdl_launch_dependents();
+  if (threadIdx.x == 0) ATT_TRACE(0);
   using Cfg = AttCfg<D>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -282,6 +289,7 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot_gen;
+  if (threadIdx.x == 0) ATT_TRACE(1);
 
   if (warp == 8) {
     if (lane == 0) {
@@ -294,6 +302,7 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       const uint32_t idesc_s = umma_idesc_bf16(128, 256, 0, 0);
       const uint32_t idesc_o = umma_idesc_bf16(128, D, 0, 1);
       mbar_wait(b_qk, 0);
+      ATT_TRACE(2);
       tc_fence_after();
 #pragma unroll
       for (int kk = 0; kk < Cfg::KSTEPS; ++kk)
@@ -301,6 +310,7 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                   umma_smem_desc_lt(sK + kk * 32, 16, 8 * Cfg::RB, Cfg::LT), idesc_s, kk > 0 ? 1u : 0u);
       umma_commit(b_sfull);
       mbar_wait(b_pready, 0);     // all 256 threads have read S and written P (over Q / K)
+      ATT_TRACE(5);
       mbar_wait(b_v, 0);
       tc_fence_after();
 #pragma unroll
@@ -318,7 +328,10 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const bool full = valid == 128;
     mbar_wait(b_sfull, 0);
     tc_fence_after();
+    if (threadIdx.x == 0) ATT_TRACE(3);
     float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    if (g_attn_dbg_dev & 1) m4[0] = 8.f;   // experiment (wrong results): skip the row-maximum pass
+    else
 #pragma unroll
     for (int cc = 0; cc < 128; cc += 32) {
       uint32_t v[32];
@@ -336,6 +349,7 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const float m_half = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
     xmax[h * 128 + r] = m_half;
     asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (threadIdx.x == 0) ATT_TRACE(4);
     const float m_row = fmaxf(m_half, xmax[(h ^ 1) * 128 + r]);
     const float moff = m_row * p.scale_log2;
     float s4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -375,6 +389,7 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     mbar_arrive(b_pready);
     mbar_wait(b_ofull, 0);
     tc_fence_after();
+    if (threadIdx.x == 0) ATT_TRACE(6);
     // every thread arrived on b_pready before the P V MMAs were issued, so both halves' sums are visible here
     const float l_row = xsum[r] + xsum[128 + r];
     const float inv = 1.f / l_row;
@@ -400,11 +415,14 @@ attn_fwd256_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     tc_fence_before();
   }
   __syncthreads();
+  if (threadIdx.x == 0) ATT_TRACE(7);
   if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
 // sfk_set_option("attn_fwd256", 0|1): single-pass forward kernel for Tk <= 256 (default 1)
 int g_attn_fwd256 = 1;
+int set_attn_dbg(int v) { return cudaMemcpyToSymbol(g_attn_dbg_dev, &v, sizeof(int)) == cudaSuccess ? 0 : -1; }
+int get_attn_trace(long long* out16) { return cudaMemcpyFromSymbol(out16, g_attn_trace, 16 * sizeof(long long)) == cudaSuccess ? 0 : -1; }
 
 template <int D>
 static int attn_fwd256_launch(const AttentionDesc& a, cudaStream_t stream) {

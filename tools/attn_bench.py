@@ -22,7 +22,7 @@ def main():
     lib = L.load()
     L.ensure_device()
     CO.lib = lib
-    for opt in ("attn_fwd256", "attn_bwd_persist"):
+    for opt in ("attn_fwd256", "attn_bwd_persist", "attn_dbg"):
         if os.environ.get("SFK_" + opt.upper()) is not None:
             L.check(lib.sfk_set_option(opt.encode(), int(os.environ["SFK_" + opt.upper()])))
             print(opt, "=", os.environ["SFK_" + opt.upper()], flush=True)
@@ -42,6 +42,17 @@ def main():
             L.check(lib.sfk_attention_fwd(q.data_ptr(), C, T * C, kv.data_ptr(), kv.data_ptr() + 2 * C, 2 * C, Tk * 2 * C, o.data_ptr(),
                                           C, T * C, lse.data_ptr(), B, heads, T, Tk, D, sc, L.stream_ptr()))
 
+        if os.environ.get("SFK_ATTN_TRACE"):
+            import ctypes
+            L.check(lib.sfk_set_option(b"attn_dbg", 2))
+            fwd()
+            torch.cuda.synchronize()
+            buf = (ctypes.c_longlong * 16)()
+            L.check(lib.sfk_debug_attn_trace(buf))
+            L.check(lib.sfk_set_option(b"attn_dbg", 0))
+            t = list(buf)
+            names = ["start", "setup", "qk_landed", "s_ready", "max_done", "p_written", "o_ready", "end"]
+            print("TRACE " + name + ": " + " ".join(f"{n}={(t[i] - t[0]) / 1965.0:.2f}us" for i, n in enumerate(names)), flush=True)
         us = time_graph(fwd)
         fl = 4.0 * B * heads * T * Tk * D
         byt = 2.0 * (2 * q.numel() + kv.numel())
