@@ -116,6 +116,11 @@ int sfk_dwconv3x3_gelu_bwd(const void* x, const float* wt, const float* bias, co
                            float* dbias, int B, int H, int W, int C, sfk_stream_t stream);
 int sfk_dw_weight_to_tap(const float* w, float* wt, int C, sfk_stream_t stream);
 int sfk_dw_wgrad_from_tap(const float* dwt, float* dw, int C, sfk_stream_t stream);
+/* All weight-layout permutations of a model in one launch (after an optimiser / EMA step): `table` is a DEVICE array of n
+ * entries; kind 0 = sfk_conv_weight_ohwi (src f32 OIHW [O,I,KH,KW] -> dst bf16 [O, ld], (ky,kx,c) order),
+ * kind 1 = sfk_dw_weight_to_tap (src f32 [O,1,3,3] -> dst f32 [9][O]; I, KH, KW, ld unused). */
+typedef struct sfk_layout_entry { const void* src; void* dst; int kind, O, I, KH, KW, pad; long long ld; } sfk_layout_entry;
+int sfk_weight_layouts_batched(const sfk_layout_entry* table, int n, sfk_stream_t stream);
 
 /* ---- patch gather / scatter for the overlapping patch-embed conv (MS:123-131) and the SR conv (MS:171-173) ---- */
 int sfk_im2col_nhwc(const void* x, void* A, int B, int H, int W, int C, int K, int S, int P, long long tok_stride,

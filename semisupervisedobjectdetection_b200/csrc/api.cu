@@ -115,6 +115,9 @@ int sfk_dwconv3x3_gelu_bwd(const void* x, const float* wt, const float* bias, co
 int sfk_dw_weight_to_tap(const float* w, float* wt, int C, sfk_stream_t stream) {
   return dw_weight_to_tap(w, wt, C, static_cast<cudaStream_t>(stream));
 }
+int sfk_weight_layouts_batched(const sfk_layout_entry* table, int n, sfk_stream_t stream) {
+  return weight_layouts_batched(table, n, static_cast<cudaStream_t>(stream));
+}
 int sfk_dw_wgrad_from_tap(const float* dwt, float* dw, int C, sfk_stream_t stream) {
   return dw_wgrad_from_tap(dwt, dw, C, static_cast<cudaStream_t>(stream));
 }

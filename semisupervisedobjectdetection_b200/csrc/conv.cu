@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "sfk_internal.h"
 #include "colsum_slots.cuh"
+#include "../../include/sfk.h"
 
 namespace sfk {
 
@@ -656,6 +657,37 @@ int dw_weight_to_tap(const float* w, float* wt, int C, cudaStream_t stream) {
   launch_k(dw_weight_to_tap_kernel, dim3((9 * C + 255) / 256), dim3(256), 0, stream, w, wt, C);
   return check_launch("dw_weight_to_tap_kernel");
 }
+// All layout permutations of a model in ONE launch: entry e (blockIdx.y) is either an SR-conv weight (kind 0: OIHW fp32 ->
+// [O, (ky,kx,c)] bf16) or a depthwise weight (kind 1: [C,1,3,3] fp32 -> tap-major [9][C] fp32).  The per-layer versions above
+// cost ~100 tiny launches (and ctypes calls) per forward pass after every optimiser / EMA step.
+static_assert(sizeof(::sfk_layout_entry) == 48, "sfk_layout_entry is mirrored as a 48-byte record by the Python host code");
+__global__ void __launch_bounds__(256) weight_layouts_batched_kernel(const ::sfk_layout_entry* __restrict__ table, int n) {
+  pdl_sync();
+  const ::sfk_layout_entry e = table[blockIdx.y];
+  const long long total = e.kind == 0 ? (long long)e.O * e.I * e.KH * e.KW : 9LL * e.O;
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    if (e.kind == 0) {
+      const int c = (int)(idx % e.I);
+      long long t = idx / e.I;
+      const int kx = (int)(t % e.KW);
+      t /= e.KW;
+      const int ky = (int)(t % e.KH);
+      const long long o = t / e.KH;
+      reinterpret_cast<__nv_bfloat16*>(e.dst)[o * e.ld + ((long long)ky * e.KW + kx) * e.I + c] =
+          __float2bfloat16(reinterpret_cast<const float*>(e.src)[((o * e.I + c) * e.KH + ky) * e.KW + kx]);
+    } else {
+      const int k = (int)(idx / e.O), c = (int)(idx % e.O);
+      reinterpret_cast<float*>(e.dst)[idx] = reinterpret_cast<const float*>(e.src)[c * 9 + k];
+    }
+  }
+}
+int weight_layouts_batched(const void* table_dev, int n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  SFK_REQUIRE(n <= 65535, "weight_layouts_batched: too many entries");
+  launch_k(weight_layouts_batched_kernel, dim3(32, (unsigned)n), dim3(256), 0, stream, static_cast<const ::sfk_layout_entry*>(table_dev), n);
+  return check_launch("weight_layouts_batched_kernel");
+}
+
 int dw_wgrad_from_tap(const float* dwt, float* dw, int C, cudaStream_t stream) {
   launch_k(dw_wgrad_from_tap_kernel, dim3((9 * C + 255) / 256), dim3(256), 0, stream, dwt, dw, C);
   return check_launch("dw_wgrad_from_tap_kernel");

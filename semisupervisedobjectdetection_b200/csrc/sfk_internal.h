@@ -59,6 +59,7 @@ struct GemmDesc {
 };
 
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream);
+int weight_layouts_batched(const void* table_dev /* sfk_layout_entry[n], include/sfk.h */, int n, cudaStream_t stream);
 // launch plan only (no device work): out = {block_n, splits, stages, grid, cta_pair, tmem_cols, smem_bytes, tiles}
 int gemm_plan(const GemmDesc& g, int out[8]);
 

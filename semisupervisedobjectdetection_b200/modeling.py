@@ -641,10 +641,49 @@ class SegformerEncoder(nn.Module):
         self._ddp_bucketer = None        # set by ddp.attach(): overlaps the gradient all-reduce with backward
         self._ddp_stage_offsets = None
 
+    def _refresh_layouts(self):
+        """After an optimiser / EMA step only libsfk's weight epoch has moved: the Linear operands are live views of the flat bf16
+        shadow, and what is left to redo are the layout permutations (SR-conv weights OIHW -> [O,(ky,kx,c)] bf16, depthwise
+        weights -> tap-major).  One batched launch for the whole encoder instead of two tiny launches per layer."""
+        layers = [layer for blk in self.block for layer in blk]
+        pending = []
+        for layer in layers:
+            key = _versions(layer._params())
+            if layer._sh_key == key:
+                continue
+            sh = layer._sh
+            if sh is None or not sh.get("flat", False) or layer._sh_key[-1] != key[-1] or layer._sh_key[:-2] != key[:-2]:
+                return   # first use or weights written through PyTorch: the per-layer path rebuilds everything
+            pending.append((layer, key))
+        if not pending:
+            return
+        entries = []
+        for layer in layers:
+            a, m, sh = layer.attention.self, layer.mlp, layer._sh
+            C = a.hidden_size
+            if a.sr_ratio > 1:
+                sr = a.sr_ratio
+                entries.append((a.sr.weight.data_ptr(), sh["wsr"].data_ptr(), 0, C, C, sr, sr, 0, sr * sr * C))
+            entries.append((m.dwconv.dwconv.weight.data_ptr(), sh["dw_wt"].data_ptr(), 1, m.dense1.out_features, 0, 0, 0, 0, 0))
+        sig = tuple(entries)
+        cached = getattr(self, "_layout_table", None)
+        if cached is None or cached[0] != sig:
+            import numpy as np
+            dt = np.dtype([("src", "<u8"), ("dst", "<u8"), ("kind", "<i4"), ("O", "<i4"), ("I", "<i4"), ("KH", "<i4"), ("KW", "<i4"),
+                           ("pad", "<i4"), ("ld", "<i8")])   # sfk_layout_entry (include/sfk.h)
+            arr = np.array(entries, dtype=dt)
+            table = torch.from_numpy(arr.view(np.uint8).copy()).to(layers[0].layer_norm_1.weight.device)
+            cached = (sig, table)
+            self._layout_table = cached
+        ops.call("sfk_weight_layouts_batched", cached[1].data_ptr(), len(entries), ops.stream())
+        for layer, key in pending:
+            layer._sh_key = key
+
     def _forward_tokens(self, pixel_values):
         """Fast path: returns ([(tokens bf16 [B,N_i,C_i], H_i, W_i)] per stage, cls list | None)."""
         if pixel_values.dim() != 4:
             raise ValueError("pixel_values must be [B, C, H, W]")
+        self._refresh_layouts()
         B = pixel_values.shape[0]
         x_in, is_image = pixel_values.float().contiguous(), True
         Hin, Win = pixel_values.shape[2], pixel_values.shape[3]
