@@ -383,11 +383,13 @@ def run_sfk(args):
         return
     pk = peaks()
     traffic = None
-    try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "gemm_traffic_r1.json")) as f:
-            traffic = json.load(f)
-    except (OSError, ValueError):
-        pass
+    for rel in (("profiles", "r2", "gemm_traffic_r2.json"), ("profiles", "gemm_traffic_r1.json")):   # newest committed ncu pass first
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), *rel)) as f:
+                traffic = json.load(f)
+            break
+        except (OSError, ValueError):
+            pass
     achieved_tf = prof["flops"] / (prof["ms"] * 1e-3) / 1e12 if prof.get("ms") else None
     gemm_share = prof["ms"] / ms_serial if prof.get("ms") else None
     cpu = time_oracle(1, 0, budget_s=60.0) if world == 1 and not args.no_cpu_baseline else None

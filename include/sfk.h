@@ -45,11 +45,20 @@ int sfk_profile_gemm_end(double* total_ms, double* total_flops, long long* launc
 /* After sfk_profile_gemm_end: one CSV line per profiled GEMM launch (M,N,K,flags,microseconds). */
 int sfk_profile_gemm_dump(const char* path);
 
-/* Tuning switches: "gemm_epi_tma" (default 1) = staged TMA-store / reduce-add epilogue; "gemm_bstat" (default 1) = weight tile resident
- * in shared memory for K <= 512 GEMMs; "gemm_dbg" = experiment bits (timing only); "gemm_cluster2" = CTA-pair (tcgen05 cta_group::2, 256-row MMA, B split across the pair) GEMM tiles:
- * 0 never, 1 (default) for large problems (M*N*K >= 1e11, K >= 1024), 2 whenever the shape allows; "gemm_occ2" (default 1) = two co-resident CTAs per SM for K <= 512 GEMMs; "dw_bwd_vec" (2 | 4, default 4)
- * = channels per thread of the depthwise-conv backward kernel; "attn_bwd_persist" (default 1) = persistent evenly split attention backward; "sr_tma_patch" (default 1) = the SR conv's GEMMs read their
- * k == stride patches through a rank-5 TMA view of the activation (implicit im2col) instead of a gathered copy. */
+/* Tuning switches (name: default = meaning):
+ *  "gemm_epi_tma": 1 = staged TMA-store / reduce-add epilogue;  "gemm_epi_bufs": 2 = staging buffers per epilogue warp;
+ *  "gemm_bstat": 1 = weight tile resident in shared memory (automatic for K <= 128, on request up to K = 512);
+ *  "gemm_cluster2": 1 = CTA-pair tiles (tcgen05 cta_group::2, 256-row MMA, B split across the pair): 0 never, 1 for large
+ *      problems (M*N*K >= 1e11, K >= 1024), 2 whenever the shape allows;
+ *  "gemm_occ2": 0 = light CTAs, two per SM, for K <= 512;  "gemm_krot": 0 = per-CTA rotated k-block order;
+ *  "gemm_max_stages": 0 = cap on the operand ring depth (experiments);  "gemm_dbg": 0 = timing-only experiment bits
+ *      (1 no stores, 2 no proxy fence, 4 no operand loads, 8 no MMAs, 16 no tiles; results are wrong by construction);
+ *  "dw_bwd_vec": 4 = channels per thread of the depthwise-conv backward kernel (2 | 4);
+ *  "attn_bwd_persist": 1 = persistent evenly split attention backward;  "attn_fwd256": 1 = single-pass forward for Tk <= 256;
+ *  "attn_dbg": 0 = experiment bits (1 skip the row-maximum pass, 2 record sfk_debug_attn_trace);
+ *  "sr_tma_patch": 1 = the SR conv's GEMMs read their k == stride patches through a rank-5 TMA view (implicit im2col);
+ *  "sr_patch_store": 1 = the SR conv's input-gradient GEMM stores through the same view (no col2im pass);
+ *  "upsample_sep": 1 = separable shared-memory up/down-sampling kernels of the folded decode head. */
 int sfk_set_option(const char* name, int value);
 
 /* Debug aid: device buffer (>= 256 x uint64; slots 8.. hold per-tile timelines, see tools/check_gemm.py trace) receiving CTA 0's globaltimer (ns) at the phase boundaries of each following
