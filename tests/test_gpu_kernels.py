@@ -18,13 +18,15 @@ def _run(script, group, timeout=600, env=None):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("group", ["nt", "nn", "tn", "epi"])
+@pytest.mark.parametrize("group", ["nt", "nn", "tn", "epi", "v2"])
 def test_gemm_tcgen05_layouts(group):
+    """v2: every epilogue combination (bias, per-sample scale, fp32 residual through the coalesced transpose path, ReLU, bf16 /
+    fp32 out, split-K reduce-add) on full, ragged and multi-column-tile shapes, B-stationary and streaming main loops."""
     _run("check_gemm.py", group)
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("group", ["nt", "nn", "tn", "epi"])
+@pytest.mark.parametrize("group", ["nt", "nn", "tn", "epi", "v2"])
 def test_gemm_cta_pair_layouts(group):
     """Same cases through the CTA-pair (tcgen05 cta_group::2, 2-CTA cluster) kernel, forced on for every eligible shape."""
     _run("check_gemm.py", group, env={"SFK_GEMM_CLUSTER2": "1"})

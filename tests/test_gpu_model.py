@@ -112,6 +112,26 @@ def test_train_one_epoch_matches_oracle_adam_step():
     assert torch.equal(named[k].detach().cpu(), sd[k])
 
 
+def test_weight_layouts_after_optimizer_step_match_a_fresh_model():
+    """After an optimiser step only libsfk's weight epoch moves and the encoder refreshes the SR-conv / depthwise weight layouts
+    with ONE batched launch (sfk_weight_layouts_batched).  A fresh model loaded from the stepped state dict rebuilds every shadow
+    through the per-layer path; both must produce bit-identical logits (same kernels, same bf16 operands)."""
+    w, ocfg, sd = _b0_wrapper()
+    x = synth.uniform01("step/x", (2, 3, 64, 64))
+    mask = (synth.uniform01("step/mask", (2, 64, 64)) > 0.7).float()
+    for _ in range(2):   # the second step's forward runs on layouts refreshed by the batched launch
+        w.train_one_epoch(x, mask)
+    w.model.eval()
+    with torch.no_grad():
+        got = w.model(pixel_values=x.cuda())[0].logits.clone()
+        w2, _, _ = _b0_wrapper()
+        w2.load_state_dict(w.state_dict())
+        w2.optimizer.sync_shadow()
+        w2.model.eval()
+        want = w2.model(pixel_values=x.cuda())[0].logits
+    assert torch.equal(got, want), float((got - want).abs().max())
+
+
 def test_ema_update_and_hard_reset():
     from semisupervisedobjectdetection_b200.optim import ema_update
     t, _, _ = _b0_wrapper()
