@@ -244,7 +244,7 @@ def run_sfk(args):
 
     lib = L.load()
     for opt in ("gemm_occ2", "gemm_cluster2", "gemm_bstat", "gemm_epi_tma", "gemm_epi_bufs", "dw_bwd_vec", "sr_tma_patch",
-                "sr_patch_store", "attn_fwd256", "attn_bwd_persist"):
+                "sr_patch_store", "attn_fwd256", "attn_bwd_persist", "fwd_kv_overlap", "upsample_sep"):
         if os.environ.get("SFK_" + opt.upper()) is not None:
             lib.sfk_set_option(opt.encode(), int(os.environ["SFK_" + opt.upper()]))
     imgs_per_step = (N_LABELED + N_UNLABELED) * world
@@ -325,6 +325,8 @@ def run_sfk(args):
     # ---- roofline leg: ONE extra step (outside the timed region) with the side streams off, so that the CUDA events around
     # each GEMM launch time that kernel alone on the GPU instead of a kernel sharing SMs with the teacher / wgrad streams ----
     ops.WGRAD_OVERLAP = False
+    fwd_kv_overlap = int(os.environ.get("SFK_FWD_KV_OVERLAP", "1"))
+    lib.sfk_set_option(b"fwd_kv_overlap", 0)   # ... nor with the K/V branch of its own layer on the auxiliary forward stream
     step(dev_l, dev_u, dev_gt, overlap=False)  # settle the single-stream scratch arenas
     barrier()
     if rank == 0:
@@ -352,6 +354,7 @@ def run_sfk(args):
         except OSError:
             pass
     ops.WGRAD_OVERLAP = True
+    lib.sfk_set_option(b"fwd_kv_overlap", fwd_kv_overlap)
     clocks = sampler.stop() if sampler else None
     # ---- the same step with the decode head's literal sequence (no algebraic fold), reported next to the headline ----
     from semisupervisedobjectdetection_b200 import modeling as MD

@@ -58,7 +58,9 @@ int sfk_profile_gemm_dump(const char* path);
  *  "attn_dbg": 0 = experiment bits (1 skip the row-maximum pass, 2 record sfk_debug_attn_trace);
  *  "sr_tma_patch": 1 = the SR conv's GEMMs read their k == stride patches through a rank-5 TMA view (implicit im2col);
  *  "sr_patch_store": 1 = the SR conv's input-gradient GEMM stores through the same view (no col2im pass);
- *  "upsample_sep": 1 = separable shared-memory up/down-sampling kernels of the folded decode head. */
+ *  "upsample_sep": 1 = separable shared-memory up/down-sampling kernels of the folded decode head;
+ *  "fwd_kv_overlap": 1 = sfk_layer_fwd runs the K/V branch (SR conv -> LayerNorm -> K|V projection) on an auxiliary stream next
+ *      to the Q projection, whose grid is capped to the SMs the SR conv's GEMM leaves free (joined before attention). */
 int sfk_set_option(const char* name, int value);
 
 /* Debug aid: device buffer (>= 256 x uint64; slots 8.. hold per-tile timelines, see tools/check_gemm.py trace) receiving CTA 0's globaltimer (ns) at the phase boundaries of each following

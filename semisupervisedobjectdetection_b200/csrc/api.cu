@@ -6,7 +6,7 @@
 
 using namespace sfk;
 
-namespace sfk { extern int g_gemm_cluster2; extern int g_gemm_occ2; extern int g_gemm_epi_tma; extern int g_gemm_bstat; extern int g_gemm_epi_bufs; extern int g_gemm_max_stages; extern int g_gemm_krot; extern int g_gemm_dbg; extern int g_ln_bwd_ring; extern unsigned long long* g_gemm_trace; void set_dw_bwd_vec(int v); extern int g_sr_tma_patch; extern int g_sr_patch_store; extern int g_upsample_sep; extern int g_attn_bwd_persist; extern int g_attn_fwd256; int set_attn_dbg(int v); int get_attn_trace(long long* out16); }
+namespace sfk { extern int g_gemm_cluster2; extern int g_gemm_occ2; extern int g_gemm_epi_tma; extern int g_gemm_bstat; extern int g_gemm_epi_bufs; extern int g_gemm_max_stages; extern int g_gemm_krot; extern int g_gemm_dbg; extern int g_ln_bwd_ring; extern unsigned long long* g_gemm_trace; void set_dw_bwd_vec(int v); extern int g_sr_tma_patch; extern int g_sr_patch_store; extern int g_fwd_kv_overlap; extern int g_upsample_sep; extern int g_attn_bwd_persist; extern int g_attn_fwd256; int set_attn_dbg(int v); int get_attn_trace(long long* out16); }
 
 extern "C" {
 
@@ -16,6 +16,7 @@ int sfk_set_option(const char* name, int value) {
   if (name != nullptr && std::string(name) == "gemm_epi_tma") { sfk::g_gemm_epi_tma = value ? 1 : 0; return 0; }
   if (name != nullptr && std::string(name) == "gemm_bstat") { sfk::g_gemm_bstat = value ? 1 : 0; return 0; }
   if (name != nullptr && std::string(name) == "upsample_sep") { sfk::g_upsample_sep = value ? 1 : 0; return 0; }
+  if (name != nullptr && std::string(name) == "fwd_kv_overlap") { sfk::g_fwd_kv_overlap = value ? 1 : 0; return 0; }
   if (name != nullptr && std::string(name) == "sr_patch_store") { sfk::g_sr_patch_store = value ? 1 : 0; return 0; }
   if (name != nullptr && std::string(name) == "gemm_krot") { sfk::g_gemm_krot = value ? 1 : 0; return 0; }
   if (name != nullptr && std::string(name) == "gemm_max_stages") { sfk::g_gemm_max_stages = value; return 0; }

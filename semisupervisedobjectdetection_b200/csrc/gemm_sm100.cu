@@ -1017,6 +1017,7 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
   } else {
     const long long slots = (long long)num_sms() * (light ? 2 : 1);
     grid = (int)(units < slots ? units : slots);
+    if (g.max_ctas > 0 && grid > g.max_ctas) grid = g.max_ctas;
   }
   // per-CTA unit stride of the round-robin deal, in mixed-radix digits over (splits, n_tiles): TileIter adds them with carries
   p.units = (int)units;

@@ -6,6 +6,9 @@
 // The residual stream is fp32, GEMM operands bf16, accumulation fp32.  Activations needed by backward live in a
 // caller-provided `saved` arena; everything else in a reusable `scratch` arena.  Parameter gradients are accumulated
 // straight into the caller's fp32 gradient buffers (split-K red.global.add), there is no separate "+=" pass.
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 #include "sfk_internal.h"
 #include "../../include/sfk.h"
@@ -17,6 +20,11 @@ int g_sr_tma_patch = 1;
 // sfk_set_option("sr_patch_store", 0|1): the SR conv's input-gradient GEMM stores through the patch view (default) or writes the
 // patch-matrix gradient and runs col2im
 int g_sr_patch_store = 1;
+// sfk_set_option("fwd_kv_overlap", 0|1): forward runs the K/V branch (SR conv -> LayerNorm -> K|V projection) on an auxiliary
+// stream next to the Q projection.  The SR conv's GEMM has only M / 128 x 2 tiles (64 CTAs at 16 tiles of 512 x 512): alone it
+// leaves 84 of the 148 SMs idle for its whole 20-k-block main loop.  The Q projection's persistent grid is capped to exactly
+// those SMs (GEMM CTAs own an SM's shared memory, so the two kernels are co-resident iff their grids add up to <= 148).
+int g_fwd_kv_overlap = 1;
 
 namespace {
 
@@ -158,6 +166,25 @@ static int side_end(cudaStream_t side, int parity) {
   return 0;
 }
 
+// auxiliary stream + fork / join events per caller stream (created on first use; the library allocates no device memory)
+struct FwdAux {
+  cudaStream_t s = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static std::mutex g_aux_mu;
+static std::map<cudaStream_t, FwdAux> g_aux;
+static FwdAux* fwd_aux(cudaStream_t main) {
+  std::lock_guard<std::mutex> lock(g_aux_mu);
+  auto it = g_aux.find(main);
+  if (it != g_aux.end()) return &it->second;
+  FwdAux a;
+  if (cudaStreamCreateWithFlags(&a.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess)
+    return nullptr;
+  return &(g_aux[main] = a);
+}
+
 #define TRY(expr)            \
   do {                       \
     int _rc = (expr);        \
@@ -245,32 +272,55 @@ int layer_forward(const sfk_layer_dims& dd, const sfk_layer_params& p, const flo
   }
   // LN1 over all rows
   TRY(layernorm_fwd(xcat, 0, id, p.ln1_g, p.ln1_b, s.xn1, 1, s.mean1, s.rstd1, rows_all, (int)C, 1e-5f, st));
-  // Q
-  TRY(gemm_bf16(linear_fwd(s.xn1, C, p.wq, C, rows_all, C, C, p.bq, s.q, C, 1), st));
-  // spatial reduction
+  // The K/V branch (SR conv -> LayerNorm -> K|V projection) depends only on xn1: with a spatial reduction it runs on an
+  // auxiliary stream next to the Q projection (see g_fwd_kv_overlap) and is joined before the attention kernel.
+  GemmDesc gq = linear_fwd(s.xn1, C, p.wq, C, rows_all, C, C, p.bq, s.q, C, 1);
+  cudaStream_t kvs = st;
+  FwdAux* aux = nullptr;
+  GemmDesc gsr;
+  __nv_bfloat16* A = nullptr;
+  bool sr_gather = false;
   if (d.sr > 1) {
     const long long Ksr = d.sr * d.sr * C;
-    __nv_bfloat16* A = sc.take<__nv_bfloat16>(d.B * d.Nkv * Ksr);
+    A = sc.take<__nv_bfloat16>(d.B * d.Nkv * Ksr);
     SFK_REQUIRE(sc.off <= scratch_bytes, "layer_forward: scratch arena too small");
     // k == stride conv as a GEMM over the patch view of xn1: TMA tiles the rank-5 strided tensor directly (implicit
     // im2col); the gather kernel is only the fallback for grids whose ox-rows do not tile a 128-row block
     const PatchView pv = sr_patch_view(d);
-    GemmDesc g;
     if (patch_view_ok(pv, 128)) {
-      g = linear_fwd(s.xn1 + d.P * C, Ksr, p.wsr, Ksr, d.B * d.Nkv, C, Ksr, p.bsr, s.sr_out, C, 0);
-      g.a_patch = pv;
+      gsr = linear_fwd(s.xn1 + d.P * C, Ksr, p.wsr, Ksr, d.B * d.Nkv, C, Ksr, p.bsr, s.sr_out, C, 0);
+      gsr.a_patch = pv;
     } else {
-      TRY(im2col_nhwc(s.xn1, A, (int)d.B, (int)d.H, (int)d.W, (int)C, (int)d.sr, (int)d.sr, 0, d.T, d.P, st));
-      g = linear_fwd(A, Ksr, p.wsr, Ksr, d.B * d.Nkv, C, Ksr, p.bsr, s.sr_out, C, 0);
+      sr_gather = true;
+      gsr = linear_fwd(A, Ksr, p.wsr, Ksr, d.B * d.Nkv, C, Ksr, p.bsr, s.sr_out, C, 0);
     }
-    g.out_map = kv_spatial_map(d);
-    TRY(gemm_bf16(g, st));
+    gsr.out_map = kv_spatial_map(d);
+    if (g_fwd_kv_overlap) {
+      int plan[8];
+      const int free_sms = gemm_plan(gsr, plan) == 0 ? num_sms() - plan[3] : 0;   // plan[3] = the SR GEMM's grid
+      if (free_sms >= num_sms() / 4 && (aux = fwd_aux(st)) != nullptr) {
+        SFK_REQUIRE(cudaEventRecord(aux->fork, st) == cudaSuccess && cudaStreamWaitEvent(aux->s, aux->fork, 0) == cudaSuccess,
+                    "layer_forward: stream fork failed");
+        kvs = aux->s;
+        gq.max_ctas = free_sms;
+      }
+    }
+  }
+  // Q
+  TRY(gemm_bf16(gq, st));
+  // spatial reduction
+  if (d.sr > 1) {
+    if (sr_gather) TRY(im2col_nhwc(s.xn1, A, (int)d.B, (int)d.H, (int)d.W, (int)C, (int)d.sr, (int)d.sr, 0, d.T, d.P, kvs));
+    TRY(gemm_bf16(gsr, kvs));
     if (d.P > 0)  // prompt rows bypass the conv but do go through the SR LayerNorm (MS:194-205)
-      TRY(scale_cast(s.xn1, 1, front_map(d.P, d.N), s.sr_out, 0, front_map(d.P, d.Nkv), nullptr, 1, d.B * d.P, (int)C, st));
-    TRY(layernorm_fwd(s.sr_out, 0, id, p.lnsr_g, p.lnsr_b, s.kvn, 1, s.mean_sr, s.rstd_sr, rows_kv, (int)C, 1e-5f, st));
+      TRY(scale_cast(s.xn1, 1, front_map(d.P, d.N), s.sr_out, 0, front_map(d.P, d.Nkv), nullptr, 1, d.B * d.P, (int)C, kvs));
+    TRY(layernorm_fwd(s.sr_out, 0, id, p.lnsr_g, p.lnsr_b, s.kvn, 1, s.mean_sr, s.rstd_sr, rows_kv, (int)C, 1e-5f, kvs));
   }
   // K | V in one GEMM
-  TRY(gemm_bf16(linear_fwd(s.kvn, C, p.wkv, C, rows_kv, 2 * C, C, p.bkv, s.kv, 2 * C, 1), st));
+  TRY(gemm_bf16(linear_fwd(s.kvn, C, p.wkv, C, rows_kv, 2 * C, C, p.bkv, s.kv, 2 * C, 1), kvs));
+  if (kvs != st)
+    SFK_REQUIRE(cudaEventRecord(aux->join, kvs) == cudaSuccess && cudaStreamWaitEvent(st, aux->join, 0) == cudaSuccess,
+                "layer_forward: stream join failed");
   // fused attention
   {
     AttentionDesc a;

@@ -56,6 +56,7 @@ struct GemmDesc {
   PatchView out_patch; // bf16 output [M = B*Ho*Wo patches, N = sr*sr*C] scattered through the patch view of `out` (col2im of a
                        // k == stride conv's input gradient as part of the store: `out` is the [B, H, W, C] activation gradient)
   int res_bf16 = 0;    // `residual` points to bf16 [M, ldr] instead of fp32 (bf16 output only)
+  int max_ctas = 0;    // > 0: cap on the persistent grid (leave SMs to a GEMM running concurrently on another stream)
 };
 
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream);

@@ -157,6 +157,7 @@ def run_patch_parity():
       sr_patch_store SR conv input gradient scattered by the dgrad GEMM's TMA stores (+ bf16 residual in the Q dgrad) vs col2im
       layer_link     LayerNorm-1 backward emitting the preceding layer's bf16 MixFFN gradient + dense2 bias gradient vs its own pass
       attn_fwd256    single-pass attention forward (Tk <= 256) vs the chunked online-softmax kernel
+      fwd_kv_overlap K/V branch of the forward pass on an auxiliary stream next to the Q projection vs one stream
     Backward-only switches must leave the logits unchanged and the gradients equal to bf16-rounding noise."""
     from semisupervisedobjectdetection_b200 import _lib as L
     from semisupervisedobjectdetection_b200 import modeling as M
@@ -179,6 +180,8 @@ def run_patch_parity():
     base = run()
     ok = True
     for name, tol_logits, tol_grad in [("sr_tma_patch", 1e-5, 1e-3), ("sr_patch_store", 1e-6, 4e-3), ("layer_link", 1e-6, 1e-3),
+                                       ("fwd_kv_overlap", 0.0, 1e-3),   # same kernels on two streams: identical logits
+
                                        # two kernels that round the softmax numerators to bf16 against different maxima
                                        # (per-chunk running maximum vs whole-row maximum): bf16-level differences
                                        ("attn_fwd256", 1e-2, 2e-2)]:
