@@ -326,7 +326,7 @@ def run_sfk(args):
     # each GEMM launch time that kernel alone on the GPU instead of a kernel sharing SMs with the teacher / wgrad streams ----
     ops.WGRAD_OVERLAP = False
     fwd_kv_overlap = int(os.environ.get("SFK_FWD_KV_OVERLAP", "1"))
-    lib.sfk_set_option(b"fwd_kv_overlap", 0)   # ... nor with the K/V branch of its own layer on the auxiliary forward stream
+    lib.sfk_set_option(b"fwd_kv_overlap", 0)   # ... nor with the K/V branch of its own layer on the auxiliary stream
     step(dev_l, dev_u, dev_gt, overlap=False)  # settle the single-stream scratch arenas
     barrier()
     if rank == 0:

@@ -9,6 +9,9 @@
 // (teacher forward: no column sums; weight-gradient stream: GEMMs, patch gathers, layout fixes).  Every kernel starts with
 // griddepcontrol.wait, so on that one stream the static slot area is never shared by two running kernels.  Two models
 // running backward concurrently on different streams of ONE process are not supported (one process per GPU).
+// The one sanctioned exception is the layer's auxiliary stream (layer.cu: the K/V chain of backward next to the dq cast): the
+// area has two BANKS, kernels launched on an auxiliary stream use bank 1.  The bank travels in bits 16+ of the `ns` argument
+// every slot-using kernel already has (colsum_num_slots(V, sharers, bank) packs it, colsum_commit unpacks it).
 #pragma once
 #include "common.cuh"
 
@@ -17,19 +20,21 @@ namespace sfk {
 static constexpr int COLSUM_SLOT_FLOATS = 1 << 18;   // 1 MiB of static device memory
 static constexpr int COLSUM_MAX_GX = 64;
 
+static constexpr int COLSUM_BANK_FLOATS = COLSUM_SLOT_FLOATS / 2;
+
 static __device__ float g_colsum_slots[COLSUM_SLOT_FLOATS];
-static __device__ unsigned int g_colsum_ticket[COLSUM_MAX_GX];
+static __device__ unsigned int g_colsum_ticket[2 * COLSUM_MAX_GX];
 
 // host helper: number of slot copies for V virtual columns and `sharers` blocks per column
-inline int colsum_num_slots(long long V, long long sharers) {
-  long long ns = COLSUM_SLOT_FLOATS / (V > 0 ? V : 1);
+inline int colsum_num_slots(long long V, long long sharers, int bank = 0) {
+  long long ns = COLSUM_BANK_FLOATS / (V > 0 ? V : 1);
   // 8 copies: ~300-600 blocks per launch leave 40-75 same-address atomics per slot word (spread over the kernel's duration),
   // while the last block's fold - L2 round trips at the very end of the kernel, nothing left to overlap them - shrinks 8x
   // against the first version's 64 (measured: stage-3 layer backward 552 -> 500 us, eight slot-using kernels per layer)
   if (ns > 8) ns = 8;
   if (ns > sharers) ns = sharers;
   if (ns < 1) ns = 1;
-  return (int)ns;
+  return (int)ns | ((bank & 1) << 16);
 }
 
 // Device: called by ALL threads of the block (contains __syncthreads).
@@ -42,7 +47,11 @@ template <typename Write>
 __device__ __forceinline__ void colsum_commit(const float* sh, int v0, int nv, int V, int ns, unsigned share_id, unsigned sharers,
                                               int ticket, Write write) {
   __shared__ unsigned s_last;
-  float* slot = g_colsum_slots + (size_t)(share_id % ns) * V + v0;
+  const int bank = ns >> 16;
+  ns &= 0xffff;
+  float* bank_slots = g_colsum_slots + (size_t)bank * COLSUM_BANK_FLOATS;
+  ticket += bank * COLSUM_MAX_GX;
+  float* slot = bank_slots + (size_t)(share_id % ns) * V + v0;
   for (int i = threadIdx.x; i < nv; i += blockDim.x) atomicAdd(slot + i, sh[i]);
   __threadfence();
   __syncthreads();
@@ -51,7 +60,7 @@ __device__ __forceinline__ void colsum_commit(const float* sh, int v0, int nv, i
   if (!s_last) return;
   __threadfence();
   for (int i = threadIdx.x; i < nv; i += blockDim.x) {
-    float* p = g_colsum_slots + v0 + i;
+    float* p = bank_slots + v0 + i;
     float part[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains: the loads of a column are all in flight together
     int s = 0;
     for (; s + 4 <= ns; s += 4) {

@@ -13,6 +13,20 @@
 
 namespace sfk {
 
+// auxiliary streams created by layer.cu: kernels launched on them use the second column-sum slot bank
+static std::mutex g_aux_streams_mu;
+static std::vector<cudaStream_t> g_aux_streams;
+void register_aux_stream(cudaStream_t s) {
+  std::lock_guard<std::mutex> lock(g_aux_streams_mu);
+  g_aux_streams.push_back(s);
+}
+int colsum_bank(cudaStream_t s) {
+  std::lock_guard<std::mutex> lock(g_aux_streams_mu);
+  for (cudaStream_t a : g_aux_streams)
+    if (a == s) return 1;
+  return 0;
+}
+
 static thread_local char g_err[1024] = "";
 
 void set_error(const char* fmt, ...) {

@@ -25,6 +25,8 @@ int g_sr_patch_store = 1;
 // leaves 84 of the 148 SMs idle for its whole 20-k-block main loop.  The Q projection's persistent grid is capped to exactly
 // those SMs (GEMM CTAs own an SM's shared memory, so the two kernels are co-resident iff their grids add up to <= 148).
 int g_fwd_kv_overlap = 1;
+// (The same trick in backward - the K/V chain next to the dq cast - was built and measured: 47.5 vs 47.3 ms/step, no gain; it
+// needed a second bank of the column-sum slot area, which colsum_slots.cuh keeps for kernels launched on an auxiliary stream.)
 
 namespace {
 
@@ -182,6 +184,7 @@ static FwdAux* fwd_aux(cudaStream_t main) {
   if (cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming) != cudaSuccess)
     return nullptr;
+  register_aux_stream(a.s);   // its slot-using kernels take the second column-sum bank (colsum_slots.cuh)
   return &(g_aux[main] = a);
 }
 

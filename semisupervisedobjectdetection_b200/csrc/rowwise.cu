@@ -457,7 +457,7 @@ static int ln_bwd_ring_launch(const void* dy, const void* x, const float* mean, 
   const size_t red_bytes = (size_t)9 * 2 * C * sizeof(float);
   if (smem < red_bytes) smem = red_bytes;
   const bool want_aux = aux != nullptr || aux_colsum != nullptr;
-  const int ns = colsum_num_slots((want_aux ? 3 : 2) * C, grid);
+  const int ns = colsum_num_slots((want_aux ? 3 : 2) * C, grid, colsum_bank(stream));
 #define LAUNCH_RING(AUXF, RESF)                                                                                               \
   do {                                                                                                                         \
     cudaFuncSetAttribute(ln_bwd_ring_kernel<TDx, NCH, AUXF, RESF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
@@ -500,7 +500,7 @@ static int layernorm_bwd_impl(const void* dy, int dy_bf16, const void* x, int x_
   rows_per_block = (rows_per_block + 7) / 8 * 8;
   const long long grid = (rows + rows_per_block - 1) / rows_per_block;
   const size_t smem = (size_t)9 * 2 * C * sizeof(float);
-  const int ns = colsum_num_slots((aux != nullptr ? 3 : 2) * C, grid);
+  const int ns = colsum_num_slots((aux != nullptr ? 3 : 2) * C, grid, colsum_bank(stream));
 #define LAUNCH_NA(TD, TX, TO, NCH, AUXF)                                                                                \
   if (smem > 48 * 1024) cudaFuncSetAttribute(ln_bwd_kernel<TD, TX, TO, NCH, AUXF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   launch_k(ln_bwd_kernel<TD, TX, TO, NCH, AUXF>, dim3((unsigned)grid), dim3(256), smem, stream, (const TD*)dy, (const TX*)x, x_map, mean, rstd, gamma, \
@@ -739,7 +739,7 @@ int scale_cast_sum(const void* x, int x_bf16, RowMap in_map, void* y, int y_bf16
     if (rows_per_scale <= 0) rows_per_scale = 1;
     if (colsum0 != nullptr && colsum1 == nullptr) { colsum1 = colsum0; split = C; }
     SFK_REQUIRE(colsum0 == nullptr || C <= COLSUM_SLOT_FLOATS, "scale_cast: C=%d too wide for fused sums", C);
-    const int nsf = colsum_num_slots(C, gy);
+    const int nsf = colsum_num_slots(C, gy, colsum_bank(stream));
     dim3 gridf(1, (unsigned)gy);
 #define LAUNCHF(TI, TO)                                                                                                        \
   launch_k(scale_cast_fast_kernel<TI, TO>, dim3(gridf), dim3(threads), 0, stream, (const TI*)x, (TO*)y, scale, (unsigned)rows_per_scale, \
@@ -763,7 +763,7 @@ int scale_cast_sum(const void* x, int x_bf16, RowMap in_map, void* y, int y_bf16
   if (rows_per_scale <= 0) rows_per_scale = 1;
   if (colsum0 != nullptr && colsum1 == nullptr) { colsum1 = colsum0; split = C; }
   SFK_REQUIRE(colsum0 == nullptr || (gx <= COLSUM_MAX_GX && C <= COLSUM_SLOT_FLOATS), "scale_cast: C=%d too wide for fused sums", C);
-  const int ns = colsum_num_slots(C, gy);
+  const int ns = colsum_num_slots(C, gy, colsum_bank(stream));
   dim3 grid(gx, (unsigned)gy);
 #define LAUNCH(TI, TO)                                                                                                       \
   launch_k(scale_cast_kernel<TI, TO>, dim3(grid), dim3(256), 0, stream, (const TI*)x, in_map, (TO*)y, out_map, scale, rows_per_scale, rows, C4, \

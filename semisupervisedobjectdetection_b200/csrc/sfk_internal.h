@@ -59,6 +59,9 @@ struct GemmDesc {
   int max_ctas = 0;    // > 0: cap on the persistent grid (leave SMs to a GEMM running concurrently on another stream)
 };
 
+// column-sum slot bank of a stream (colsum_slots.cuh): 1 for the layer's auxiliary streams (registered by layer.cu), else 0
+void register_aux_stream(cudaStream_t s);
+int colsum_bank(cudaStream_t s);
 int gemm_bf16(const GemmDesc& g, cudaStream_t stream);
 int weight_layouts_batched(const void* table_dev /* sfk_layout_entry[n], include/sfk.h */, int n, cudaStream_t stream);
 // launch plan only (no device work): out = {block_n, splits, stages, grid, cta_pair, tmem_cols, smem_bytes, tiles}
