@@ -473,6 +473,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       // (The first version let each thread read its own row: 32 cache lines per load instruction, 2560 L1 tag cycles per
       // 128 x 160 tile - the epilogue of the residual GEMMs alone took 6.6 us more than the bf16 ones, profiles/r2.)
       constexpr int CWR = EPI == 2 ? 64 : 32;
+      // first row of this warp's 32 rows in the residual / output tensors (row maps with period % 32 == 0 keep them consecutive)
+      const long long res_row0 = gemm_map_row((long long)row0, p.res_map);
+      const int out_row0 = (int)gemm_map_row((long long)row0, p.out_map);
       float4 rr[8];
       const int res_r = lane >> 3, res_p = lane & 7;   // row within a 4-row group / 16-byte piece of the 128-byte row segment
       const bool res16 = EPI == 2 && p.res_bf16 != 0;   // bf16 residual: a 128-byte row segment is a whole 64-column chunk
@@ -480,7 +483,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int wf = (EPI == 2 && c0f + CWR > p.block_n) ? 32 : CWR;
         const int cc = res16 ? 8 * res_p : 32 * hf + 4 * res_p;
         const bool cok = cc < wf && n0 + c0f + cc < p.N;
-        const long long off = (long long)(row0 + res_r) * p.ldr + n0 + c0f + cc;
+        const long long off = (res_row0 + res_r) * p.ldr + n0 + c0f + cc;
         const char* base = reinterpret_cast<const char*>(p.residual) + off * (res16 ? 2 : 4);
         const long long rstep = 4 * p.ldr * (res16 ? 2 : 4);
 #pragma unroll
@@ -609,7 +612,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           if (lane == 0) {
             // boxes reaching past M or N are clipped by the TMA unit
             if (p.dbg & 1) {}   // experiment: no stores
-            else if (EPI == 1 && p.atomic_add) tma_reduce_add_2d(&tmap_out, stage_buf, n0 + c0, row0);
+            else if (row0 >= p.M) {}   // mapped tensors are taller than M: rows past the problem must not be written
+            else if (EPI == 1 && p.atomic_add) tma_reduce_add_2d(&tmap_out, stage_buf, n0 + c0, out_row0);
             else if (EPI == 2 && p.out_patch) {
               // scatter through the patch view: these 32 patch rows are (32 / Wo) ox-rows of one sample, the 64 columns one
               // (kx, c) run of a single ky
@@ -617,8 +621,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               const int bi = row0 / p.po_rows_b, oy0 = (row0 - bi * p.po_rows_b) / p.po_wo;
               tma_store_5d(&tmap_out, stage_buf, n % p.po_span, n / p.po_span, 0, oy0, bi);
             }
-            else if (EPI == 2 && w == 32) tma_store_2d(&tmap_tail, stage_buf, n0 + c0, row0);
-            else tma_store_2d(&tmap_out, stage_buf, n0 + c0, row0);
+            else if (EPI == 2 && w == 32) tma_store_2d(&tmap_tail, stage_buf, n0 + c0, out_row0);
+            else tma_store_2d(&tmap_out, stage_buf, n0 + c0, out_row0);
             tma_store_commit();
           }
         }
@@ -865,8 +869,13 @@ static int gemm_make_plan(const GemmDesc& g, GemmKernelParams& p, int& grid, siz
   p.cluster2 = pair_bn > 0 ? 1 : 0;
 
   // epilogue mode: TMA tile stores need identity row maps (prompt-token remaps keep the per-thread path)
+  // Row maps (prompt / cls rows in front of every sample's spatial tokens) whose period is a multiple of 32 keep each epilogue
+  // warp's 32 rows inside one sample: the mapped rows are still 32 consecutive rows, so tile stores and the coalesced residual
+  // fetch only need the mapped index of their first row.  Other maps keep the per-thread path.
+  auto map_ok = [](const RowMap& m) { return m.period == 0 ? true : (m.period % 32 == 0 && m.extra >= 0); };
   const bool maps_identity = g.out_map.period == 0 && g.out_map.offset == 0 && g.res_map.period == 0 && g.res_map.offset == 0;
-  bool epi_tma = g_gemm_epi_tma && maps_identity;
+  bool epi_tma = g_gemm_epi_tma && map_ok(g.out_map) && map_ok(g.res_map) && (maps_identity || g.M % 32 == 0) &&
+                 !(g.out_patch.enabled && !maps_identity);
   int epi_bufs = epi_tma ? (g_gemm_epi_bufs >= 2 ? 2 : 1) : 1;
   const uint32_t res_bytes = (epi_tma && g.residual != nullptr) ? (uint32_t)GEMM_EPI_WARPS * EPI_WARP_BUF : 0u;
   uint32_t stage_bytes_epi = epi_tma ? (uint32_t)GEMM_EPI_WARPS * (uint32_t)epi_bufs * EPI_WARP_BUF + res_bytes : 0u;
@@ -1089,8 +1098,14 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
   memset(&tout, 0, sizeof(tout));
   memset(&ttail, 0, sizeof(ttail));
   const int epi = !p.epi_tma ? 0 : (g.out_bf16 ? 2 : 1);
+  // rows of the output tensor as the tile stores see it: the mapped index of the last row + 1
+  long long out_rows = g.M;
+  if (g.out_map.period > 0 || g.out_map.offset != 0) {
+    const long long last = (long long)g.M - 1;
+    out_rows = last + (g.out_map.period > 0 ? (last / g.out_map.period) * g.out_map.extra : 0) + g.out_map.offset + 1;
+  }
   if (epi == 1) {
-    rc = make_tmap_2d_any(&tout, g.out, 4, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo * 4, 32, 32, 128);
+    rc = make_tmap_2d_any(&tout, g.out, 4, (uint64_t)g.N, (uint64_t)out_rows, (uint64_t)g.ldo * 4, 32, 32, 128);
     if (rc) return rc;
     ttail = tout;
   } else if (epi == 2 && p.out_patch) {
@@ -1104,9 +1119,9 @@ int gemm_bf16(const GemmDesc& g, cudaStream_t stream) {
     if (rc) return rc;
     ttail = tout;
   } else if (epi == 2) {
-    rc = make_tmap_2d_any(&tout, g.out, 2, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo * 2, 64, 32, 128);
+    rc = make_tmap_2d_any(&tout, g.out, 2, (uint64_t)g.N, (uint64_t)out_rows, (uint64_t)g.ldo * 2, 64, 32, 128);
     if (rc) return rc;
-    rc = make_tmap_2d_any(&ttail, g.out, 2, (uint64_t)g.N, (uint64_t)g.M, (uint64_t)g.ldo * 2, 32, 32, 64);
+    rc = make_tmap_2d_any(&ttail, g.out, 2, (uint64_t)g.N, (uint64_t)out_rows, (uint64_t)g.ldo * 2, 32, 32, 64);
     if (rc) return rc;
   }
 
