@@ -266,3 +266,27 @@ def test_from_pretrained_warns_on_random_init_and_loads_local_checkpoints(tmp_pa
         got = cls.from_pretrained("nvidia/mit-b0", num_labels=1)
     assert float(got.segformer.encoder.patch_embeddings[0].proj.weight.mean()) == 0.5
     assert float(got.decode_head.linear_fuse.weight.abs().max()) < 0.5       # head not in the dump: random init kept
+
+
+def test_semantic_segmenter_output_builds_hidden_states_lazily():
+    """The wrapper switches output_hidden_states on like the reference (SFM:17) but no script reads the maps: they are built on
+    first access, once, under the grad mode of the forward call; attribute / index / tuple access keep working."""
+    import torch
+    from semisupervisedobjectdetection_b200.modeling import SemanticSegmenterOutput
+    calls = []
+
+    def build():
+        calls.append(torch.is_grad_enabled())
+        return (torch.ones(1), torch.zeros(1))
+
+    with torch.no_grad():
+        out = SemanticSegmenterOutput(loss=None, logits=torch.full((1,), 2.0), hidden_states=build)
+    assert calls == []                                   # nothing materialised by the forward call
+    assert float(out.logits) == 2.0 and out["logits"] is out.logits
+    hs = out.hidden_states
+    assert calls == [False] and len(hs) == 2             # built once, with grad disabled as in the forward call
+    assert out.hidden_states is hs and calls == [False]
+    assert out.to_tuple()[0] is out.logits and out.to_tuple()[1] is hs and out[1] is hs
+    out.hidden_states = None
+    assert out.hidden_states is None and out.to_tuple() == (out.logits,)
+    assert SemanticSegmenterOutput(logits=torch.ones(1)).hidden_states is None
