@@ -494,10 +494,18 @@ int attention_fwd(const AttentionDesc& a, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------------
 // delta[b, h, t] = sum_d dO[b,t,h*D+d] * O[b,t,h*D+d]
 // ------------------------------------------------------------------------------------------------
+// Optionally also zero-fills the gradient accumulators of the main kernel (dq: same (b, t, h, chunk) geometry as this pass; dk|dv:
+// a flat block, grid-stride) - two memset launches per layer less.
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dO,
                                                          float* __restrict__ delta, int B, int T, int heads, int D,
-                                                         long long ld, long long batch_stride) {
+                                                         long long ld, long long batch_stride, float* __restrict__ zq,
+                                                         long long zq_ld, long long zq_batch_stride, float4* __restrict__ zkv,
+                                                         long long zkv_n4) {
   pdl_sync();
+  if (zkv != nullptr) {
+    const long long nthreads = (long long)gridDim.x * 256;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < zkv_n4; i += nthreads) zkv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   // one thread per (b, t, h, 8-element chunk); reduce across the D/8 chunk lanes with shuffles
   const int chunks = D / 8;
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
@@ -513,6 +521,11 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
     const long long off = b * batch_stride + (long long)t * ld + h * D + ch * 8;
     const uint4 a = *reinterpret_cast<const uint4*>(o + off);
     const uint4 g = *reinterpret_cast<const uint4*>(dO + off);
+    if (zq != nullptr) {
+      float4* z = reinterpret_cast<float4*>(zq + b * zq_batch_stride + (long long)t * zq_ld + h * D + ch * 8);
+      z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     const uint32_t* ap = reinterpret_cast<const uint32_t*>(&a);
     const uint32_t* gp = reinterpret_cast<const uint32_t*>(&g);
 #pragma unroll
@@ -1066,9 +1079,20 @@ static int attn_bwd_launch(const AttentionBwdDesc& a, cudaStream_t stream) {
   // delta = rowsum(dO * O)
   {
     const long long total = (long long)a.B * a.T * a.heads * (D / 8);
+    float* zq = nullptr;
+    float4* zkv = nullptr;
+    long long zkv_n4 = 0;
+    if (a.zero_fill) {
+      SFK_REQUIRE(a.dv == a.dk + a.ld_dkv / 2 && a.dkv_batch_stride == (long long)a.Tk * a.ld_dkv &&
+                  (reinterpret_cast<uintptr_t>(a.dk) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.dq) & 15) == 0,
+                  "attention_bwd: zero_fill needs dk|dv as one contiguous 16-byte aligned [B, Tk, ld_dkv] block");
+      zq = a.dq;
+      zkv = reinterpret_cast<float4*>(a.dk);
+      zkv_n4 = (long long)a.B * a.Tk * a.ld_dkv / 4;
+    }
     launch_k(attn_delta_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, (const __nv_bfloat16*)a.o, (const __nv_bfloat16*)a.dO,
                                                                            a.delta, a.B, a.T, a.heads, D, a.ldo,
-                                                                           a.o_batch_stride);
+                                                                           a.o_batch_stride, zq, a.ld_dq, a.dq_batch_stride, zkv, zkv_n4);
     rc = check_launch("attn_delta_kernel");
     if (rc) return rc;
   }

@@ -433,11 +433,10 @@ int layer_backward(const sfk_layer_dims& dd, const sfk_layer_params& p, const sf
   TRY(gemm_bf16(linear_dgrad(da, C, p.wo, C, rows_all, C, C, dctx, C, 1), st));
   if (gr.dwo) TRY(gemm_bf16(linear_wgrad(da, C, s.ctx, C, rows_all, C, C, gr.dwo, C), side_fork(st, side)));
   {
-    cudaError_t e = cudaMemsetAsync(dq32, 0, (size_t)rows_all * C * sizeof(float), st);
-    SFK_REQUIRE(e == cudaSuccess, "layer_backward: memset failed");
-    e = cudaMemsetAsync(dkv32, 0, (size_t)rows_kv * 2 * C * sizeof(float), st);
-    SFK_REQUIRE(e == cudaSuccess, "layer_backward: memset failed");
+    // dq32 / dkv32 are accumulated with red.add by the attention kernel: its delta pre-pass zero-fills them (dq32 is [B, T, C]
+    // with C == heads * D, so every element is covered) instead of two memset launches
     AttentionBwdDesc a;
+    a.zero_fill = 1;
     a.B = (int)d.B; a.heads = (int)d.heads; a.T = (int)d.T; a.Tk = (int)d.Tk; a.D = (int)d.D;
     a.scale = 1.0f / sqrtf((float)d.D);
     a.q = s.q; a.ldq = C; a.q_batch_stride = d.T * C;

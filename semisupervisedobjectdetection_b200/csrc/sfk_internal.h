@@ -83,7 +83,9 @@ struct AttentionDesc {
 struct AttentionBwdDesc : AttentionDesc {
   const void* dO = nullptr;      // bf16, addressed like o
   float* delta = nullptr;        // workspace [B, heads, T]
-  float* dq = nullptr;           // fp32, += (caller zero-fills)
+  int zero_fill = 0;             // 1: the delta pre-pass zero-fills dq and dk|dv itself (dq: heads*D columns of every row; dk|dv: one
+                                 // contiguous [B, Tk, ld_dkv] block starting at dk) - the caller then skips its two memsets
+  float* dq = nullptr;           // fp32, += (caller zero-fills unless zero_fill)
   long long ld_dq = 0, dq_batch_stride = 0;
   float* dk = nullptr;           // fp32, += (caller zero-fills)
   float* dv = nullptr;
