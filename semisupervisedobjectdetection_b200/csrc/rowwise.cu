@@ -400,48 +400,38 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_ring_kernel(const __nv_bfloat16
   }
   cp_async_wait<0>();
   __syncthreads();   // the ring is dead: its shared memory now carries the cross-warp column reductions
-  float* red = reinterpret_cast<float*>(ring_raw);   // [8][2C] partials + [2C] totals  (9 * 2C floats <= ring size, checked on the host)
-  if (AUX && aux_colsum != nullptr) {
-    float* my = red + warp * 2 * C;
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const unsigned ci = lane + 32 * k;
-      if (ci < nchunk) *reinterpret_cast<float4*>(my + ci * 4) = cacc[k];
-    }
-    __syncthreads();
-    float* tot = red + 8 * 2 * C;
-    for (unsigned c = threadIdx.x; c < C; c += 256) {
-      float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) t += red[w * 2 * C + c];
-      tot[c] = t;
-    }
-    __syncthreads();
-    colsum_commit(tot, 2 * C, C, 3 * C, ns, blockIdx.x, gridDim.x, 1, [&](int c, float sum) { aux_colsum[c - 2 * C] += sum; });
-    __syncthreads();
-  }
-  if (dgamma == nullptr) return;
-  float* my = red + warp * 2 * C;
+  // ONE reduction + commit for all column sums of the pass: [dgamma | dbeta | aux column sums].  (Two separate commits meant two
+  // device-scope fences, two ticket rounds and two last-block folds at the tail of a kernel that is 18 us long for the
+  // 4096-row SR LayerNorm.)
+  const bool csum = AUX && aux_colsum != nullptr;
+  if (dgamma == nullptr && !csum) return;
+  const unsigned W3 = csum ? 3 * C : 2 * C;
+  float* red = reinterpret_cast<float*>(ring_raw);   // [8][W3] partials + [W3] totals  (9 * W3 floats <= ring size, checked on the host)
+  float* my = red + warp * W3;
 #pragma unroll
   for (int k = 0; k < NCH; ++k) {
     const unsigned ci = lane + 32 * k;
     if (ci < nchunk) {
       *reinterpret_cast<float4*>(my + ci * 4) = gacc[k];
       *reinterpret_cast<float4*>(my + C + ci * 4) = bacc[k];
+      if (AUX) {
+        if (csum) *reinterpret_cast<float4*>(my + 2 * C + ci * 4) = cacc[k];
+      }
     }
   }
   __syncthreads();
-  float* tot = red + 8 * 2 * C;
-  for (unsigned c = threadIdx.x; c < 2 * C; c += 256) {
+  float* tot = red + 8 * W3;
+  for (unsigned c = threadIdx.x; c < W3; c += 256) {
     float t = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) t += red[w * 2 * C + c];
+    for (int w = 0; w < 8; ++w) t += red[w * W3 + c];
     tot[c] = t;
   }
   __syncthreads();
-  colsum_commit(tot, 0, 2 * C, AUX ? 3 * C : 2 * C, ns, blockIdx.x, gridDim.x, 0, [&](int c, float sum) {
-    if (c < (int)C) dgamma[c] += sum;
-    else dbeta[c - C] += sum;
+  colsum_commit(tot, 0, (int)W3, AUX ? 3 * C : 2 * C, ns, blockIdx.x, gridDim.x, 0, [&](int c, float sum) {
+    if (c < (int)C) { if (dgamma != nullptr) dgamma[c] += sum; }
+    else if (c < 2 * (int)C) { if (dbeta != nullptr) dbeta[c - C] += sum; }
+    else aux_colsum[c - 2 * C] += sum;
   });
 }
 
@@ -454,9 +444,9 @@ static int ln_bwd_ring_launch(const void* dy, const void* x, const float* mean, 
   rows_per_block = (rows_per_block + 7) / 8 * 8;
   const long long grid = (rows + rows_per_block - 1) / rows_per_block;
   size_t smem = (size_t)8 * (NCH <= 3 ? 3 : 2) * NCH * 1280;
-  const size_t red_bytes = (size_t)9 * 2 * C * sizeof(float);
-  if (smem < red_bytes) smem = red_bytes;
   const bool want_aux = aux != nullptr || aux_colsum != nullptr;
+  const size_t red_bytes = (size_t)9 * (want_aux ? 3 : 2) * C * sizeof(float);
+  if (smem < red_bytes) smem = red_bytes;
   const int ns = colsum_num_slots((want_aux ? 3 : 2) * C, grid, colsum_bank(stream));
 #define LAUNCH_RING(AUXF, RESF)                                                                                               \
   do {                                                                                                                         \
