@@ -503,21 +503,20 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
                                                          long long zkv_n4) {
   pdl_sync();
   if (zkv != nullptr) {
-    const long long nthreads = (long long)gridDim.x * 256;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < zkv_n4; i += nthreads) zkv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const long long nthreads = (long long)gridDim.x * gridDim.y * 256;
+    for (long long j = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 256 + threadIdx.x; j < zkv_n4; j += nthreads)
+      zkv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  // one thread per (b, t, h, 8-element chunk); reduce across the D/8 chunk lanes with shuffles
-  const int chunks = D / 8;
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long total = (long long)B * T * heads * chunks;
+  // one thread per (t, h, 8-element chunk) of sample blockIdx.y; reduce across the D/8 chunk lanes with shuffles.  32-bit index
+  // arithmetic (the first version decoded a flat 64-bit index with four long-long divisions per thread).
+  const unsigned chunks = (unsigned)D / 8;                      // 8 | 4: a power of two
+  const unsigned per_sample = (unsigned)T * (unsigned)heads * chunks;
+  const unsigned i = blockIdx.x * 256u + threadIdx.x;
+  const long long b = blockIdx.y;
+  const unsigned th = i / chunks, ch = i % chunks;
+  const unsigned t = th / (unsigned)heads, h = th - t * (unsigned)heads;
   float s = 0.f;
-  long long bth = idx / chunks;
-  const int ch = (int)(idx % chunks);
-  if (idx < total) {
-    const int h = (int)(bth % heads);
-    const long long bt = bth / heads;
-    const int t = (int)(bt % T);
-    const long long b = bt / T;
+  if (i < per_sample) {
     const long long off = b * batch_stride + (long long)t * ld + h * D + ch * 8;
     const uint4 a = *reinterpret_cast<const uint4*>(o + off);
     const uint4 g = *reinterpret_cast<const uint4*>(dO + off);
@@ -529,19 +528,13 @@ __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __
     const uint32_t* ap = reinterpret_cast<const uint32_t*>(&a);
     const uint32_t* gp = reinterpret_cast<const uint32_t*>(&g);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 x = unpack_bf16x2(ap[i]), y = unpack_bf16x2(gp[i]);
+    for (int k = 0; k < 4; ++k) {
+      const float2 x = unpack_bf16x2(ap[k]), y = unpack_bf16x2(gp[k]);
       s += x.x * y.x + x.y * y.y;
     }
   }
-  for (int o2 = chunks >> 1; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
-  if (idx < total && ch == 0) {
-    const int h = (int)(bth % heads);
-    const long long bt = bth / heads;
-    const int t = (int)(bt % T);
-    const long long b = bt / T;
-    delta[(b * heads + h) * T + t] = s;
-  }
+  for (unsigned o2 = chunks >> 1; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+  if (i < per_sample && ch == 0) delta[(b * heads + h) * T + t] = s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1078,7 +1071,8 @@ static int attn_bwd_launch(const AttentionBwdDesc& a, cudaStream_t stream) {
 
   // delta = rowsum(dO * O)
   {
-    const long long total = (long long)a.B * a.T * a.heads * (D / 8);
+    const long long total = (long long)a.T * a.heads * (D / 8);   // threads per sample; grid.y = sample
+    SFK_REQUIRE(total < (1LL << 31), "attention_bwd: sample too large for the delta pass");
     float* zq = nullptr;
     float4* zkv = nullptr;
     long long zkv_n4 = 0;
@@ -1090,7 +1084,7 @@ static int attn_bwd_launch(const AttentionBwdDesc& a, cudaStream_t stream) {
       zkv = reinterpret_cast<float4*>(a.dk);
       zkv_n4 = (long long)a.B * a.Tk * a.ld_dkv / 4;
     }
-    launch_k(attn_delta_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, (const __nv_bfloat16*)a.o, (const __nv_bfloat16*)a.dO,
+    launch_k(attn_delta_kernel, dim3((unsigned)((total + 255) / 256), (unsigned)a.B), dim3(256), 0, stream, (const __nv_bfloat16*)a.o, (const __nv_bfloat16*)a.dO,
                                                                            a.delta, a.B, a.T, a.heads, D, a.ldo,
                                                                            a.o_batch_stride, zq, a.ld_dq, a.dq_batch_stride, zkv, zkv_n4);
     rc = check_launch("attn_delta_kernel");
