@@ -500,7 +500,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       const long long row = (long long)row0 + lane;
       const bool row_ok = row < p.M;
       float rscale = p.alpha;
-      if (p.row_scale != nullptr && row_ok) rscale *= p.row_scale[row / p.rows_per_scale];
+      if (p.row_scale != nullptr && row_ok) rscale *= p.row_scale[(unsigned)row / (unsigned)p.rows_per_scale];   // M < 2^31: 32-bit division
       const p2 rs2 = p2_splat(rscale);
       const uint32_t tmem_acc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (p.tmem_cols >> 1);
       if (EPI != 0) {

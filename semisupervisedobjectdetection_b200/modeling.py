@@ -665,6 +665,7 @@ class SegformerEncoder(nn.Module):
                 sr = a.sr_ratio
                 entries.append((a.sr.weight.data_ptr(), sh["wsr"].data_ptr(), 0, C, C, sr, sr, 0, sr * sr * C))
             entries.append((m.dwconv.dwconv.weight.data_ptr(), sh["dw_wt"].data_ptr(), 1, m.dense1.out_features, 0, 0, 0, 0, 0))
+        assert all(e[3] * max(e[4], 1) * max(e[5], 1) * max(e[6], 1) < 2 ** 31 for e in entries)   # the kernel indexes in 32 bits
         sig = tuple(entries)
         cached = getattr(self, "_layout_table", None)
         if cached is None or cached[0] != sig:
