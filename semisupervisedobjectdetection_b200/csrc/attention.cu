@@ -816,13 +816,26 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
   const long long U = (long long)p.batches * p.heads * kv_blocks * p.q_tiles;
   const long long u_begin = U * blockIdx.x / gridDim.x, u_end = U * (blockIdx.x + 1) / gridDim.x;
   const int ntiles = (int)(u_end - u_begin);
+  // (U < 2^31, checked on the host: 32-bit divisions, and only for a CTA's FIRST unit - the walk to the next unit is an
+  // increment with carries; six long-long divisions per unit in every thread were ~0.4 us on each tile's critical path)
   auto decode = [&](long long u, int& qt, int& kvb, int& hd, int& bt) {
-    qt = (int)(u % p.q_tiles);
-    long long t = u / p.q_tiles;
-    kvb = (int)(t % kv_blocks);
-    t /= kv_blocks;
-    hd = (int)(t % p.heads);
-    bt = (int)(t / p.heads);
+    const unsigned uu = (unsigned)u;
+    qt = (int)(uu % (unsigned)p.q_tiles);
+    unsigned t = uu / (unsigned)p.q_tiles;
+    kvb = (int)(t % (unsigned)kv_blocks);
+    t /= (unsigned)kv_blocks;
+    hd = (int)(t % (unsigned)p.heads);
+    bt = (int)(t / (unsigned)p.heads);
+  };
+  auto next_unit = [&](int qt, int kvb, int hd, int bt, int& nqt, int& nkvb, int& nhd, int& nbt) {
+    nqt = qt + 1; nkvb = kvb; nhd = hd; nbt = bt;
+    if (nqt == p.q_tiles) {
+      nqt = 0;
+      if (++nkvb == kv_blocks) {
+        nkvb = 0;
+        if (++nhd == p.heads) { nhd = 0; ++nbt; }
+      }
+    }
   };
 
   if (threadIdx.x == 256) {
@@ -870,7 +883,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
         // coordinates of the next unit; does it start a new segment?
         int nqt = 0, nkvb = kvb, nhead = head, nbatch = batch;
         const bool has_next = i + 1 < ntiles;
-        if (has_next) decode(u_begin + i + 1, nqt, nkvb, nhead, nbatch);
+        if (has_next) next_unit(qt, kvb, head, batch, nqt, nkvb, nhead, nbatch);
         const bool seg_last = !has_next || nkvb != kvb || nhead != head || nbatch != batch;
         // prefetch the next tile into the other buffer once the MMAs that read it (tile i-1) have retired
         if (has_next) {
@@ -949,7 +962,7 @@ attn_bwd_persist_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid
       const uint32_t ph = i & 1;
       int nqt = 0, nkvb = kvb, nhead = head, nbatch = batch;
       const bool has_next = i + 1 < ntiles;
-      if (has_next) decode(u_begin + i + 1, nqt, nkvb, nhead, nbatch);
+      if (has_next) next_unit(qt, kvb, head, batch, nqt, nkvb, nhead, nbatch);
       const bool seg_last = !has_next || nkvb != kvb || nhead != head || nbatch != batch;
       const int kv0 = kvb * ATT_BN;
       const bool kv_ok = (kv0 + r) < p.Tk;
@@ -1113,6 +1126,7 @@ static int attn_bwd_launch(const AttentionBwdDesc& a, cudaStream_t stream) {
     attr_set = true;
   }
   p.batches = a.B;
+  SFK_REQUIRE((long long)a.B * a.heads * kv_blocks * p.q_tiles < (1LL << 31), "attention_bwd: too many work units");
   if (g_attn_bwd_persist) {
     static bool attr2 = false;
     if (!attr2) {
