@@ -483,28 +483,47 @@ int im2col_nhwc(const void* x, void* A, int B, int H, int W, int C, int K, int S
 // Stage-1 gather from the fp32 NCHW image: A[m, c*K*K + ky*K + kx] (OIHW-flatten order), K padded to Kp with zeros.
 // One block per output row (b, oy); a thread produces 8 consecutive k of one output pixel (one 16-byte store) with 32-bit
 // index arithmetic.  (The first version wrote one bf16 per thread behind two 64-bit divisions: 330 us for 80 MB.)
+static constexpr int IM2COL_MAX_KP = 1024;   // padded patch length the table kernel supports (stage 1: 3 * 7 * 7 -> 152)
 __global__ void __launch_bounds__(256) im2col_nchw_f32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ A, int B,
                                                               int Cin, int H, int W, int K, int S, int P, int Ho, int Wo,
                                                               int Kp) {
   pdl_sync();
+  // per-column table (tap offset inside the sample, ky, kx), built once per block: decoding k -> (c, ky, kx) with two runtime
+  // divisions for every one of the 40 M elements made this pass instruction bound (141 us for 130 MB)
+  __shared__ int t_off[IM2COL_MAX_KP];
+  __shared__ int t_yx[IM2COL_MAX_KP];
   const int oy = blockIdx.x % Ho;
   const int b = blockIdx.x / Ho;
   const int KK = K * K, Kreal = Cin * KK, nch = Kp >> 3;
+  for (int k = threadIdx.x; k < Kp; k += 256) {
+    int off = 0, yx = -1;
+    if (k < Kreal) {
+      const int c = k / KK, r = k - c * KK;
+      const int ky = r / K, kx = r - ky * K;
+      off = (c * H + ky) * W + kx;
+      yx = (ky << 16) | kx;
+    }
+    t_off[k] = off;
+    t_yx[k] = yx;
+  }
+  __syncthreads();
   const int n = Wo * nch;
   const float* xb = x + (size_t)b * Cin * H * W;
   __nv_bfloat16* arow = A + ((size_t)b * Ho + oy) * Wo * Kp;
+  const int y0 = oy * S - P;
   for (int i = threadIdx.x; i < n; i += 256) {
     const int ox = i / nch, ch = i - ox * nch;
+    const int x0 = ox * S - P;
+    const float* xp = xb + y0 * W + x0;   // (formed as an offset: only dereferenced for in-range taps)
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = ch * 8 + j;
+      const int yx = t_yx[k];
       v[j] = 0.f;
-      if (k < Kreal) {
-        const int c = k / KK, r = k - c * KK;
-        const int ky = r / K, kx = r - ky * K;
-        const int sy = oy * S + ky - P, sx = ox * S + kx - P;
-        if (sy >= 0 && sy < H && sx >= 0 && sx < W) v[j] = __ldg(xb + ((size_t)c * H + sy) * W + sx);
+      if (yx >= 0) {
+        const int sy = y0 + (yx >> 16), sx = x0 + (yx & 0xffff);
+        if (sy >= 0 && sy < H && sx >= 0 && sx < W) v[j] = __ldg(xp + t_off[k]);
       }
     }
     uint4 o;
@@ -518,6 +537,7 @@ int im2col_nchw_f32(const float* x, void* A, int B, int Cin, int H, int W, int K
                     cudaStream_t stream) {
   const int Ho = (H + 2 * P - K) / S + 1, Wo = (W + 2 * P - K) / S + 1;
   SFK_REQUIRE(Kp % 8 == 0 && Kp >= Cin * K * K, "im2col_nchw_f32: padded K=%d must be a multiple of 8 and >= Cin*K*K", Kp);
+  SFK_REQUIRE(Kp <= IM2COL_MAX_KP && K < 65536 && (long long)Cin * H * W < (1LL << 31), "im2col_nchw_f32: patch of %d values too long", Kp);
   if ((long long)B * Ho * Wo == 0) return 0;
   launch_k(im2col_nchw_f32_kernel, dim3((unsigned)(B * Ho)), dim3(256), 0, stream, x, (__nv_bfloat16*)A, B, Cin, H, W, K, S, P, Ho, Wo,
            Kp);
