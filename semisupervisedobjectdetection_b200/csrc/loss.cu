@@ -40,14 +40,17 @@ __device__ __forceinline__ void block_reduce(float (&v)[NV], float* sh /* [NV][8
 // ------------------------------------------------------------------------------------------------
 // y[p, Y, X] = act(bilinear(x[p, :, :]))      planes p = B*C (NCHW, fp32)
 // ------------------------------------------------------------------------------------------------
+// IDX = unsigned when the tensor has fewer than 2^31 elements (every case of this path): the flat-index decode is then three
+// 32-bit divisions instead of three long-long ones per element
+template <typename IDX>
 __global__ void __launch_bounds__(256) upsample_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, long long planes,
                                                             int h, int w, int H, int W, int act) {
   pdl_sync();
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= planes * H * W) return;
-  const int X = (int)(idx % W);
-  const int Y = (int)((idx / W) % H);
-  const long long p = idx / ((long long)W * H);
+  const IDX idx = (IDX)blockIdx.x * 256 + threadIdx.x;
+  if ((long long)idx >= planes * H * W) return;
+  const int X = (int)(idx % (IDX)W);
+  const int Y = (int)((idx / (IDX)W) % (IDX)H);
+  const long long p = (long long)(idx / ((IDX)W * (IDX)H));
   int y0, y1, x0, x1;
   float ly, lx;
   bil_src(Y, (float)h / (float)H, h, y0, y1, ly);
@@ -62,20 +65,24 @@ __global__ void __launch_bounds__(256) upsample_nchw_kernel(const float* __restr
 int upsample_nchw_fwd(const float* x, float* y, long long planes, int h, int w, int H, int W, int act, cudaStream_t stream) {
   const long long total = planes * H * W;
   if (total == 0) return 0;
-  launch_k(upsample_nchw_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, x, y, planes, h, w, H, W, act);
+  if (total < (1LL << 31))
+    launch_k(upsample_nchw_kernel<unsigned>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, x, y, planes, h, w, H, W, act);
+  else
+    launch_k(upsample_nchw_kernel<long long>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, x, y, planes, h, w, H, W, act);
   return check_launch("upsample_nchw_kernel");
 }
 
 // dx[p, yi, xi] = sum_{Y,X} w(Y,X -> yi,xi) * dy[p,Y,X] * (act ? y(1-y) : 1)
+template <typename IDX>
 __global__ void __launch_bounds__(256) upsample_nchw_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ yact,
                                                                 float* __restrict__ dx, long long planes, int h, int w, int H,
                                                                 int W, int accumulate) {
   pdl_sync();
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= planes * h * w) return;
-  const int xi = (int)(idx % w);
-  const int yi = (int)((idx / w) % h);
-  const long long p = idx / ((long long)w * h);
+  const IDX idx = (IDX)blockIdx.x * 256 + threadIdx.x;
+  if ((long long)idx >= planes * h * w) return;
+  const int xi = (int)(idx % (IDX)w);
+  const int yi = (int)((idx / (IDX)w) % (IDX)h);
+  const long long p = (long long)(idx / ((IDX)w * (IDX)h));
   const float sy = (float)h / (float)H, sx = (float)w / (float)W;
   const float fy = (float)H / (float)h, fx = (float)W / (float)w;
   int ylo = (int)floorf((yi - 1 + 0.5f) * fy - 0.5f) - 1, yhi = (int)ceilf((yi + 1 + 0.5f) * fy - 0.5f) + 1;
@@ -112,7 +119,10 @@ int upsample_nchw_bwd(const float* dy, const float* yact, float* dx, long long p
                       int accumulate, cudaStream_t stream) {
   const long long total = planes * h * w;
   if (total == 0) return 0;
-  launch_k(upsample_nchw_bwd_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, dy, yact, dx, planes, h, w, H, W, accumulate);
+  if (total < (1LL << 31) && planes * H * W < (1LL << 31))
+    launch_k(upsample_nchw_bwd_kernel<unsigned>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, dy, yact, dx, planes, h, w, H, W, accumulate);
+  else
+    launch_k(upsample_nchw_bwd_kernel<long long>, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, dy, yact, dx, planes, h, w, H, W, accumulate);
   return check_launch("upsample_nchw_bwd_kernel");
 }
 
